@@ -1,0 +1,404 @@
+"""oracle/gfs_oracle.py -- TEST INFRASTRUCTURE ONLY.
+
+CPU restatement (functional PyTorch / numpy, state-dict driven) of the reference's hot
+path.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+reference legs may import this module; the product (gfs-3dseg_gws_b200/) never does.
+
+Parity status: the reference ships no tests or golden vectors, so this
+restatement is pinned against OUTPUTS OF THE REFERENCE ITSELF, generated in the build
+container by tests/golden/make_golden.py (which imports /root/reference unmodified) and
+committed under tests/golden/.  tests/test_oracle_golden.py re-checks that pin on CPU.
+
+Every function cites the reference lines it restates (paths relative to the reference
+repository root).  Functions take a plain ``dict[str, Tensor]`` using the reference's
+state-dict key names, so they double as a check of the state-dict contract.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+SD = Dict[str, torch.Tensor]
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CLIB = None
+
+
+# ----------------------------------------------------------------------------------------
+# C part (pinned evaluation order; see gfs_oracle.c)
+# ----------------------------------------------------------------------------------------
+def build_c(force: bool = False) -> str:
+    """gcc the C restatement into oracle/_build/libgfs_oracle.so (git-ignored)."""
+    out_dir = os.path.join(_HERE, "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libgfs_oracle.so")
+    src = os.path.join(_HERE, "gfs_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        cmd = ["gcc", "-O2", "-fPIC", "-shared", "-fopenmp", "-mfma", "-ffp-contract=off",
+               "-o", so, src, "-lm"]
+        subprocess.check_call(cmd)
+    return so
+
+
+def _clib():
+    global _CLIB
+    if _CLIB is None:
+        lib = ctypes.CDLL(build_c())
+        lib.gfs_oracle_knn.restype = ctypes.c_int
+        lib.gfs_oracle_kmeans_assign.restype = ctypes.c_int
+        lib.gfs_oracle_kmeans_accumulate.restype = ctypes.c_int
+        _CLIB = lib
+    return _CLIB
+
+
+def knn_exact(x: torch.Tensor, k: int, return_dist: bool = False):
+    """model/dgcnn.py:17-23 with the pinned fma order; ties -> ascending index.
+
+    x: (B, C, N) fp32 CPU.  Returns idx (B, N, k) int32 sorted nearest-first."""
+    x = x.detach().to(torch.float32).contiguous().cpu()
+    B, C, N = x.shape
+    idx = np.empty((B, N, k), dtype=np.int32)
+    dist = np.empty((B, N, k), dtype=np.float32)
+    rc = _clib().gfs_oracle_knn(
+        ctypes.c_void_p(x.data_ptr()), B, C, N, k,
+        idx.ctypes.data_as(ctypes.c_void_p), dist.ctypes.data_as(ctypes.c_void_p))
+    if rc != 0:
+        raise ValueError("gfs_oracle_knn: bad arguments")
+    if return_dist:
+        return torch.from_numpy(idx), torch.from_numpy(dist)
+    return torch.from_numpy(idx)
+
+
+def kmeans_assign_exact(X: np.ndarray, centers: np.ndarray, return_score: bool = False):
+    """E-step of sklearn's Lloyd iteration (_k_means_lloyd.pyx:196-218) in the pinned order."""
+    X = np.ascontiguousarray(X, dtype=np.float32)
+    centers = np.ascontiguousarray(centers, dtype=np.float32)
+    n, D = X.shape
+    K = centers.shape[0]
+    labels = np.empty(n, dtype=np.int32)
+    best = np.empty(n, dtype=np.float32)
+    rc = _clib().gfs_oracle_kmeans_assign(
+        X.ctypes.data_as(ctypes.c_void_p), ctypes.c_long(n), D,
+        centers.ctypes.data_as(ctypes.c_void_p), K,
+        labels.ctypes.data_as(ctypes.c_void_p), best.ctypes.data_as(ctypes.c_void_p))
+    assert rc == 0
+    return (labels, best) if return_score else labels
+
+
+def kmeans_accumulate_exact(X: np.ndarray, labels: np.ndarray, K: int):
+    """M-step sums/counts (fp64 sums, ascending point order)."""
+    X = np.ascontiguousarray(X, dtype=np.float32)
+    labels = np.ascontiguousarray(labels, dtype=np.int32)
+    n, D = X.shape
+    sums = np.zeros((K, D), dtype=np.float64)
+    counts = np.zeros(K, dtype=np.int64)
+    rc = _clib().gfs_oracle_kmeans_accumulate(
+        X.ctypes.data_as(ctypes.c_void_p), ctypes.c_long(n), D,
+        labels.ctypes.data_as(ctypes.c_void_p), K,
+        sums.ctypes.data_as(ctypes.c_void_p), counts.ctypes.data_as(ctypes.c_void_p))
+    assert rc == 0
+    return sums, counts
+
+
+# ----------------------------------------------------------------------------------------
+# DGCNN backbone  (model/dgcnn.py)
+# ----------------------------------------------------------------------------------------
+def knn_formula(x: torch.Tensor, k: int) -> torch.Tensor:
+    """model/dgcnn.py:17-23 -- the reference formula with library matmul/topk (tie order and
+    summation order are the library's; use knn_exact for the pinned version)."""
+    gram = torch.bmm(x.transpose(1, 2), x)                 # (B,N,N)
+    sq = x.pow(2).sum(dim=1, keepdim=True)                 # (B,1,N)
+    neg_d = -sq - (-2.0 * gram) - sq.transpose(1, 2)
+    return neg_d.topk(k, dim=-1).indices
+
+
+def edge_feature(x: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """model/dgcnn.py:26-42 -- (B,C,N),(B,N,k) -> (B,2C,N,k) = cat(x_j - x_i, x_i)."""
+    B, C, N = x.shape
+    k = idx.shape[-1]
+    flat = idx.reshape(B, 1, N * k).expand(B, C, N * k).long()
+    nbr = x.gather(2, flat).reshape(B, C, N, k)
+    ctr = x.unsqueeze(-1).expand(B, C, N, k)
+    return torch.cat([nbr - ctr, ctr], dim=1)
+
+
+def _bn(sd: SD, prefix: str, x: torch.Tensor, training: bool = False) -> torch.Tensor:
+    """nn.BatchNorm{1,2}d, eps 1e-5, momentum 0.1 (model/dgcnn.py:54-55,73-74)."""
+    return F.batch_norm(x, sd[prefix + ".running_mean"].clone(), sd[prefix + ".running_var"].clone(),
+                        sd[prefix + ".weight"], sd[prefix + ".bias"], training, 0.1, 1e-5)
+
+
+def conv_stack(sd: SD, prefix: str, x: torch.Tensor, n_layers: int, training: bool = False) -> torch.Tensor:
+    """model/dgcnn.py:45-80 -- (Conv{1,2}d 1x1 no-bias, BN, LeakyReLU(0.2)) x n_layers."""
+    conv = F.conv2d if x.dim() == 4 else F.conv1d
+    for i in range(n_layers):
+        x = conv(x, sd[f"{prefix}.layer.{3 * i}.weight"])
+        x = _bn(sd, f"{prefix}.layer.{3 * i + 1}", x, training)
+        x = F.leaky_relu(x, 0.2)
+    return x
+
+
+def _count_layers(sd: SD, prefix: str) -> int:
+    n = 0
+    while f"{prefix}.layer.{3 * n}.weight" in sd:
+        n += 1
+    return n
+
+
+def dgcnn_forward(sd: SD, x: torch.Tensor, k: int = 20, prefix: str = "",
+                  idx_list: Optional[Sequence[torch.Tensor]] = None, knn: str = "formula",
+                  training: bool = False) -> Tuple[List[torch.Tensor], torch.Tensor, List[torch.Tensor]]:
+    """model/dgcnn.py:113-127.  Returns (edgeconv_outputs, mlp_out, idx_used).
+
+    idx_list pins the neighbour sets (used to decouple feature parity from kNN near-ties)."""
+    n_ec = 0
+    while f"{prefix}edge_convs.{n_ec}.layer.0.weight" in sd:
+        n_ec += 1
+    outs, used = [], []
+    for i in range(n_ec):
+        if idx_list is not None:
+            idx = idx_list[i].long()
+        elif knn == "exact":
+            idx = knn_exact(x, k).long()
+        else:
+            idx = knn_formula(x, k)
+        used.append(idx)
+        p = f"{prefix}edge_convs.{i}"
+        e = conv_stack(sd, p, edge_feature(x, idx), _count_layers(sd, p), training)
+        x = e.max(dim=-1).values
+        outs.append(x)
+    p = f"{prefix}conv"
+    out = conv_stack(sd, p, torch.cat(outs, dim=1), _count_layers(sd, p), training)
+    return outs, out, used
+
+
+# ----------------------------------------------------------------------------------------
+# adjacent blocks: SelfAttention (model/attention.py:32-48), BaseLearner (model/capl.py:435-457)
+# ----------------------------------------------------------------------------------------
+def self_attention(sd: SD, prefix: str, x: torch.Tensor) -> torch.Tensor:
+    """eval mode (dropout off).  (B,256,N) -> (B,64,N)."""
+    q = F.conv1d(x, sd[prefix + ".q_map.weight"])
+    kk = F.conv1d(x, sd[prefix + ".k_map.weight"])
+    v = F.conv1d(x, sd[prefix + ".v_map.weight"])
+    temp = float(q.shape[1]) ** 0.5
+    attn = torch.softmax(torch.matmul(q.transpose(1, 2) / temp, kk), dim=-1)
+    return torch.matmul(attn, v.transpose(1, 2)).transpose(1, 2)
+
+
+def base_learner(sd: SD, prefix: str, x: torch.Tensor, training: bool = False) -> torch.Tensor:
+    i = 0
+    n = 0
+    while f"{prefix}.convs.{n}.0.weight" in sd:
+        n += 1
+    for i in range(n):
+        x = F.conv1d(x, sd[f"{prefix}.convs.{i}.0.weight"], sd[f"{prefix}.convs.{i}.0.bias"])
+        x = _bn(sd, f"{prefix}.convs.{i}.1", x, training)
+        if i != n - 1:
+            x = F.relu(x)
+    return x
+
+
+# ----------------------------------------------------------------------------------------
+# GW head  (model/capl.py)
+# ----------------------------------------------------------------------------------------
+def get_features(sd: SD, gp: torch.Tensor, x: torch.Tensor, k: int = 20,
+                 idx_list=None, knn: str = "formula"):
+    """model/capl.py:324-362.  Returns dict with point_feat, semantic_feat, one_hot_feat and
+    the intermediates the parity tests look at."""
+    ecs, lvl2, used = dgcnn_forward(sd, x, k, "encoder.", idx_list, knn)
+    lvl3 = base_learner(sd, "base_learner", lvl2)
+    att = self_attention(sd, "att_learner", lvl2)
+    ec = torch.cat(ecs, dim=1)
+    semantic = torch.cat([ecs[0], att, lvl3], dim=1)
+    cos = torch.matmul(F.normalize(gp, p=2, dim=1).unsqueeze(0), F.normalize(ec, p=2, dim=1))
+    cosine_feat = torch.softmax(10 * cos, dim=1)
+    assignment = cosine_feat.argmax(dim=1)
+    one_hot = F.one_hot(assignment, num_classes=gp.shape[0]).transpose(2, 1).float()
+    z = torch.cat([cosine_feat, semantic], dim=1)
+    z = F.conv1d(z, sd["fusion.0.weight"], sd["fusion.0.bias"])
+    z = F.leaky_relu(_bn(sd, "fusion.1", z), 0.2)
+    return dict(point_feat=z, semantic_feat=semantic, one_hot_feat=one_hot, edge_convs=ec,
+                feat_level2=lvl2, att_feat=att, feat_level3=lvl3, cos=cos,
+                cosine_feat=cosine_feat, assignment=assignment, idx=used)
+
+
+def get_pred(x: torch.Tensor, proto: torch.Tensor, bg_proto: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """model/capl.py:290-322 -- 10 * cos(proto, x) ; proto (cls,c) or (b,cls,c); optional bg row first."""
+    if proto.dim() == 3:
+        if bg_proto is not None:
+            proto = torch.cat([bg_proto.unsqueeze(0).expand(proto.shape[0], -1, -1), proto], dim=1)
+        pn = F.normalize(proto, p=2, dim=-1)
+    else:
+        if bg_proto is not None:
+            proto = torch.cat([bg_proto, proto], dim=0)
+        pn = F.normalize(proto, p=2, dim=1).unsqueeze(0)
+    return torch.matmul(pn, F.normalize(x, p=2, dim=1)) * 10
+
+
+def post_refine_proto_v2(proto: torch.Tensor, point_feat: torch.Tensor,
+                         bg_proto: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """model/capl.py:245-287 -- query-adaptive prototype refinement -> (b, classes, c)."""
+    pred = torch.softmax(get_pred(point_feat, proto, bg_proto), dim=2)
+    pp = torch.matmul(pred, point_feat.transpose(1, 2))
+    if bg_proto is not None:
+        pp = pp[:, 1:, :]
+    w = (F.normalize(pp, p=2, dim=-1) * F.normalize(proto, p=2, dim=-1).unsqueeze(0)).sum(-1, keepdim=True)
+    w = w * (w > 0).float()
+    return w * pp + (1 - w) * proto.unsqueeze(0)
+
+
+def get_gp_weight(gp_coding: torch.Tensor, one_hot: torch.Tensor, th: float) -> torch.Tensor:
+    """model/capl.py:92-142 (eval use: use_bg_weight=False) -- weight th where coding@one_hot == 1."""
+    score = torch.matmul(gp_coding.unsqueeze(0).expand(one_hot.shape[0], -1, -1), one_hot)
+    w = torch.ones_like(score)
+    w[score == 1] = th
+    return w
+
+
+def gp_accuracies(gp_coding, one_hot, gt_label, base_num):
+    """model/capl.py:104-114 diagnostic accuracies of the eval branch."""
+    score = torch.matmul(gp_coding.unsqueeze(0).expand(one_hot.shape[0], -1, -1), one_hot)
+    gt = F.one_hot(gt_label, num_classes=score.shape[1]).transpose(2, 1)
+    per_point = (gt * score).sum(dim=1)
+    acc = per_point.mean()
+    novel = gt_label > base_num - 1
+    novel_acc = per_point[novel].mean() if novel.sum() > 0 else torch.zeros_like(acc)
+    return acc, novel_acc
+
+
+def forward_eval(sd: SD, gp: torch.Tensor, x: torch.Tensor, gened_proto: torch.Tensor,
+                 base_class_coding: torch.Tensor, novel_class_coding: torch.Tensor,
+                 base_num: int, eval_weight: float, k: int = 20, idx_list=None, knn: str = "formula"):
+    """model/capl.py:167-192 (eval_model=True branch).  Returns (logits (b,cls,n), features dict)."""
+    f = get_features(sd, gp, x, k, idx_list, knn)
+    pf = f["point_feat"]
+    if gened_proto.dim() == 3:
+        gened_proto = gened_proto[0]
+    rp = post_refine_proto_v2(sd["main_proto"], pf)
+    rp = rp.clone()
+    rp[:, :base_num] = rp[:, :base_num] + gened_proto[:base_num].unsqueeze(0)
+    rp[:, base_num:] = rp[:, base_num:] * 0 + gened_proto[base_num:].unsqueeze(0)
+    logits = get_pred(pf, rp)
+    coding = torch.cat([base_class_coding, novel_class_coding], dim=0)
+    logits = logits * get_gp_weight(coding, f["one_hot_feat"], eval_weight)
+    f["refine_proto"] = rp
+    return logits, f
+
+
+# ----------------------------------------------------------------------------------------
+# GW basis builder  (get_basis.py)
+# ----------------------------------------------------------------------------------------
+def kmean_to_proto(feat: np.ndarray, labels: np.ndarray, num_cnt: int) -> np.ndarray:
+    """get_basis.py:27-44 -- per-cluster mean (asserts non-empty)."""
+    rows = []
+    for c in range(num_cnt):
+        m = labels == c
+        assert m.sum() != 0, f"empty cluster {c}"
+        rows.append(feat[m].mean(axis=0))
+    return np.stack(rows, axis=0)
+
+
+def svd_reconstruct(protos: np.ndarray, energy: float = 0.95) -> np.ndarray:
+    """get_basis.py:50-71 -- rank-r reconstruction, r = first rank whose singular-value mass > 95 %."""
+    u, s, vh = np.linalg.svd(protos.T, full_matrices=False)
+    r = len(s) - 1
+    for i in range(len(s)):
+        if s[: i + 1].sum() > energy * s.sum():
+            r = i
+            break
+    rec = u[:, : r + 1] @ np.diag(s[: r + 1]) @ vh[: r + 1, :]
+    return rec.T
+
+
+def lloyd_reference(X: np.ndarray, init: np.ndarray, max_iter: int = 300, tol: float = 1e-4):
+    """sklearn 1.9.0 KMeans(init=<array>, n_init=1).fit as get_basis.py:210 drives it, restated with the
+    pinned E-step: mean-centring (_kmeans.py:1487-1490), tol scaling (_kmeans.py:289-296), Lloyd loop and
+    convergence (_kmeans.py:630-759).  Empty clusters raise (the caller asserts non-empty,
+    get_basis.py:37).  Returns (labels int32, centers fp32 (un-centred), n_iter)."""
+    X = np.ascontiguousarray(X, dtype=np.float32)
+    mean = X.mean(axis=0)
+    Xc = X - mean
+    centers = np.ascontiguousarray(init, dtype=np.float32) - mean
+    K = centers.shape[0]
+    tol_abs = float(np.mean(np.var(Xc, axis=0)) * tol)
+    labels_old = np.full(X.shape[0], -1, dtype=np.int32)
+    strict = False
+    it = 0
+    for it in range(1, max_iter + 1):
+        labels = kmeans_assign_exact(Xc, centers)
+        sums, counts = kmeans_accumulate_exact(Xc, labels, K)
+        empty = np.where(counts == 0)[0]
+        if len(empty):
+            # sklearn _k_means_common.pyx:167-211: move each empty centre onto one of the points
+            # farthest from its own (old) centre, taking that point out of its old cluster's sum.
+            dist = ((Xc - centers[labels]) ** 2).sum(axis=1)
+            if dist.max() > 0:
+                far = np.argpartition(dist, -len(empty))[: -len(empty) - 1: -1]
+                for e, fi in zip(empty, far):
+                    old = labels[fi]
+                    sums[old] -= Xc[fi]
+                    sums[e] = Xc[fi]
+                    counts[e] = 1
+                    counts[old] -= 1
+        new = np.empty_like(centers)
+        big = int(np.argmax(counts))
+        for c in range(K):  # _k_means_common.pyx:236-260 (_average_centers)
+            new[c] = (sums[c] / counts[c]).astype(np.float32) if counts[c] > 0 else 0
+        for c in range(K):
+            if counts[c] <= 0:
+                new[c] = new[big]
+        shift = float(((new - centers).astype(np.float64) ** 2).sum())
+        centers = new
+        if np.array_equal(labels, labels_old):
+            strict = True
+            break
+        if shift <= tol_abs:
+            break
+        labels_old = labels
+    if not strict:
+        labels = kmeans_assign_exact(Xc, centers)
+    return labels, centers + mean, it
+
+
+# ----------------------------------------------------------------------------------------
+# synthetic inputs -- shared by tests, smoke and bench
+# ----------------------------------------------------------------------------------------
+def synthetic_blocks(B: int, N: int, seed: int = 1234, dup_frac: float = 0.0) -> torch.Tensor:
+    """(B, 9, N) fp32 S3DIS-shaped blocks as dataloaders/loader.py:87-101 emits them:
+    ch0-2 xyz (x,y in [0,1], z in [0,3]), ch3-5 rgb in [0,1], ch6-8 XYZ normalised per block.
+    dup_frac > 0 makes that fraction of points exact copies (sampling with replacement, loader.py:66)."""
+    out = torch.empty(B, 9, N, dtype=torch.float32)
+    for b in range(B):
+        g = torch.Generator().manual_seed(seed + b)
+        xyz = torch.rand(3, N, generator=g) * torch.tensor([[1.0], [1.0], [3.0]])
+        rgb = torch.rand(3, N, generator=g)
+        if dup_frac > 0:
+            nd = int(N * dup_frac)
+            src = torch.randint(0, N, (nd,), generator=g)
+            dst = torch.randperm(N, generator=g)[:nd]
+            xyz[:, dst] = xyz[:, src]
+            rgb[:, dst] = rgb[:, src]
+        xyz = xyz - xyz.min(dim=1, keepdim=True).values
+        out[b, 0:3] = xyz
+        out[b, 3:6] = rgb
+        out[b, 6:9] = xyz / xyz.max(dim=1, keepdim=True).values.clamp_min(1e-12)
+    return out
+
+
+def randomize_bn_(sd: SD, seed: int = 5) -> SD:
+    """Make BN folding non-trivial: gamma~N(1,.3) beta~N(0,.2) mean~N(0,.2) var~U[.5,2]."""
+    g = torch.Generator().manual_seed(seed)
+    for key in sorted(sd.keys()):
+        if key.endswith("running_mean"):
+            p = key[: -len("running_mean")]
+            n = sd[key].numel()
+            sd[p + "weight"] = 1.0 + 0.3 * torch.randn(n, generator=g)
+            sd[p + "bias"] = 0.2 * torch.randn(n, generator=g)
+            sd[p + "running_mean"] = 0.2 * torch.randn(n, generator=g)
+            sd[p + "running_var"] = 0.5 + 1.5 * torch.rand(n, generator=g)
+    return sd

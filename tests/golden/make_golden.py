@@ -1,0 +1,154 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (PYTHONPATH=/root/reference)
+on CPU in the build container, and check that oracle/gfs_oracle.py reproduces it.
+
+    python tests/golden/make_golden.py            # writes fixtures + prints oracle-vs-reference deltas
+
+/root/reference does not exist on the GPU box; only the committed .npz files travel.
+The reference ships no golden vectors of its own: these files ARE the pin.
+"""
+import argparse
+import os
+import sys
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("GFS_REFERENCE", "/root/reference")
+sys.path.insert(0, REF)
+sys.path.insert(0, ROOT)
+
+from model.capl import mpti_net_Point_GeoAsWeight_v2  # noqa: E402  (reference)
+from model.dgcnn import DGCNN, knn as ref_knn  # noqa: E402  (reference)
+from oracle import gfs_oracle as O  # noqa: E402
+
+torch.set_num_threads(8)
+
+
+def ref_args(k=20, eval_weight=1.2):
+    return SimpleNamespace(edgeconv_widths=[[64, 64]] * 3, dgcnn_mlp_widths=[512, 256], pc_in_dim=9,
+                           dgcnn_k=k, base_widths=[128, 64], output_dim=64, eval_weight=eval_weight)
+
+
+def np_sd(sd):
+    return {k: v.detach().cpu().numpy() for k, v in sd.items()}
+
+
+def save(name, **arrs):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez(path, **arrs)
+    print(f"  wrote {name}.npz  {os.path.getsize(path) / 1e6:.2f} MB")
+
+
+def maxdiff(a, b):
+    return float((a - b).abs().max())
+
+
+def make_dgcnn(name, B, N, k, seed, dup=0.0, subsample=1):
+    torch.manual_seed(321)
+    m = DGCNN([[64, 64]] * 3, [512, 256], 9, k=k, return_edgeconvs=True).eval()
+    sd = O.randomize_bn_({k_: v.clone() for k_, v in m.state_dict().items()}, seed=5)
+    m.load_state_dict(sd)
+    x = O.synthetic_blocks(B, N, seed=seed, dup_frac=dup)
+    with torch.no_grad():
+        ecs, out = m(x)
+        # reference neighbour indices per layer (inputs: x, ecs[0], ecs[1])
+        idx = [ref_knn(t, k) for t in (x, ecs[0], ecs[1])]
+        o_ecs, o_out, _ = O.dgcnn_forward(sd, x, k, "", knn="formula")
+    d = max(maxdiff(torch.cat(ecs, 1), torch.cat(o_ecs, 1)), maxdiff(out, o_out))
+    print(f"{name}: oracle(formula) vs reference max|diff| = {d:.3e}")
+    assert d == 0.0, "oracle restatement is not bit-identical to the reference on CPU"
+    s = slice(None, None, subsample)
+    save(name, x=x.numpy(), k=np.int32(k), subsample=np.int32(subsample),
+         ec=torch.cat(ecs, 1)[:, :, s].numpy(), out=out[:, :, s].numpy(),
+         idx0=idx[0].numpy().astype(np.int16), idx1=idx[1].numpy().astype(np.int16),
+         idx2=idx[2].numpy().astype(np.int16))
+    return sd
+
+
+def make_gfs(name, B, N, classes, base_num, G, seed, wname):
+    torch.manual_seed(321)
+    args = ref_args()
+    gp = torch.randn(G, 192, generator=torch.Generator().manual_seed(7))
+    m = mpti_net_Point_GeoAsWeight_v2(classes=classes, criterion=torch.nn.CrossEntropyLoss(ignore_index=255),
+                                      args=args, base_num=base_num, gp=gp.clone(), energy=0.9).eval()
+    sd = O.randomize_bn_({k_: v.clone() for k_, v in m.state_dict().items()}, seed=6)
+    m.load_state_dict(sd)
+    x = O.synthetic_blocks(B, N, seed=seed)
+    g = torch.Generator().manual_seed(11)
+    y = torch.randint(0, classes, (B, N), generator=g)
+    gened = torch.nn.functional.normalize(torch.randn(classes, 128, generator=g), dim=1)
+    coding = (torch.rand(classes, G, generator=g) < 0.3).float()
+    base_c, novel_c = coding[:base_num], coding[base_num:]
+    with torch.no_grad():
+        pf, sem, oh = m.getFeatures(x)
+        logits, gp_acc, gp_nacc = m(x=x, y=y, eval_model=True, gened_proto=gened.unsqueeze(0).repeat(8, 1, 1),
+                                    base_class_coding=base_c, novel_class_coding=novel_c)
+        fg_feat, fg_gp = m.Get_Fg_Feat(x[:1], (y[:1] == 1).long())
+        o_logits, f = O.forward_eval(sd, gp, x, gened, base_c, novel_c, base_num, args.eval_weight)
+        o_acc, o_nacc = O.gp_accuracies(coding, f["one_hot_feat"], y, base_num)
+        idx = [t.numpy().astype(np.int16) for t in f["idx"]]
+    d = max(maxdiff(pf, f["point_feat"]), maxdiff(sem, f["semantic_feat"]), maxdiff(oh, f["one_hot_feat"]),
+            maxdiff(logits, o_logits), abs(float(gp_acc) - float(o_acc)), abs(float(gp_nacc) - float(o_nacc)))
+    print(f"{name}: oracle vs reference max|diff| = {d:.3e}")
+    assert d == 0.0
+    save(wname, **np_sd(sd))
+    save(name, x=x.numpy(), y=y.numpy().astype(np.int16), gp=gp.numpy(), gened_proto=gened.numpy(),
+         base_class_coding=base_c.numpy(), novel_class_coding=novel_c.numpy(),
+         classes=np.int32(classes), base_num=np.int32(base_num), eval_weight=np.float32(args.eval_weight),
+         point_feat=pf.numpy(), semantic_feat=sem.numpy(), assignment=oh.argmax(1).numpy().astype(np.int16),
+         logits=logits.numpy(), gp_acc=np.float32(gp_acc), gp_novel_acc=np.float32(gp_nacc),
+         fg_feat=fg_feat.numpy(), fg_gp_sum=fg_gp.sum(0).numpy(),
+         idx0=idx[0], idx1=idx[1], idx2=idx[2], feat_level2=f["feat_level2"].numpy())
+
+
+def make_kmeans(name, n, D, K, seed):
+    """sklearn KMeans driven exactly as get_basis.py:210 does, with an injected init (pins the Lloyd part)."""
+    import sklearn
+    from sklearn.cluster import KMeans
+    rs = np.random.RandomState(seed)
+    cent = rs.randn(K, D).astype(np.float32)
+    lab = rs.randint(0, K, size=n)
+    X = (cent[lab] + 0.35 * rs.randn(n, D)).astype(np.float32)
+    init = X[rs.choice(n, K, replace=False)].copy()
+    km = KMeans(n_clusters=K, init=init, n_init=1).fit(X)
+    o_labels, o_centers, o_it = O.lloyd_reference(X, init)
+    agree = float((o_labels == km.labels_).mean())
+    print(f"{name}: sklearn {sklearn.__version__} n_iter={km.n_iter_} oracle n_iter={o_it} "
+          f"label agreement={agree:.6f} centers max|diff|={np.abs(o_centers - km.cluster_centers_).max():.3e}")
+    # Kmean2Proto / compute_svd straight from the reference source (exec of get_basis.py:27-71 only: the module
+    # itself cannot be imported here, it needs h5py/transforms3d -- SURVEY.md H6)
+    src = open(os.path.join(REF, "get_basis.py")).read().split("\n")
+    ns = {"np": np}
+    exec("\n".join(src[26:71]), ns)
+    proto = ns["Kmean2Proto"](X, km.labels_, K)
+    basis = ns["compute_svd"](proto)
+    o_basis = O.svd_reconstruct(O.kmean_to_proto(X, km.labels_, K))
+    print(f"{name}: svd basis oracle vs reference max|diff| = {np.abs(basis - o_basis).max():.3e}")
+    assert np.abs(basis - o_basis).max() == 0.0
+    save(name, seed=np.int32(seed), n=np.int32(n), D=np.int32(D), K=np.int32(K), init=init,
+         labels=km.labels_.astype(np.int16), centers=km.cluster_centers_.astype(np.float32),
+         n_iter=np.int32(km.n_iter_), basis=basis.astype(np.float32),
+         x_checksum=np.float64(X.astype(np.float64).sum()))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="")
+    a = ap.parse_args()
+    todo = a.only.split(",") if a.only else ["dgcnn", "gfs", "kmeans"]
+    if "dgcnn" in todo:
+        sd = make_dgcnn("dgcnn_b2_n256", 2, 256, 20, seed=1234)
+        save("dgcnn_weights", **np_sd(sd))
+        make_dgcnn("dgcnn_dup_b1_n256", 1, 256, 20, seed=77, dup=0.25)
+        make_dgcnn("dgcnn_b1_n2048", 1, 2048, 20, seed=1234, subsample=8)       # BASELINE.json configs[0]
+        make_dgcnn("dgcnn_b1_n320_k40", 1, 320, 40, seed=99)
+    if "gfs" in todo:
+        make_gfs("gfs_s3dis_b2_n256", 2, 256, 13, 7, 150, seed=4321, wname="gfs_s3dis_weights")
+        make_gfs("gfs_scannet_b2_n128", 2, 128, 21, 15, 180, seed=8765, wname="gfs_scannet_weights")
+    if "kmeans" in todo:
+        make_kmeans("kmeans_n6000_k150", 6000, 192, 150, seed=99)
+        make_kmeans("kmeans_n2000_k20", 2000, 192, 20, seed=3)
