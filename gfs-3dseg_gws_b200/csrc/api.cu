@@ -1,0 +1,51 @@
+// api.cu -- error plumbing and small utilities of the C ABI (include/gfs3d.h).
+#include <cstdarg>
+#include <cstdio>
+#include <mutex>
+#include <set>
+#include <utility>
+
+#include "common.cuh"
+
+namespace gfs {
+
+static thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+cudaError_t allow_smem(const void* func, size_t bytes) {
+    static std::mutex mu;
+    static std::set<std::pair<int, const void*>> done;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(mu);
+    if (done.count({dev, func})) return cudaSuccess;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) done.insert({dev, func});
+    return e;
+}
+
+}  // namespace gfs
+
+extern "C" int gfs_version(void) { return 100; }
+extern "C" const char* gfs_last_error_string(void) { return gfs::g_err; }
+extern "C" int gfs_device_sm_count(void) { return gfs::sm_count(); }

@@ -1,0 +1,290 @@
+// edgeconv.cu -- fused EdgeConv given the kNN graph, conv2 on tcgen05 with the accumulator in TMEM.
+//
+// Replaces model/dgcnn.py:35-41 (gather / x_j - x_i / cat -> (B,2C,N,k)), :53-58 (conv1+BN+LReLU, conv2+BN+LReLU
+// over (B,64,N,k)) and :118 (max over k).  With the first conv split per point (pointwise.cu) an edge's hidden
+// vector is h1 = LReLU(P'[j] + Q'[i]); a tile is 128 points x ONE neighbour slot, so the max over the k slots is an
+// element-wise max across k accumulator tiles held by the same thread -- no cross-lane reduction, and because BN2's
+// scale is folded into W2 the remaining "+shift, LeakyReLU" is monotone and is applied once after the max.
+//
+// Warp roles (persistent CTA, one per SM):
+//   warps 0-3  producers : gather P'[idx] (256 B contiguous per edge) + Q' (registers) -> LReLU -> bf16 -> SWIZZLE_128B
+//                          A tile in shared memory -> fence.proxy.async -> arrive full[stage]
+//   warp  8    MMA       : one thread issues 4 x tcgen05.mma (128x64x16) per A tile into TMEM stage acc;
+//                          tcgen05.commit -> empty[stage], accf[acc].  W2 (8 KB image) arrives once by TMA bulk copy.
+//   warps 4-7  epilogue  : tcgen05.ld 32x32b, running max in registers, arrive acce[acc]; after slot k-1:
+//                          +shift, LeakyReLU, store fp32 channel-major and bf16 "act" tiles.
+#include "common.cuh"
+
+namespace gfs {
+
+constexpr int EC_TM = 128;
+constexpr int EC_NST = 4;
+constexpr int EC_NACC = 4;
+constexpr int EC_THREADS = 288;
+constexpr uint32_t EC_TMEM_COLS = 256;
+
+struct EcSmem {
+    uint8_t A[EC_NST][16384];
+    uint8_t W[8192];
+    float shift[64];
+    uint64_t full[EC_NST], empty[EC_NST], accf[EC_NACC], acce[EC_NACC], wbar;
+    uint32_t tmem_base;
+};
+
+template <bool ARGMAX>
+__global__ void __launch_bounds__(EC_THREADS, 1)
+edgeconv_kernel(const float* __restrict__ pq, const int32_t* __restrict__ idx, const uint8_t* __restrict__ w2p,
+                const float* __restrict__ shift2, int N, int k, int64_t M, int ntiles, float* __restrict__ y_cm,
+                int64_t y_bstride, uint8_t* __restrict__ y_act, int act_kblocks, int act_kb, uint8_t* __restrict__ y_act2,
+                int act2_kblocks, int act2_kb, uint8_t* __restrict__ argmax) {
+    extern __shared__ unsigned char smem_raw[];
+    EcSmem& s = *reinterpret_cast<EcSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid < 64) s.shift[tid] = shift2[tid];
+    if (warp == 8) {
+        if (lane == 0) {
+            for (int i = 0; i < EC_NST; ++i) {
+                mbar_init(&s.full[i], 128);
+                mbar_init(&s.empty[i], 1);
+            }
+            for (int i = 0; i < EC_NACC; ++i) {
+                mbar_init(&s.accf[i], 1);
+                mbar_init(&s.acce[i], 128);
+            }
+            mbar_init(&s.wbar, 1);
+            mbar_fence_init();
+            mbar_arrive_expect_tx(&s.wbar, 8192);
+            tma_load_1d(s.W, w2p, 8192, &s.wbar);
+        }
+        __syncwarp();
+        tmem_alloc(&s.tmem_base, EC_TMEM_COLS);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s.tmem_base;
+
+    if (warp < 4) {
+        // =============================== producers ===============================
+        const int q = tid & 7, rsub = tid >> 3;
+        int stage = 0, phase = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int64_t m0 = (int64_t)tile * EC_TM;
+            float4 Q[8][2];
+            int64_t base[8];   // b*N of the row's block, or -1 for rows past M
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+                const int64_t m = m0 + p * 16 + rsub;
+                if (m < M) {
+                    base[p] = (m / N) * N;
+                    const float4* src = reinterpret_cast<const float4*>(pq + m * 128 + 64 + q * 8);
+                    Q[p][0] = __ldg(src);
+                    Q[p][1] = __ldg(src + 1);
+                } else {
+                    base[p] = -1;
+                    Q[p][0] = Q[p][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            for (int kk = 0; kk < k; ++kk) {
+                bool waited = false;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {   // two batches of 4 rows: 8 x LDG.128 in flight per thread
+                    float4 v[4][2];
+#pragma unroll
+                    for (int pp = 0; pp < 4; ++pp) {
+                        const int p = half * 4 + pp;
+                        if (base[p] >= 0) {
+                            const int64_t m = m0 + p * 16 + rsub;
+                            const int j = __ldg(idx + m * k + kk);
+                            const float4* src = reinterpret_cast<const float4*>(pq + (base[p] + j) * 128 + q * 8);
+                            v[pp][0] = __ldg(src);
+                            v[pp][1] = __ldg(src + 1);
+                        } else {
+                            v[pp][0] = v[pp][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
+                    if (!waited) {
+                        mbar_wait(&s.empty[stage], phase ^ 1);
+                        waited = true;
+                    }
+                    uint8_t* A = s.A[stage];
+#pragma unroll
+                    for (int pp = 0; pp < 4; ++pp) {
+                        const int p = half * 4 + pp;
+                        uint4 o;
+                        if (base[p] >= 0) {
+                            o.x = pack_bf16x2(lrelu02(v[pp][0].x + Q[p][0].x), lrelu02(v[pp][0].y + Q[p][0].y));
+                            o.y = pack_bf16x2(lrelu02(v[pp][0].z + Q[p][0].z), lrelu02(v[pp][0].w + Q[p][0].w));
+                            o.z = pack_bf16x2(lrelu02(v[pp][1].x + Q[p][1].x), lrelu02(v[pp][1].y + Q[p][1].y));
+                            o.w = pack_bf16x2(lrelu02(v[pp][1].z + Q[p][1].z), lrelu02(v[pp][1].w + Q[p][1].w));
+                        } else {
+                            o = make_uint4(0u, 0u, 0u, 0u);
+                        }
+                        *reinterpret_cast<uint4*>(A + sw128(p * 16 + rsub, q)) = o;
+                    }
+                }
+                fence_proxy_async();
+                mbar_arrive(&s.full[stage]);
+                if (++stage == EC_NST) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 8) {
+        // =============================== MMA issuer ===============================
+        if (lane == 0) {
+            mbar_wait(&s.wbar, 0);
+            const uint32_t idesc = umma_idesc_bf16(128, 64);
+            const uint64_t bdesc = umma_desc_sw128(smem_u32(s.W));
+            int stage = 0, phase = 0, acc = 0, aphase = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int kk = 0; kk < k; ++kk) {
+                    mbar_wait(&s.acce[acc], aphase ^ 1);
+                    mbar_wait(&s.full[stage], phase);
+                    tc_fence_after();
+                    const uint64_t adesc = umma_desc_sw128(smem_u32(s.A[stage]));
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)   // K = 64 = 4 x 16; +32 bytes per step inside the 128 B swizzle row
+                        umma_bf16(tmem + acc * 64, adesc + ks * 2, bdesc + ks * 2, idesc, ks > 0 ? 1u : 0u);
+                    umma_commit(&s.empty[stage]);
+                    umma_commit(&s.accf[acc]);
+                    if (++stage == EC_NST) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                    if (++acc == EC_NACC) {
+                        acc = 0;
+                        aphase ^= 1;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // =============================== epilogue ===============================
+        const int quarter = warp - 4;            // == warp % 4: the TMEM lane quarter this warp may read
+        const int row = quarter * 32 + lane;
+        const uint32_t tlane = (uint32_t)(quarter * 32) << 16;
+        int acc = 0, aphase = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            float mx[64];
+            uint32_t am[ARGMAX ? 16 : 1];
+#pragma unroll
+            for (int c = 0; c < 64; ++c) mx[c] = -INFINITY;
+            if (ARGMAX) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) am[c] = 0u;
+            }
+            for (int kk = 0; kk < k; ++kk) {
+                mbar_wait(&s.accf[acc], aphase);
+                tc_fence_after();
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem + tlane + acc * 64 + h * 32, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const float vv = __uint_as_float(r[c]);
+                        if (ARGMAX) {
+                            if (vv > mx[h * 32 + c]) {
+                                mx[h * 32 + c] = vv;
+                                const int cc = h * 32 + c;
+                                am[cc >> 2] = (am[cc >> 2] & ~(0xffu << ((cc & 3) * 8))) | ((uint32_t)kk << ((cc & 3) * 8));
+                            }
+                        } else {
+                            mx[h * 32 + c] = fmaxf(mx[h * 32 + c], vv);
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&s.acce[acc]);
+                if (++acc == EC_NACC) {
+                    acc = 0;
+                    aphase ^= 1;
+                }
+            }
+            const int64_t m = (int64_t)tile * EC_TM + row;
+            if (m < M) {
+#pragma unroll
+                for (int c = 0; c < 64; ++c) mx[c] = lrelu02(mx[c] + s.shift[c]);
+                if (y_cm) {
+                    const int64_t b = m / N, n = m - b * N;
+                    float* o = y_cm + b * y_bstride + n;
+#pragma unroll
+                    for (int c = 0; c < 64; ++c) o[(int64_t)c * N] = mx[c];
+                }
+                uint4 pk[8];
+#pragma unroll
+                for (int qq = 0; qq < 8; ++qq) {
+                    pk[qq].x = pack_bf16x2(mx[qq * 8 + 0], mx[qq * 8 + 1]);
+                    pk[qq].y = pack_bf16x2(mx[qq * 8 + 2], mx[qq * 8 + 3]);
+                    pk[qq].z = pack_bf16x2(mx[qq * 8 + 4], mx[qq * 8 + 5]);
+                    pk[qq].w = pack_bf16x2(mx[qq * 8 + 6], mx[qq * 8 + 7]);
+                }
+                if (y_act) {
+                    uint8_t* t = y_act + ((int64_t)tile * act_kblocks + act_kb) * 16384;
+#pragma unroll
+                    for (int qq = 0; qq < 8; ++qq) *reinterpret_cast<uint4*>(t + sw128(row, qq)) = pk[qq];
+                }
+                if (y_act2) {
+                    uint8_t* t = y_act2 + ((int64_t)tile * act2_kblocks + act2_kb) * 16384;
+#pragma unroll
+                    for (int qq = 0; qq < 8; ++qq) *reinterpret_cast<uint4*>(t + sw128(row, qq)) = pk[qq];
+                }
+                if (ARGMAX) {
+                    uint4* a = reinterpret_cast<uint4*>(argmax + m * 64);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) a[c] = make_uint4(am[c * 4], am[c * 4 + 1], am[c * 4 + 2], am[c * 4 + 3]);
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        tmem_dealloc(tmem, EC_TMEM_COLS);
+    }
+}
+
+}  // namespace gfs
+
+extern "C" int gfs_edgeconv_fwd(const float* pq, const int32_t* idx, const void* w2_packed, const float* shift2, int B, int N,
+                                int k, float* y_cm, int64_t y_bstride, void* y_act, int y_act_kblocks, int y_act_kb,
+                                void* y_act2, int y_act2_kblocks, int y_act2_kb, uint8_t* argmax, void* stream) {
+    using namespace gfs;
+    GFS_REQUIRE(pq && idx && w2_packed && shift2, GFS_ERR_BAD_ARG, "gfs_edgeconv_fwd: null pointer");
+    GFS_REQUIRE(B > 0 && N > 0 && k > 0, GFS_ERR_BAD_ARG, "gfs_edgeconv_fwd: non-positive size");
+    GFS_REQUIRE(k <= 255, GFS_ERR_UNSUPPORTED, "gfs_edgeconv_fwd: k=%d > 255", k);
+    GFS_REQUIRE(y_cm || y_act || y_act2, GFS_ERR_BAD_ARG, "gfs_edgeconv_fwd: no output requested");
+    GFS_REQUIRE((reinterpret_cast<uintptr_t>(pq) & 15) == 0 && (reinterpret_cast<uintptr_t>(w2_packed) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(y_act) & 15) == 0 && (reinterpret_cast<uintptr_t>(y_act2) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(argmax) & 15) == 0,
+                GFS_ERR_BAD_ARG, "gfs_edgeconv_fwd: pointers must be 16-byte aligned");
+    const int64_t M = (int64_t)B * N;
+    const int ntiles = (int)((M + EC_TM - 1) / EC_TM);
+    const int sms = sm_count();
+    GFS_REQUIRE(sms > 0, GFS_ERR_CUDA, "gfs_edgeconv_fwd: cannot query the device");
+    const int grid = ntiles < sms ? ntiles : sms;
+    const size_t smem = sizeof(EcSmem) + 1024;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (argmax) {
+        GFS_CUDA_OK(allow_smem(reinterpret_cast<const void*>(edgeconv_kernel<true>), smem));
+        edgeconv_kernel<true><<<grid, EC_THREADS, smem, st>>>(
+            pq, idx, static_cast<const uint8_t*>(w2_packed), shift2, N, k, M, ntiles, y_cm, y_bstride,
+            static_cast<uint8_t*>(y_act), y_act_kblocks, y_act_kb, static_cast<uint8_t*>(y_act2), y_act2_kblocks, y_act2_kb,
+            argmax);
+    } else {
+        GFS_CUDA_OK(allow_smem(reinterpret_cast<const void*>(edgeconv_kernel<false>), smem));
+        edgeconv_kernel<false><<<grid, EC_THREADS, smem, st>>>(
+            pq, idx, static_cast<const uint8_t*>(w2_packed), shift2, N, k, M, ntiles, y_cm, y_bstride,
+            static_cast<uint8_t*>(y_act), y_act_kblocks, y_act_kb, static_cast<uint8_t*>(y_act2), y_act2_kblocks, y_act2_kb,
+            nullptr);
+    }
+    GFS_LAUNCH_OK("edgeconv_kernel");
+    return GFS_OK;
+}

@@ -1,0 +1,56 @@
+"""ctypes binding of libgfs3d.so (the C ABI declared in include/gfs3d.h).
+
+The product path has NO fallback: if the shared library is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgfs3d.so")
+
+_i, _i64, _p, _f = ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_float
+
+# name -> argtypes; every function returns int (gfs_status) except the three utilities
+SIGNATURES = {
+    "gfs_knn_f32": [_p, _i64, _i, _i, _i, _i, _p, _p, _p, _p],
+    "gfs_pointwise_f32": [_p, _i64, _i, _i, _i, _p, _p, _i, _p, _p],
+    "gfs_edgeconv_fwd": [_p, _p, _p, _p, _i, _i, _i, _p, _i64, _p, _i, _i, _p, _i, _i, _p, _p],
+    "gfs_pack_weight_bf16": [_p, _p, _i, _i, _p, _p],
+    "gfs_cm_to_act": [_p, _i64, _i, _i, _i, _p, _i, _i, _p],
+    "gfs_linear_bf16": [_p, _i, _i, _i, _p, _p, _i, _i, _i, _i, _p, _i, _i, _p, _i64, _p],
+    "gfs_gw_project": [_p, _i64, _i, _i, _i, _p, _i, _i, _p, _i, _i, _p, _p, _p],
+    "gfs_cos_logits": [_p, _i64, _i, _i, _i, _p, _i, _i, _p, _i, _p, _f, _p, _p],
+    "gfs_softmax_pool": [_p, _p, _i64, _i, _i, _i, _i, _p, _p],
+    "gfs_kmeans_assign": [_p, _i64, _i, _p, _i, _p, _p, _p, _p],
+    "gfs_kmeans_accumulate": [_p, _i64, _i, _p, _i, _p, _p, _p, _p, _p],
+}
+UTILITIES = {"gfs_version": (_i, []), "gfs_last_error_string": (ctypes.c_char_p, []),
+             "gfs_device_sm_count": (_i, []), "gfs_kmeans_partials": (_i, [])}
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python gfs-3dseg_gws_b200/build.py` "
+                "(there is no CPU or PyTorch fallback for the hot path)")
+        l = ctypes.CDLL(LIB_PATH)
+        for name, args in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = _i
+            fn.argtypes = args
+        for name, (res, args) in UTILITIES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().gfs_last_error_string().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (gfs_status {rc}): {msg}")

@@ -1,0 +1,148 @@
+/*
+ * gfs3d.h -- C ABI of the B200-native (sm_100a) hot path of GFS-3DSeg_GWs.
+ *
+ * The reference (Pixie8888/GFS-3DSeg_GWs) is pure PyTorch and has no FFI of its own; its boundary for this path
+ * is the Python module API of model/dgcnn.py and model/capl.py plus the sklearn KMeans call in get_basis.py.
+ * Each entry point below names the reference lines whose arithmetic it replaces.  The Python drop-in modules in
+ * gfs-3dseg_gws_b200/model/ call these through ctypes (gfs-3dseg_gws_b200/gfs3d/_lib.py); INTEGRATION.md shows the
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless its name ends in _host
+ *   - the caller owns all memory (outputs and workspaces are caller-allocated); the library never allocates,
+ *     frees or retains device memory
+ *   - every call enqueues asynchronously on `stream` (a cudaStream_t passed as void*) and never synchronises
+ *   - every call returns 0 on success, or a gfs_status code; gfs_last_error_string() describes the last failure
+ *     of the calling thread.  There is no CPU fallback anywhere.
+ *   - "cm"  = channel-major fp32 activations  (B, C, N) with an explicit batch stride in elements
+ *   - "act" = bf16 activation matrix in the tiled layout described below
+ *
+ * bf16 "act" layout (memory laid out for tcgen05: a tile is bulk-copied by TMA straight into a UMMA operand)
+ *   logical matrix (M rows = points b*N+n, Kc columns), M padded to 128, Kc a multiple of 64;
+ *   stored as tiles [M/128][Kc/64], each tile 128 rows x 64 bf16 = 16 KiB in the canonical K-major SWIZZLE_128B
+ *   arrangement:  byte(r, c) = r*128 + (((c/8) ^ (r&7)) << 4) + (c%8)*2.
+ *   weights use the same arrangement with [Kc/64] tiles of R rows x 64 bf16 (see gfs_pack_weight_bf16).
+ */
+#ifndef GFS3D_H
+#define GFS3D_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    GFS_OK = 0,
+    GFS_ERR_BAD_ARG = 1,       /* null pointer / non-positive size / misaligned pointer */
+    GFS_ERR_UNSUPPORTED = 2,   /* a width / size this build does not specialise (raised, never silently emulated) */
+    GFS_ERR_CUDA = 3           /* a CUDA runtime error; the string carries cudaGetErrorString */
+} gfs_status;
+
+enum { GFS_ACT_NONE = 0, GFS_ACT_LRELU02 = 1, GFS_ACT_RELU = 2 };
+
+int gfs_version(void);
+const char* gfs_last_error_string(void);
+/* number of SMs of the current device (grid sizing of the persistent kernels); <0 on error */
+int gfs_device_sm_count(void);
+
+/* ---- kNN graph: model/dgcnn.py:17-23 (knn) -------------------------------------------------------------------
+ * d(i,j) = -|x_i|^2 + 2 x_i.x_j - |x_j|^2 in fp32 with the pinned order of oracle/gfs_oracle.c; the k largest per
+ * row, nearest first, ties -> ascending index.  The N x N matrix is never written to memory.
+ *   x        cm fp32, channel stride N, batch stride x_bstride (elements); C <= 64, N % 4 == 0
+ *   sqnorm   workspace, B*N floats (per-point |x|^2, written by the call)
+ *   idx_out  (B, N, k) int32, neighbour index inside its own block;  k <= 32, k <= N
+ *   dist_out optional (B, N, k) fp32 (may be NULL)                                                              */
+int gfs_knn_f32(const float* x, int64_t x_bstride, int B, int C, int N, int k,
+                float* sqnorm, int32_t* idx_out, float* dist_out, void* stream);
+
+/* ---- per-point fp32 1x1 conv: the split first EdgeConv conv, model/dgcnn.py:26-42 + :53 (SURVEY a3')---------
+ * out[b*N+n, o] = bias[o] + sum_c x[b,c,n] * wt[c,o]        (wt = W^T, (C, O) row-major; O % 128 == 0, C <= 64)
+ * For EdgeConv the caller passes wt = [s1*Wa | s1*(Wb-Wa)]^T and bias = [0 | t1] so that out = [P' | Q'].     */
+int gfs_pointwise_f32(const float* x, int64_t x_bstride, int B, int C, int N,
+                      const float* wt, const float* bias, int O, float* out, void* stream);
+
+/* ---- fused EdgeConv given the graph: model/dgcnn.py:35-41 (gather, x_j - x_i, cat), :56-58 (LeakyReLU of conv1,
+ * conv2, BN2 eval, LeakyReLU) and :118 (max over k).  h1 = LReLU(P'[j] + Q'[i]) is formed in shared memory as a
+ * bf16 UMMA operand, conv2 runs on tcgen05 with the accumulator in TMEM, max over k is taken on the accumulator
+ * (BN2 scale is folded into w2, so +shift and LeakyReLU commute with max) -- the (B,2C,N,k) edge tensor and the
+ * (B,64,N,k) activations never exist in memory.
+ *   pq        (B*N, 128) fp32 = [P' | Q'] from gfs_pointwise_f32
+ *   idx       (B, N, k) int32
+ *   w2_packed 64x64 bf16, K-major SWIZZLE_128B image of diag(s2) W2 (gfs_pack_weight_bf16)
+ *   shift2    64 floats (BN2 beta - mean*s2)
+ *   y_cm      fp32 cm output, y[b, c, n] at y_cm[b*y_bstride + c*N + n], c < 64          (may be NULL)
+ *   y_act     bf16 act output tile column `y_act_kb` of a matrix with y_act_kblocks 64-col blocks (may be NULL)
+ *   y_act2    second optional bf16 act destination (same arguments)
+ *   argmax    optional (B*N, 64) uint8: neighbour slot that produced the max (for the backward scatter)        */
+int gfs_edgeconv_fwd(const float* pq, const int32_t* idx, const void* w2_packed, const float* shift2,
+                     int B, int N, int k,
+                     float* y_cm, int64_t y_bstride,
+                     void* y_act, int y_act_kblocks, int y_act_kb,
+                     void* y_act2, int y_act2_kblocks, int y_act2_kb,
+                     uint8_t* argmax, void* stream);
+
+/* ---- weight packing for the tcgen05 kernels ---------------------------------------------------------------------
+ * w (R, K) fp32 row-major, optional per-row scale (R) folded in before rounding -> bf16 tiles [ceil(K/64)][R x 64]
+ * K-major SWIZZLE_128B; R % 8 == 0.  out must hold ceil(K/64)*R*128 bytes.                                        */
+int gfs_pack_weight_bf16(const float* w, const float* row_scale, int R, int K, void* out, void* stream);
+
+/* fp32 cm (B, C, N) -> bf16 act tiles (columns [kb0*64, kb0*64+C) of a matrix with kblocks blocks); C % 64 == 0 */
+int gfs_cm_to_act(const float* x, int64_t x_bstride, int B, int C, int N, void* act, int kblocks, int kb0, void* stream);
+
+/* ---- dense layer on tcgen05: Conv1d(k=1)+BN(eval)+activation, model/dgcnn.py:63-80,121-122; model/capl.py:63-65,
+ * 435-457; model/attention.py:25-27 (q/k/v maps)
+ * Y[m, n] = act(acc[m, n] + shift[n]),  acc = X (M x Kc, bf16 act) . Wp^T  (Wp: packed, BN scale folded, R=Nout)
+ *   Nout % 16 == 0, Nout <= 256 per call;  M = B*N
+ *   y_act   bf16 act destination, 64-col block offset y_kb0 in a matrix of y_kblocks blocks (may be NULL)
+ *   y_cm    fp32 cm destination (B, Nout, N) with batch stride y_bstride (may be NULL)                           */
+int gfs_linear_bf16(const void* x_act, int x_kblocks, int x_kb0, int kb_count,
+                    const void* w_packed, const float* shift, int Nout, int act,
+                    int B, int N,
+                    void* y_act, int y_kblocks, int y_kb0,
+                    float* y_cm, int64_t y_bstride, void* stream);
+
+/* ---- geometric-word projection: model/capl.py:344-353 -----------------------------------------------------------
+ * cos[g] = <gp_l2[g], ec> / max(|ec|, 1e-12); cosine_feat = softmax_g(10 cos); assignment = argmax_g (first max).
+ * fp32 CUDA-core contraction in a pinned order (assignment parity), fused norm/softmax/argmax.
+ *   ec        cm fp32 (B, D, N), D <= 192 (batch stride ec_bstride)
+ *   gp_l2t    (D, Gp) fp32: L2-normalised GW basis, transposed, zero-padded to Gp = 160 or 192 columns (G <= Gp)
+ *   cosine_act bf16 act destination (G columns starting at block kb0, zero padded)    (may be NULL)
+ *   cosine_cm  fp32 cm (B, G, N) destination, batch stride G*N                          (may be NULL)
+ *   assignment (B*N) int32                                                                                     */
+int gfs_gw_project(const float* ec, int64_t ec_bstride, int B, int D, int N,
+                   const float* gp_l2t, int G, int Gp,
+                   void* cosine_act, int kblocks, int kb0, float* cosine_cm, int32_t* assignment, void* stream);
+
+/* ---- cosine / prototype logits: model/capl.py:290-322 (get_pred) fused with :127-128,:188 (get_gp_weight) -------
+ * logits[b,c,n] = 10 * <proto_n[b?,c,:], feat[b,:,n]> / max(|feat|,1e-12)  [ * th if coding[c, assignment[b,n]] == 1 ]
+ *   feat      cm fp32 (B, D, N), D <= 128;  proto_l2 (PB, CLS, D) already L2-normalised, PB = 1 or B;  CLS <= 32
+ *   coding    optional (CLS, G) fp32 0/1 with assignment (B*N) int32 and weight th                              */
+int gfs_cos_logits(const float* feat, int64_t feat_bstride, int B, int D, int N,
+                   const float* proto_l2, int PB, int CLS,
+                   const float* coding, int G, const int32_t* assignment, float th,
+                   float* logits, void* stream);
+
+/* ---- prototype refinement: model/capl.py:245-287 (post_refine_proto_v2), softmax over POINTS then pred @ feat^T ---
+ *   logits (B, CLS, N) fp32 (= get_pred output);  feat cm (B, D, N);  out pred_proto (B, CLS, D) fp32 (un-normalised
+ *   sum_n softmax_n(logits)[b,c,n] * feat[b,:,n]); the tiny gating arithmetic stays in the host wrapper.          */
+int gfs_softmax_pool(const float* logits, const float* feat, int64_t feat_bstride, int B, int CLS, int D, int N,
+                     float* pred_proto, void* stream);
+
+/* ---- k-means E/M step: sklearn KMeans.fit as called at get_basis.py:210 (_k_means_lloyd.pyx:196-218) ------------
+ * labels[i] = argmin_c (|c|^2 - 2 x_i.c), fp32 pinned order, strict '<' (lowest index wins).
+ *   X (n, D) row-major fp32, D % 4 == 0, D <= 256;  centers (K, D), K <= 256;  cnorm workspace K floats
+ *   labels (n) int32;  score optional (n) fp32 = |c|^2 - 2 x.c of the winner                                    */
+int gfs_kmeans_assign(const float* X, int64_t n, int D, const float* centers, int K,
+                      float* cnorm, int32_t* labels, float* score, void* stream);
+/* deterministic centroid sums: partial (P, K, D) fp32 + pcount (P, K) int32 workspaces, P = number of CTAs used
+ * (gfs_kmeans_partials()); sums (K, D) fp64 and counts (K) int64 are written in a fixed reduction order.        */
+int gfs_kmeans_partials(void);
+int gfs_kmeans_accumulate(const float* X, int64_t n, int D, const int32_t* labels, int K,
+                          float* partial, int32_t* pcount, double* sums, int64_t* counts, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GFS3D_H */
