@@ -45,4 +45,18 @@ __device__ __forceinline__ void load_panel_async(float* dst, int width, const fl
     }
 }
 
+// per-point squared norm as the same fma chain (c ascending) the tile core uses for a dot product: |x|^2 == dot(x, x)
+static __global__ void sqnorm_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, float* __restrict__ out) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (n >= N) return;
+    const float* p = x + (int64_t)b * bstride + n;
+    float acc = 0.0f;
+    for (int c = 0; c < C; ++c) {
+        const float v = p[(int64_t)c * N];
+        acc = fmaf(v, v, acc);
+    }
+    out[(int64_t)b * N + n] = acc;
+}
+
 }  // namespace gfs

@@ -1,0 +1,169 @@
+// head.cu -- the small fused reductions of the geometric-word head.
+//
+//   gfs_cos_logits   model/capl.py:290-322 (get_pred: 2 x normalize, proto @ x, x10) fused with
+//                    :127-128,:188 (get_gp_weight: weight th where coding[c, assignment] == 1; logits *= weight)
+//   gfs_softmax_pool model/capl.py:262-265 (softmax over the POINTS of a block, then pred @ point_feat^T)
+#include "common.cuh"
+
+namespace gfs {
+
+constexpr int CL_MAXC = 32;
+
+// one thread per point; prototypes (already L2-normalised) broadcast from shared memory
+__global__ void __launch_bounds__(128)
+cos_logits_kernel(const float* __restrict__ feat, int64_t bstride, int D, int N, const float* __restrict__ proto, int PB, int CLS,
+                  const float* __restrict__ coding, int G, const int32_t* __restrict__ assignment, float th,
+                  float* __restrict__ logits) {
+    extern __shared__ float sp[];   // [CLS][D]
+    const int b = blockIdx.y;
+    const float* pb = proto + (PB > 1 ? (int64_t)b * CLS * D : 0);
+    for (int i = threadIdx.x; i < CLS * D; i += blockDim.x) sp[i] = pb[i];
+    __syncthreads();
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const float* f = feat + (int64_t)b * bstride + n;
+    float acc[CL_MAXC];
+#pragma unroll
+    for (int c = 0; c < CL_MAXC; ++c) acc[c] = 0.0f;
+    float nrm = 0.0f;
+    for (int d = 0; d < D; ++d) {
+        const float v = f[(int64_t)d * N];
+        nrm = fmaf(v, v, nrm);
+#pragma unroll
+        for (int c = 0; c < CL_MAXC; ++c)
+            if (c < CLS) acc[c] = fmaf(v, sp[c * D + d], acc[c]);
+    }
+    const float inv = 10.0f / fmaxf(sqrtf(nrm), 1e-12f);
+    int a = 0;
+    if (coding) a = assignment[(int64_t)b * N + n];
+#pragma unroll
+    for (int c = 0; c < CL_MAXC; ++c) {
+        if (c < CLS) {
+            float v = acc[c] * inv;
+            if (coding && coding[(int64_t)c * G + a] == 1.0f) v *= th;
+            logits[((int64_t)b * CLS + c) * N + n] = v;
+        }
+    }
+}
+
+// max and sum-exp over the points of one (block, class) row
+__global__ void __launch_bounds__(256)
+softmax_stats_kernel(const float* __restrict__ logits, int N, float* __restrict__ stats) {
+    __shared__ float red[8];
+    const float* row = logits + (int64_t)blockIdx.x * N;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float mx = -INFINITY;
+    for (int n = tid; n < N; n += 256) mx = fmaxf(mx, row[n]);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = red[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+    __syncthreads();
+    float sum = 0.0f;
+    for (int n = tid; n < N; n += 256) sum += expf(row[n] - mx);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    if (tid == 0) {
+        float t = 0.0f;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        stats[blockIdx.x * 2 + 0] = mx;
+        stats[blockIdx.x * 2 + 1] = t;
+    }
+}
+
+// CTA = (block b, chunk of 128 points): partial[b][chunk][c][d] = sum_{n in chunk} p[c][n] * feat[b][d][n]
+constexpr int SP_CH = 128;
+__global__ void __launch_bounds__(128)
+softmax_pool_kernel(const float* __restrict__ logits, const float* __restrict__ stats, const float* __restrict__ feat,
+                    int64_t bstride, int CLS, int D, int N, int nchunks, float* __restrict__ partial) {
+    extern __shared__ float sm[];
+    float* P = sm;                       // [CLS][SP_CH]
+    float* F = sm + CLS * SP_CH;         // [D][SP_CH + 1]
+    const int b = blockIdx.y, ch = blockIdx.x, n0 = ch * SP_CH, tid = threadIdx.x;
+    for (int i = tid; i < CLS * SP_CH; i += 128) {
+        const int c = i / SP_CH, j = i - c * SP_CH;
+        const int n = n0 + j;
+        float v = 0.0f;
+        if (n < N) {
+            const float* st = stats + ((int64_t)b * CLS + c) * 2;
+            v = expf(logits[((int64_t)b * CLS + c) * N + n] - st[0]) / st[1];
+        }
+        P[i] = v;
+    }
+    for (int i = tid; i < D * SP_CH; i += 128) {
+        const int d = i / SP_CH, j = i - d * SP_CH;
+        const int n = n0 + j;
+        F[d * (SP_CH + 1) + j] = n < N ? feat[(int64_t)b * bstride + (int64_t)d * N + n] : 0.0f;
+    }
+    __syncthreads();
+    for (int d = tid; d < D; d += 128) {
+        float acc[CL_MAXC];
+#pragma unroll
+        for (int c = 0; c < CL_MAXC; ++c) acc[c] = 0.0f;
+        const float* fr = F + d * (SP_CH + 1);
+        for (int j = 0; j < SP_CH; ++j) {
+            const float v = fr[j];
+#pragma unroll
+            for (int c = 0; c < CL_MAXC; ++c)
+                if (c < CLS) acc[c] = fmaf(P[c * SP_CH + j], v, acc[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < CL_MAXC; ++c)
+            if (c < CLS) partial[(((int64_t)b * nchunks + ch) * CLS + c) * D + d] = acc[c];
+    }
+}
+
+__global__ void softmax_pool_reduce_kernel(const float* __restrict__ partial, int nchunks, int CD, int64_t total,
+                                           float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int64_t b = i / CD, r = i - b * CD;
+    float acc = 0.0f;
+    for (int ch = 0; ch < nchunks; ++ch) acc += partial[(b * nchunks + ch) * CD + r];   // fixed order: deterministic
+    out[i] = acc;
+}
+
+}  // namespace gfs
+
+extern "C" int gfs_cos_logits(const float* feat, int64_t feat_bstride, int B, int D, int N, const float* proto_l2, int PB,
+                              int CLS, const float* coding, int G, const int32_t* assignment, float th, float* logits,
+                              void* stream) {
+    using namespace gfs;
+    GFS_REQUIRE(feat && proto_l2 && logits, GFS_ERR_BAD_ARG, "gfs_cos_logits: null pointer");
+    GFS_REQUIRE(B > 0 && D > 0 && N > 0 && CLS > 0, GFS_ERR_BAD_ARG, "gfs_cos_logits: non-positive size");
+    GFS_REQUIRE(CLS <= CL_MAXC, GFS_ERR_UNSUPPORTED, "gfs_cos_logits: CLS=%d > %d is not built", CLS, CL_MAXC);
+    GFS_REQUIRE(PB == 1 || PB == B, GFS_ERR_BAD_ARG, "gfs_cos_logits: PB=%d must be 1 or B=%d", PB, B);
+    GFS_REQUIRE(!coding || (assignment && G > 0), GFS_ERR_BAD_ARG, "gfs_cos_logits: coding needs assignment and G");
+    const size_t smem = (size_t)CLS * D * sizeof(float);
+    GFS_REQUIRE(smem <= 48 * 1024, GFS_ERR_UNSUPPORTED, "gfs_cos_logits: CLS*D too large");
+    cos_logits_kernel<<<dim3((N + 127) / 128, B), 128, smem, static_cast<cudaStream_t>(stream)>>>(
+        feat, feat_bstride, D, N, proto_l2, PB, CLS, coding, G, assignment, th, logits);
+    GFS_LAUNCH_OK("cos_logits_kernel");
+    return GFS_OK;
+}
+
+extern "C" int gfs_softmax_pool(const float* logits, const float* feat, int64_t feat_bstride, int B, int CLS, int D, int N,
+                                float* stats, float* partial, float* pred_proto, void* stream) {
+    using namespace gfs;
+    GFS_REQUIRE(logits && feat && stats && partial && pred_proto, GFS_ERR_BAD_ARG, "gfs_softmax_pool: null pointer");
+    GFS_REQUIRE(B > 0 && D > 0 && N > 0 && CLS > 0, GFS_ERR_BAD_ARG, "gfs_softmax_pool: non-positive size");
+    GFS_REQUIRE(CLS <= CL_MAXC, GFS_ERR_UNSUPPORTED, "gfs_softmax_pool: CLS=%d > %d is not built", CLS, CL_MAXC);
+    const size_t smem = ((size_t)CLS * SP_CH + (size_t)D * (SP_CH + 1)) * sizeof(float);
+    GFS_REQUIRE(smem <= 200 * 1024, GFS_ERR_UNSUPPORTED, "gfs_softmax_pool: D=%d too large", D);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int nchunks = (N + SP_CH - 1) / SP_CH;
+    softmax_stats_kernel<<<B * CLS, 256, 0, st>>>(logits, N, stats);
+    GFS_LAUNCH_OK("softmax_stats_kernel");
+    GFS_CUDA_OK(allow_smem(reinterpret_cast<const void*>(softmax_pool_kernel), 200 * 1024));
+    softmax_pool_kernel<<<dim3(nchunks, B), 128, smem, st>>>(logits, stats, feat, feat_bstride, CLS, D, N, nchunks, partial);
+    GFS_LAUNCH_OK("softmax_pool_kernel");
+    const int64_t total = (int64_t)B * CLS * D;
+    softmax_pool_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(partial, nchunks, CLS * D, total, pred_proto);
+    GFS_LAUNCH_OK("softmax_pool_reduce_kernel");
+    return GFS_OK;
+}

@@ -22,19 +22,6 @@ struct KnnSmem {
     // followed by As[C][64]
 };
 
-__global__ void sqnorm_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, float* __restrict__ out) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = blockIdx.y;
-    if (n >= N) return;
-    const float* p = x + (int64_t)b * bstride + n;
-    float acc = 0.0f;
-    for (int c = 0; c < C; ++c) {
-        const float v = p[(int64_t)c * N];
-        acc = fmaf(v, v, acc);
-    }
-    out[(int64_t)b * N + n] = acc;
-}
-
 __global__ void __launch_bounds__(T_THREADS, 2)
 knn_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int k, const float* __restrict__ sqnorm,
            int32_t* __restrict__ idx_out, float* __restrict__ dist_out) {

@@ -20,8 +20,8 @@ SIGNATURES = {
     "gfs_linear_bf16": [_p, _i, _i, _i, _p, _p, _i, _i, _i, _i, _p, _i, _i, _p, _i64, _p],
     "gfs_gw_project": [_p, _i64, _i, _i, _i, _p, _i, _i, _p, _i, _i, _p, _p, _p],
     "gfs_cos_logits": [_p, _i64, _i, _i, _i, _p, _i, _i, _p, _i, _p, _f, _p, _p],
-    "gfs_softmax_pool": [_p, _p, _i64, _i, _i, _i, _i, _p, _p],
-    "gfs_kmeans_assign": [_p, _i64, _i, _p, _i, _p, _p, _p, _p],
+    "gfs_softmax_pool": [_p, _p, _i64, _i, _i, _i, _i, _p, _p, _p, _p],
+    "gfs_kmeans_assign": [_p, _i64, _i, _p, _i, _i, _p, _p, _p, _p],
     "gfs_kmeans_accumulate": [_p, _i64, _i, _p, _i, _p, _p, _p, _p, _p],
 }
 UTILITIES = {"gfs_version": (_i, []), "gfs_last_error_string": (ctypes.c_char_p, []),
@@ -39,13 +39,15 @@ def lib():
                 "(there is no CPU or PyTorch fallback for the hot path)")
         l = ctypes.CDLL(LIB_PATH)
         for name, args in SIGNATURES.items():
-            fn = getattr(l, name)
-            fn.restype = _i
-            fn.argtypes = args
+            fn = getattr(l, name, None)     # a missing export surfaces as AttributeError at the call site
+            if fn is not None:
+                fn.restype = _i
+                fn.argtypes = args
         for name, (res, args) in UTILITIES.items():
-            fn = getattr(l, name)
-            fn.restype = res
-            fn.argtypes = args
+            fn = getattr(l, name, None)
+            if fn is not None:
+                fn.restype = res
+                fn.argtypes = args
         _lib = l
     return _lib
 

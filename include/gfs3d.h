@@ -126,18 +126,20 @@ int gfs_cos_logits(const float* feat, int64_t feat_bstride, int B, int D, int N,
 
 /* ---- prototype refinement: model/capl.py:245-287 (post_refine_proto_v2), softmax over POINTS then pred @ feat^T ---
  *   logits (B, CLS, N) fp32 (= get_pred output);  feat cm (B, D, N);  out pred_proto (B, CLS, D) fp32 (un-normalised
- *   sum_n softmax_n(logits)[b,c,n] * feat[b,:,n]); the tiny gating arithmetic stays in the host wrapper.          */
+ *   sum_n softmax_n(logits)[b,c,n] * feat[b,:,n]); the tiny gating arithmetic stays in the host wrapper.
+ *   workspaces: stats (B*CLS*2) floats, partial (B * ceil(N/128) * CLS * D) floats; the reduction order is fixed.     */
 int gfs_softmax_pool(const float* logits, const float* feat, int64_t feat_bstride, int B, int CLS, int D, int N,
-                     float* pred_proto, void* stream);
+                     float* stats, float* partial, float* pred_proto, void* stream);
 
 /* ---- k-means E/M step: sklearn KMeans.fit as called at get_basis.py:210 (_k_means_lloyd.pyx:196-218) ------------
  * labels[i] = argmin_c (|c|^2 - 2 x_i.c), fp32 pinned order, strict '<' (lowest index wins).
- *   X (n, D) row-major fp32, D % 4 == 0, D <= 256;  centers (K, D), K <= 256;  cnorm workspace K floats
- *   labels (n) int32;  score optional (n) fp32 = |c|^2 - 2 x.c of the winner                                    */
-int gfs_kmeans_assign(const float* X, int64_t n, int D, const float* centers, int K,
+ *   xt        (D, n) fp32: the shard's points TRANSPOSED (channel-major, like every other fp32 operand here); n % 4 == 0
+ *   centers_t (D, Kp) fp32: centroids transposed, zero-padded to Kp columns (K <= Kp <= 192, Kp % 4 == 0)
+ *   cnorm     workspace, Kp floats;  labels (n) int32;  score optional (n) fp32 = |c|^2 - 2 x.c of the winner          */
+int gfs_kmeans_assign(const float* xt, int64_t n, int D, const float* centers_t, int K, int Kp,
                       float* cnorm, int32_t* labels, float* score, void* stream);
-/* deterministic centroid sums: partial (P, K, D) fp32 + pcount (P, K) int32 workspaces, P = number of CTAs used
- * (gfs_kmeans_partials()); sums (K, D) fp64 and counts (K) int64 are written in a fixed reduction order.        */
+/* deterministic centroid sums over X (n, D) row-major: partial (P, K, D) fp32 + pcount (P, K) int32 workspaces with
+ * P = gfs_kmeans_partials() (one per SM); sums (K, D) fp64 and counts (K) int64 are reduced in a fixed order.       */
 int gfs_kmeans_partials(void);
 int gfs_kmeans_accumulate(const float* X, int64_t n, int D, const int32_t* labels, int K,
                           float* partial, int32_t* pcount, double* sums, int64_t* counts, void* stream);
