@@ -98,3 +98,97 @@ def edgeconv(pq, idx, w2_packed, shift2, B, N, k, y_cm=None, y_act=None, y_act_k
         _ptr(y_act), 0 if y_act is None else y_act.shape[1], y_act_kb,
         _ptr(y_act2), 0 if y_act2 is None else y_act2.shape[1], y_act2_kb,
         _ptr(argmax), _stream()), "gfs_edgeconv_fwd")
+
+
+def linear(x_act: torch.Tensor, x_kb0: int, kb_count: int, w_packed: torch.Tensor, shift: Optional[torch.Tensor],
+           nout: int, act: int, B: int, N: int, y_act: Optional[torch.Tensor] = None, y_kb0: int = 0,
+           y_cm: Optional[torch.Tensor] = None):
+    """Y = act(X . Wp^T + shift) on tcgen05; X / Y bf16 act tiles, optional fp32 channel-major copy of Y"""
+    _need_cuda(x_act, w_packed, shift, y_act, y_cm)
+    if y_cm is not None:
+        assert y_cm.stride(2) == 1 and y_cm.stride(1) == N and y_cm.shape[1] == nout
+    check(lib().gfs_linear_bf16(
+        _ptr(x_act), x_act.shape[1], x_kb0, kb_count, _ptr(w_packed), _ptr(shift), nout, act, B, N,
+        _ptr(y_act), 0 if y_act is None else y_act.shape[1], y_kb0,
+        _ptr(y_cm), 0 if y_cm is None else y_cm.stride(0), _stream()), "gfs_linear_bf16")
+
+
+def gw_project(ec: torch.Tensor, gp_l2t: torch.Tensor, G: int, cosine_act: Optional[torch.Tensor] = None, kb0: int = 0,
+               want_cm: bool = False):
+    """ec (B, D, N) cm fp32; gp_l2t (D, Gp) -> assignment (B, N) int32 [, cosine_feat (B, G, N) fp32]"""
+    _need_cuda(ec, gp_l2t, cosine_act)
+    B, D, N = ec.shape
+    assert ec.stride(2) == 1 and ec.stride(1) == N and gp_l2t.is_contiguous() and gp_l2t.shape[0] == D
+    Gp = gp_l2t.shape[1]
+    assign = torch.empty(B, N, dtype=torch.int32, device=ec.device)
+    cm = torch.empty(B, G, N, dtype=torch.float32, device=ec.device) if want_cm else None
+    check(lib().gfs_gw_project(_ptr(ec), ec.stride(0), B, D, N, _ptr(gp_l2t), G, Gp, _ptr(cosine_act),
+                               0 if cosine_act is None else cosine_act.shape[1], kb0, _ptr(cm), _ptr(assign), _stream()),
+          "gfs_gw_project")
+    return assign, cm
+
+
+def cos_logits(feat: torch.Tensor, proto_l2: torch.Tensor, coding: Optional[torch.Tensor] = None,
+               assignment: Optional[torch.Tensor] = None, th: float = 1.0) -> torch.Tensor:
+    """feat (B, D, N) cm fp32; proto_l2 (CLS, D) or (B, CLS, D), already L2-normalised -> logits (B, CLS, N)"""
+    _need_cuda(feat, proto_l2, coding, assignment)
+    B, D, N = feat.shape
+    assert feat.stride(2) == 1 and feat.stride(1) == N
+    proto_l2 = proto_l2.contiguous().float()
+    PB = 1 if proto_l2.dim() == 2 else proto_l2.shape[0]
+    CLS = proto_l2.shape[-2]
+    out = torch.empty(B, CLS, N, dtype=torch.float32, device=feat.device)
+    G = 0
+    if coding is not None:
+        coding = coding.contiguous().float()
+        G = coding.shape[1]
+        assert coding.shape[0] == CLS and assignment is not None and assignment.dtype == torch.int32
+    check(lib().gfs_cos_logits(_ptr(feat), feat.stride(0), B, D, N, _ptr(proto_l2), PB, CLS, _ptr(coding), G,
+                               _ptr(assignment), float(th), _ptr(out), _stream()), "gfs_cos_logits")
+    return out
+
+
+def softmax_pool(logits: torch.Tensor, feat: torch.Tensor) -> torch.Tensor:
+    """sum_n softmax_n(logits[b,c,:]) * feat[b,:,n] -> (B, CLS, D)"""
+    _need_cuda(logits, feat)
+    B, CLS, N = logits.shape
+    D = feat.shape[1]
+    assert logits.is_contiguous() and feat.stride(2) == 1 and feat.stride(1) == N
+    dev = feat.device
+    stats = torch.empty(B * CLS * 2, dtype=torch.float32, device=dev)
+    partial = torch.empty(B * ((N + 127) // 128) * CLS * D, dtype=torch.float32, device=dev)
+    out = torch.empty(B, CLS, D, dtype=torch.float32, device=dev)
+    check(lib().gfs_softmax_pool(_ptr(logits), _ptr(feat), feat.stride(0), B, CLS, D, N, _ptr(stats), _ptr(partial),
+                                 _ptr(out), _stream()), "gfs_softmax_pool")
+    return out
+
+
+def kmeans_assign(xt: torch.Tensor, centers_t: torch.Tensor, K: int, want_score: bool = False):
+    """xt (D, n) fp32, centers_t (D, Kp) fp32 zero padded -> labels (n) int32"""
+    _need_cuda(xt, centers_t)
+    D, n = xt.shape
+    assert xt.is_contiguous() and centers_t.is_contiguous() and centers_t.shape[0] == D
+    Kp = centers_t.shape[1]
+    cnorm = torch.empty(Kp, dtype=torch.float32, device=xt.device)
+    labels = torch.empty(n, dtype=torch.int32, device=xt.device)
+    score = torch.empty(n, dtype=torch.float32, device=xt.device) if want_score else None
+    check(lib().gfs_kmeans_assign(_ptr(xt), n, D, _ptr(centers_t), K, Kp, _ptr(cnorm), _ptr(labels), _ptr(score), _stream()),
+          "gfs_kmeans_assign")
+    return (labels, score) if want_score else labels
+
+
+def kmeans_accumulate(X: torch.Tensor, labels: torch.Tensor, K: int, n_valid: Optional[int] = None):
+    """X (n, D) fp32 row-major, labels (n) int32 -> sums (K, D) fp64, counts (K) int64 (deterministic)"""
+    _need_cuda(X, labels)
+    n, D = X.shape
+    if n_valid is not None:
+        n = n_valid
+    assert X.is_contiguous() and labels.dtype == torch.int32
+    P = lib().gfs_kmeans_partials()
+    partial = torch.empty(P * K * D, dtype=torch.float32, device=X.device)
+    pcount = torch.empty(P * K, dtype=torch.int32, device=X.device)
+    sums = torch.empty(K, D, dtype=torch.float64, device=X.device)
+    counts = torch.empty(K, dtype=torch.int64, device=X.device)
+    check(lib().gfs_kmeans_accumulate(_ptr(X), n, D, _ptr(labels), K, _ptr(partial), _ptr(pcount), _ptr(sums), _ptr(counts),
+                                      _stream()), "gfs_kmeans_accumulate")
+    return sums, counts

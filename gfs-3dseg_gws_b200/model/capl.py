@@ -1,0 +1,205 @@
+"""Geometric-word GFS model -- drop-in for the reference's model/capl.py, head computed by the sm_100a kernels.
+
+Kept from the reference (file:line):
+  mpti_net_Point_GeoAsWeight_v2(classes, criterion, args, base_num, gp, energy)      model/capl.py:21-69
+    .getFeatures(x)            -> (point_feat, semantic_feat, one_hot_feat)          :324-362
+    .get_pred(x, proto, use_bg_proto)                                                :290-322
+    .post_refine_proto_v2(proto, x, point_feat, use_bg_proto)                        :245-287
+    .get_gp_weight(gp_classifier, gp_feat, use_bg_weight, gt_label, th)              :92-142
+    .forward(x, y, gened_proto, gen_proto, eval_model, ...)                          :144-242
+    .Get_Fg_Feat(x, y)                                                               :71-88
+    .generate_fake_proto / .post_processing_hard_coding                              :364-433
+  BaseLearner                                                                        :435-457
+State-dict keys: encoder.*, base_learner.convs.*, att_learner.{q,k,v}_map.weight, main_proto, bg_proto, fusion.{0,1}.*
+"""
+import random
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from gfs3d import ops
+from model.attention import SelfAttention
+from model.dgcnn import DGCNN, BaseLearner, _Folded, _cm, _state_key, fold_bn
+
+manual_seed = 321
+torch.manual_seed(manual_seed)
+random.seed(manual_seed)
+
+
+class mpti_net_Point_GeoAsWeight_v2(nn.Module):
+    def __init__(self, classes=13, criterion=nn.CrossEntropyLoss(), args=None, base_num=7, gp=None, energy=None):
+        super(mpti_net_Point_GeoAsWeight_v2, self).__init__()
+        assert classes > 1
+        self.criterion = criterion
+        self.classes = classes
+        self.encoder = DGCNN(args.edgeconv_widths, args.dgcnn_mlp_widths, args.pc_in_dim, k=args.dgcnn_k, return_edgeconvs=True)
+        self.base_learner = BaseLearner(args.dgcnn_mlp_widths[-1], args.base_widths)
+        self.att_learner = SelfAttention(args.dgcnn_mlp_widths[-1], args.output_dim)
+        self.feat_dim = args.edgeconv_widths[0][-1] + args.output_dim + args.base_widths[-1]
+        self.gp = gp                       # plain attribute, NOT a buffer (model/capl.py:49-50): it travels as the .pkl
+        self.gp.requires_grad = False
+        main_dim = 128
+        self.main_proto = nn.Parameter(torch.randn((classes, main_dim)))
+        self.bg_proto = nn.Parameter(torch.randn((1, main_dim)))
+        self.args = args
+        self.base_num = base_num
+        self.fusion = nn.Sequential(nn.Conv1d(in_channels=self.feat_dim + self.gp.shape[0], out_channels=main_dim, kernel_size=1),
+                                    nn.BatchNorm1d(main_dim), nn.LeakyReLU(0.2))
+        self.energy = energy
+        print('model using energy: {}'.format(self.energy))
+        self._folded = _Folded()
+
+    # ------------------------------------------------------------------ weight folding for the head
+    def _prepare(self, device):
+        key = _state_key(self.fusion, device) + (id(self.gp), self.gp._version)
+        if self._folded.key != key:
+            G = self.gp.shape[0]
+            sem = self.feat_dim
+            if sem != 192 or self.encoder.n_edgeconv * 64 != self.gp.shape[1] or G > 192:
+                raise NotImplementedError(
+                    f"head shapes (feat_dim={sem}, GW basis {tuple(self.gp.shape)}) are outside what the sm_100a head is built for "
+                    "(feat_dim 192, <=192 geometric words of width 64*n_edgeconv)")
+            with torch.no_grad():
+                Gp = (G + 63) // 64 * 64
+                gp_l2 = F.normalize(self.gp.detach().float().to(device), p=2, dim=1)            # (G, D)
+                gp_l2t = torch.zeros(gp_l2.shape[1], Gp, dtype=torch.float32, device=device)
+                gp_l2t[:, :G] = gp_l2.t()
+                conv, bn = self.fusion[0], self.fusion[1]
+                s, t = fold_bn(bn)
+                w = conv.weight.detach().float().reshape(conv.weight.shape[0], conv.weight.shape[1])   # (128, G + 192)
+                # kernel-side column order: [semantic 192 | cosine G | zero pad]  (reference order: [cosine G | semantic 192])
+                wk = torch.zeros(w.shape[0], sem + Gp, dtype=torch.float32, device=device)
+                wk[:, :sem] = w[:, G:]
+                wk[:, sem:sem + G] = w[:, :G]
+                shift = (conv.bias.detach().float() * s + t).contiguous()
+                data = dict(G=G, Gp=Gp, gp_l2t=gp_l2t.contiguous(), wp=ops.pack_weight(wk, s), shift=shift,
+                            kblocks=(sem + Gp) // 64, nout=w.shape[0])
+            self._folded.key, self._folded.data = key, data
+        return self._folded.data
+
+    # ------------------------------------------------------------------ fused feature extraction
+    def _features(self, x, need_semantic=False):
+        """-> (point_feat (B,128,N) fp32 cm, assignment (B,N) int32, semantic (B,192,N) fp32 or None)"""
+        if self.training:
+            raise NotImplementedError(
+                "training-mode forward of the GW model is not built yet in the B200 path (eval / inference only); "
+                "there is deliberately no PyTorch fallback")
+        if not x.is_cuda:
+            raise RuntimeError("the GW model needs CUDA tensors: the hot path has no CPU fallback")
+        hd = self._prepare(x.device)
+        x = _cm(x)
+        B, _, N = x.shape
+        M = B * N
+        fus_in = ops.new_act(M, hd["kblocks"], x.device)                 # [level1 | att | level3 | cosine_feat | pad]
+        enc = self.encoder.forward_fused(x, want_lvl2_cm=False, level1_act=fus_in, level1_kb=0)
+        semantic = torch.empty(B, 192, N, dtype=torch.float32, device=x.device) if need_semantic else None
+        att = self.att_learner.forward_fused(enc.lvl2_act, B, N)                                    # (B, 64, N) fp32
+        ops.cm_to_act(att, fus_in, 1)
+        self.base_learner.forward_fused(enc.lvl2_act, B, N, y_act=fus_in, y_kb0=2,
+                                        y_cm=semantic[:, 128:192, :] if need_semantic else None)
+        assignment, _ = ops.gw_project(enc.ec, hd["gp_l2t"], hd["G"], cosine_act=fus_in, kb0=3)
+        point_feat = torch.empty(B, hd["nout"], N, dtype=torch.float32, device=x.device)
+        ops.linear(fus_in, 0, hd["kblocks"], hd["wp"], hd["shift"], hd["nout"], ops.ACT_LRELU02, B, N, y_cm=point_feat)
+        if need_semantic:
+            semantic[:, 0:64, :].copy_(enc.ec[:, 0:64, :])
+            semantic[:, 64:128, :].copy_(att)
+        return point_feat, assignment, semantic
+
+    def getFeatures(self, x, segment_label=None):
+        """(B, C_in, N) -> point_feat (B,128,N), semantic_feat (B,192,N), one_hot_feat (B,G,N) float 0/1"""
+        point_feat, assignment, semantic = self._features(x, need_semantic=True)
+        one_hot = F.one_hot(assignment.long(), num_classes=self.gp.shape[0]).transpose(2, 1).float()
+        return point_feat, semantic, one_hot
+
+    def Get_Fg_Feat(self, x, y):
+        y = y[0]
+        point_feat, _, gp_feat = self.getFeatures(x)
+        fg_feat = point_feat[0][:, y == 1]
+        fg_gp_feat = gp_feat[0][:, y == 1]
+        return fg_feat.transpose(1, 0), fg_gp_feat.transpose(1, 0)
+
+    # ------------------------------------------------------------------ logits / prototypes
+    def get_pred(self, x, proto, use_bg_proto=False):
+        """10 * cos(proto, x): x (b, c, n); proto (cls, c) or (b, cls, c); optional bg_proto row first -> (b, cls, n)"""
+        if proto.dim() == 3:
+            if use_bg_proto:
+                proto = torch.cat([self.bg_proto.unsqueeze(0).repeat(proto.shape[0], 1, 1), proto], dim=1)
+            pn = F.normalize(proto, p=2, dim=-1)
+        else:
+            if use_bg_proto:
+                proto = torch.cat([self.bg_proto, proto], dim=0)
+            pn = F.normalize(proto, p=2, dim=1)
+        return ops.cos_logits(_cm(x), pn.detach())
+
+    def post_refine_proto_v2(self, proto, x, point_feat, use_bg_proto=False):
+        """query-adaptive prototype refinement (eqn. 6) -> (b, classes, c)"""
+        pred = self.get_pred(x, proto, use_bg_proto)
+        pred_proto = ops.softmax_pool(pred, _cm(point_feat))
+        if use_bg_proto:
+            pred_proto = pred_proto[:, 1:, :]
+        w = (F.normalize(pred_proto, 2, -1) * F.normalize(proto, 2, -1).unsqueeze(0)).sum(-1, keepdim=True)
+        w = w * (w > 0).float()
+        return w * pred_proto + (1 - w) * proto.unsqueeze(0)
+
+    def get_gp_weight(self, gp_classifier, gp_feat, use_bg_weight=False, gt_label=None, th=None):
+        """(n_cls, k) coding x one-hot (b, k, n) -> weight (b, cls, n) in {1, th} and the two diagnostic accuracies.
+        The eval forward does not call this (the weight is applied inside gfs_cos_logits); kept for API parity."""
+        assignment = gp_feat.argmax(dim=1)                                   # (b, n)
+        score = gp_classifier[:, assignment].permute(1, 0, 2)                # (b, cls, n) == coding @ one_hot
+        acc, novel_acc = 0., 0.
+        if gt_label is not None and not use_bg_weight:
+            per_point = torch.gather(score, 1, gt_label.unsqueeze(1)).squeeze(1)
+            acc = per_point.mean()
+            novel_mask = gt_label > self.base_num - 1
+            novel_acc = per_point[novel_mask].mean() if novel_mask.sum() > 0 else torch.zeros_like(acc)
+        elif gt_label is not None and use_bg_weight:
+            gt_one_hot = F.one_hot(gt_label, num_classes=score.shape[1] + 1).transpose(2, 1)[:, 1:, :]
+            acc = (gt_one_hot * score).sum(dim=1).mean()
+        weight = torch.ones_like(score)
+        weight[score == 1] = th
+        if use_bg_weight:
+            weight = torch.cat([torch.ones_like(weight[:, :1]), weight], dim=1)
+            gt_mask = F.one_hot(gt_label, num_classes=score.shape[1] + 1).transpose(2, 1)
+            weight[gt_mask == 1] = 1
+        return weight, acc, novel_acc
+
+    def forward(self, x, y=None, gened_proto=None, gen_proto=False, eval_model=False, target_cls=None, segment_label=None,
+                geo2sem_proto=None, base_class_coding=None, novel_class_coding=None, bg_class_coding=None):
+        base_num = self.base_num
+        if not eval_model:
+            raise NotImplementedError(
+                "the training branch (model/capl.py:194-242) is not built yet in the B200 path; eval_model=True only")
+        point_feat, assignment, _ = self._features(x)
+        if gened_proto.dim() == 3:
+            gened_proto = gened_proto[0]
+        with torch.no_grad():
+            refine_proto = self.post_refine_proto_v2(proto=self.main_proto, x=point_feat, point_feat=point_feat)
+            refine_proto[:, :base_num] = refine_proto[:, :base_num] + gened_proto[:base_num].unsqueeze(0)
+            refine_proto[:, base_num:] = refine_proto[:, base_num:] * 0 + gened_proto[base_num:].unsqueeze(0)
+            gp_coding = torch.cat([base_class_coding, novel_class_coding], dim=0).float()
+            x_pre = ops.cos_logits(point_feat, F.normalize(refine_proto, p=2, dim=-1), gp_coding, assignment,
+                                   float(self.args.eval_weight))
+            # diagnostics of model/capl.py:104-114: mean of coding[gt, assignment] over all / novel points
+            if y is not None:
+                per_point = gp_coding[y.long(), assignment.long()]
+                gp_acc = per_point.mean()
+                novel = y > base_num - 1
+                gp_novel_acc = per_point[novel].mean() if novel.sum() > 0 else torch.zeros_like(gp_acc)
+            else:
+                gp_acc, gp_novel_acc = 0., 0.
+        return x_pre, gp_acc, gp_novel_acc
+
+    def generate_fake_proto(self, x, y, main_proto, fake_novel=None, post_processing=False):
+        raise NotImplementedError("training-only episodic helper (model/capl.py:364-411): training branch not built yet")
+
+    def post_processing_hard_coding(self, coding):
+        """keep the most frequent geometric words up to `energy` of the mass -> multi-hot (model/capl.py:413-433)"""
+        order = torch.argsort(coding, descending=True)
+        csum = torch.cumsum(coding[order], dim=0)
+        keep = int((csum > self.energy * coding.sum()).nonzero()[0]) + 1 if (csum > self.energy * coding.sum()).any() else len(order)
+        mask = torch.zeros_like(coding)
+        mask[order[:keep]] = 1
+        coding[mask == 1] = 1
+        coding[mask == 0] = 0
+        return coding
