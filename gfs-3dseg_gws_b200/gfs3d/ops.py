@@ -9,6 +9,26 @@ from ._lib import check, lib
 ACT_NONE, ACT_LRELU02, ACT_RELU = 0, 1, 2
 
 
+# ---- launch accounting / optional per-call CUDA-event timing (bench.py's roofline leg) ----
+LAUNCHES = 0            # kernels launched through the C ABI since import (each entry point launches a fixed number)
+PROFILE = None          # set to {} to record (name, start_event, end_event) per call on the current stream
+
+
+def _call(name: str, n_kernels: int, *args):
+    global LAUNCHES
+    fn = getattr(lib(), name)
+    if PROFILE is None:
+        rc = fn(*args)
+    else:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        PROFILE.setdefault(name, []).append((e0, e1))
+    LAUNCHES += n_kernels
+    check(rc, name)
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
@@ -51,7 +71,7 @@ def knn(x: torch.Tensor, k: int, return_dist: bool = False):
     sq = torch.empty(B, N, dtype=torch.float32, device=x.device)
     idx = torch.empty(B, N, k, dtype=torch.int32, device=x.device)
     dist = torch.empty(B, N, k, dtype=torch.float32, device=x.device) if return_dist else None
-    check(lib().gfs_knn_f32(_ptr(x), x.stride(0), B, C, N, k, _ptr(sq), _ptr(idx), _ptr(dist), _stream()), "gfs_knn_f32")
+    _call("gfs_knn_f32", 2, _ptr(x), x.stride(0), B, C, N, k, _ptr(sq), _ptr(idx), _ptr(dist), _stream())
     return (idx, dist) if return_dist else idx
 
 
@@ -62,8 +82,7 @@ def pointwise(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor]) -
     assert x.stride(2) == 1 and x.stride(1) == N and wt.is_contiguous() and wt.shape[0] == C
     O = wt.shape[1]
     out = torch.empty(B * N, O, dtype=torch.float32, device=x.device)
-    check(lib().gfs_pointwise_f32(_ptr(x), x.stride(0), B, C, N, _ptr(wt), _ptr(bias), O, _ptr(out), _stream()),
-          "gfs_pointwise_f32")
+    _call("gfs_pointwise_f32", 1, _ptr(x), x.stride(0), B, C, N, _ptr(wt), _ptr(bias), O, _ptr(out), _stream())
     return out
 
 
@@ -75,7 +94,7 @@ def pack_weight(w: torch.Tensor, row_scale: Optional[torch.Tensor] = None) -> to
     kb = (K + 63) // 64
     out = torch.empty(kb, R * 64, dtype=torch.bfloat16, device=w.device)
     rs = None if row_scale is None else row_scale.contiguous().float()
-    check(lib().gfs_pack_weight_bf16(_ptr(w), _ptr(rs), R, K, _ptr(out), _stream()), "gfs_pack_weight_bf16")
+    _call("gfs_pack_weight_bf16", 1, _ptr(w), _ptr(rs), R, K, _ptr(out), _stream())
     return out
 
 
@@ -83,7 +102,7 @@ def cm_to_act(x: torch.Tensor, act: torch.Tensor, kb0: int):
     _need_cuda(x, act)
     B, C, N = x.shape
     assert x.stride(2) == 1 and x.stride(1) == N
-    check(lib().gfs_cm_to_act(_ptr(x), x.stride(0), B, C, N, _ptr(act), act.shape[1], kb0, _stream()), "gfs_cm_to_act")
+    _call("gfs_cm_to_act", 1, _ptr(x), x.stride(0), B, C, N, _ptr(act), act.shape[1], kb0, _stream())
 
 
 def edgeconv(pq, idx, w2_packed, shift2, B, N, k, y_cm=None, y_act=None, y_act_kb=0, y_act2=None, y_act2_kb=0,
@@ -92,12 +111,12 @@ def edgeconv(pq, idx, w2_packed, shift2, B, N, k, y_cm=None, y_act=None, y_act_k
     _need_cuda(pq, idx, w2_packed, shift2)
     if y_cm is not None:
         assert y_cm.stride(2) == 1 and y_cm.stride(1) == N and y_cm.shape[1] == 64
-    check(lib().gfs_edgeconv_fwd(
+    _call("gfs_edgeconv_fwd", 1, 
         _ptr(pq), _ptr(idx), _ptr(w2_packed), _ptr(shift2), B, N, k,
         _ptr(y_cm), 0 if y_cm is None else y_cm.stride(0),
         _ptr(y_act), 0 if y_act is None else y_act.shape[1], y_act_kb,
         _ptr(y_act2), 0 if y_act2 is None else y_act2.shape[1], y_act2_kb,
-        _ptr(argmax), _stream()), "gfs_edgeconv_fwd")
+        _ptr(argmax), _stream())
 
 
 def linear(x_act: torch.Tensor, x_kb0: int, kb_count: int, w_packed: torch.Tensor, shift: Optional[torch.Tensor],
@@ -107,10 +126,10 @@ def linear(x_act: torch.Tensor, x_kb0: int, kb_count: int, w_packed: torch.Tenso
     _need_cuda(x_act, w_packed, shift, y_act, y_cm)
     if y_cm is not None:
         assert y_cm.stride(2) == 1 and y_cm.stride(1) == N and y_cm.shape[1] == nout
-    check(lib().gfs_linear_bf16(
+    _call("gfs_linear_bf16", 1, 
         _ptr(x_act), x_act.shape[1], x_kb0, kb_count, _ptr(w_packed), _ptr(shift), nout, act, B, N,
         _ptr(y_act), 0 if y_act is None else y_act.shape[1], y_kb0,
-        _ptr(y_cm), 0 if y_cm is None else y_cm.stride(0), _stream()), "gfs_linear_bf16")
+        _ptr(y_cm), 0 if y_cm is None else y_cm.stride(0), _stream())
 
 
 def gw_project(ec: torch.Tensor, gp_l2t: torch.Tensor, G: int, cosine_act: Optional[torch.Tensor] = None, kb0: int = 0,
@@ -122,9 +141,8 @@ def gw_project(ec: torch.Tensor, gp_l2t: torch.Tensor, G: int, cosine_act: Optio
     Gp = gp_l2t.shape[1]
     assign = torch.empty(B, N, dtype=torch.int32, device=ec.device)
     cm = torch.empty(B, G, N, dtype=torch.float32, device=ec.device) if want_cm else None
-    check(lib().gfs_gw_project(_ptr(ec), ec.stride(0), B, D, N, _ptr(gp_l2t), G, Gp, _ptr(cosine_act),
-                               0 if cosine_act is None else cosine_act.shape[1], kb0, _ptr(cm), _ptr(assign), _stream()),
-          "gfs_gw_project")
+    _call("gfs_gw_project", 1, _ptr(ec), ec.stride(0), B, D, N, _ptr(gp_l2t), G, Gp, _ptr(cosine_act),
+                               0 if cosine_act is None else cosine_act.shape[1], kb0, _ptr(cm), _ptr(assign), _stream())
     return assign, cm
 
 
@@ -143,8 +161,8 @@ def cos_logits(feat: torch.Tensor, proto_l2: torch.Tensor, coding: Optional[torc
         coding = coding.contiguous().float()
         G = coding.shape[1]
         assert coding.shape[0] == CLS and assignment is not None and assignment.dtype == torch.int32
-    check(lib().gfs_cos_logits(_ptr(feat), feat.stride(0), B, D, N, _ptr(proto_l2), PB, CLS, _ptr(coding), G,
-                               _ptr(assignment), float(th), _ptr(out), _stream()), "gfs_cos_logits")
+    _call("gfs_cos_logits", 1, _ptr(feat), feat.stride(0), B, D, N, _ptr(proto_l2), PB, CLS, _ptr(coding), G,
+                               _ptr(assignment), float(th), _ptr(out), _stream())
     return out
 
 
@@ -158,8 +176,8 @@ def softmax_pool(logits: torch.Tensor, feat: torch.Tensor) -> torch.Tensor:
     stats = torch.empty(B * CLS * 2, dtype=torch.float32, device=dev)
     partial = torch.empty(B * ((N + 127) // 128) * CLS * D, dtype=torch.float32, device=dev)
     out = torch.empty(B, CLS, D, dtype=torch.float32, device=dev)
-    check(lib().gfs_softmax_pool(_ptr(logits), _ptr(feat), feat.stride(0), B, CLS, D, N, _ptr(stats), _ptr(partial),
-                                 _ptr(out), _stream()), "gfs_softmax_pool")
+    _call("gfs_softmax_pool", 3, _ptr(logits), _ptr(feat), feat.stride(0), B, CLS, D, N, _ptr(stats), _ptr(partial),
+                                 _ptr(out), _stream())
     return out
 
 
@@ -172,8 +190,7 @@ def kmeans_assign(xt: torch.Tensor, centers_t: torch.Tensor, K: int, want_score:
     cnorm = torch.empty(Kp, dtype=torch.float32, device=xt.device)
     labels = torch.empty(n, dtype=torch.int32, device=xt.device)
     score = torch.empty(n, dtype=torch.float32, device=xt.device) if want_score else None
-    check(lib().gfs_kmeans_assign(_ptr(xt), n, D, _ptr(centers_t), K, Kp, _ptr(cnorm), _ptr(labels), _ptr(score), _stream()),
-          "gfs_kmeans_assign")
+    _call("gfs_kmeans_assign", 2, _ptr(xt), n, D, _ptr(centers_t), K, Kp, _ptr(cnorm), _ptr(labels), _ptr(score), _stream())
     return (labels, score) if want_score else labels
 
 
@@ -189,6 +206,6 @@ def kmeans_accumulate(X: torch.Tensor, labels: torch.Tensor, K: int, n_valid: Op
     pcount = torch.empty(P * K, dtype=torch.int32, device=X.device)
     sums = torch.empty(K, D, dtype=torch.float64, device=X.device)
     counts = torch.empty(K, dtype=torch.int64, device=X.device)
-    check(lib().gfs_kmeans_accumulate(_ptr(X), n, D, _ptr(labels), K, _ptr(partial), _ptr(pcount), _ptr(sums), _ptr(counts),
-                                      _stream()), "gfs_kmeans_accumulate")
+    _call("gfs_kmeans_accumulate", 2, _ptr(X), n, D, _ptr(labels), K, _ptr(partial), _ptr(pcount), _ptr(sums), _ptr(counts),
+                                      _stream())
     return sums, counts
