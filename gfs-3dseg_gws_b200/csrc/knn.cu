@@ -3,10 +3,12 @@
 // One CTA owns 64 query points of one block and streams all N candidates in tiles of 128 through shared memory
 // (cp.async, double buffered).  Distances are formed in registers by the shared FFMA core in the pinned order
 //     dot = fma chain over c ascending;  d = fmaf(2, dot, -xx_i) - xx_j
-// and dropped into a 64x128 shared tile; each warp then scans its 16 rows against the row's current k-th best
-// (a one-compare filter that rejects ~97 % of candidates after the first tile) and inserts survivors into a sorted
-// 32-entry list held one entry per lane (ballot/popc rank + shfl_up shift).  Order: larger d first, ties -> smaller
-// index.  The N x N matrix never leaves the SM.
+// and dropped into a 64x128 shared tile; each warp then scans its 16 rows against the row's threshold (the k-th best at
+// the last merge: a one-compare filter that rejects ~97 % of candidates after the first tile) and appends survivors to a
+// 32-entry per-row buffer.  Only when the buffer would overflow (about 4 times per row at N=2048) is it merged into the
+// row's sorted list: a warp-wide bitonic sort of 64-bit keys (orderable distance << 32 | ~index) followed by a bitonic
+// top-32 merge -- 20 compare-exchange stages, no serial insertion.  Order: larger d first, ties -> smaller index.
+// The N x N matrix never leaves the SM.
 #include "fp32_tile.cuh"
 
 namespace gfs {
@@ -15,12 +17,57 @@ constexpr int KNN_KC = 32;   // channels per pipeline stage
 
 struct KnnSmem {
     float Bs[2][KNN_KC * T_COLS];   // 32 KB
-    float Ds[T_ROWS * T_COLS];      // 32 KB
-    float Ld[T_ROWS * 32];          // 8 KB   sorted best distances, one row of 32 per query
-    int Li[T_ROWS * 32];            // 8 KB
-    float tau[T_ROWS];
+    float Ds[T_ROWS * T_COLS];      // 32 KB  distance tile of the current candidate tile
+    uint2 list[T_ROWS * 32];        // 16 KB  per query: 32 best so far, sorted descending; (x = orderable distance, y = ~index)
+    uint2 buf[T_ROWS * 32];         // 16 KB  per query: raw (distance bits, index) appended since the last merge
+    float tau[T_ROWS];              // distance of the k-th best at the last merge (filter threshold, never decreases)
+    int fill[T_ROWS];
     // followed by As[C][64]
 };
+
+typedef unsigned long long u64;
+
+// fp32 -> uint32 whose unsigned order equals the float order
+__device__ __forceinline__ uint32_t ord_key(float d) {
+    const uint32_t u = __float_as_uint(d);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord_val(uint32_t u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+// compare-exchange with the lane `lane ^ j2`: keep the larger key if keep_max else the smaller
+__device__ __forceinline__ u64 cmpex(u64 k, int j2, bool keep_max) {
+    const u64 o = __shfl_xor_sync(0xffffffffu, k, j2);
+    return (keep_max == (k > o)) ? k : o;
+}
+
+// Merge the row's append buffer into its sorted list (one warp; key = (orderable d << 32) | ~index, larger = better, so
+// equal distances order by ascending index).  Bitonic sort of the <=32 buffered keys, then the classic
+// "max(list, reverse(sorted buffer))" + 5-stage bitonic merge keeps the 32 largest of the union, sorted descending.
+__device__ __forceinline__ float knn_flush(KnnSmem& s, int q, int lane, int fill, int k) {
+    const uint2 raw = s.buf[q * 32 + lane];
+    u64 key = lane < fill ? (((u64)ord_key(__uint_as_float(raw.x)) << 32) | (u64)(~raw.y)) : 0ull;
+#pragma unroll
+    for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+#pragma unroll
+        for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+            const bool lower = (lane & j2) == 0;
+            const bool desc = (lane & k2) == 0;
+            key = cmpex(key, j2, lower == desc);
+        }
+    }
+    const uint2 l2 = s.list[q * 32 + lane];
+    const u64 lst = ((u64)l2.x << 32) | (u64)l2.y;
+    const u64 rev = __shfl_sync(0xffffffffu, key, 31 - lane);
+    key = lst > rev ? lst : rev;
+#pragma unroll
+    for (int j2 = 16; j2 > 0; j2 >>= 1) key = cmpex(key, j2, (lane & j2) == 0);
+    s.list[q * 32 + lane] = make_uint2((uint32_t)(key >> 32), (uint32_t)key);
+    const uint32_t kth = __shfl_sync(0xffffffffu, (uint32_t)(key >> 32), k - 1);
+    const float tau = kth ? ord_val(kth) : -INFINITY;
+    if (lane == 0) s.tau[q] = tau;
+    return tau;
+}
 
 __global__ void __launch_bounds__(T_THREADS, 2)
 knn_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int k, const float* __restrict__ sqnorm,
@@ -34,16 +81,17 @@ knn_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int k, co
     const int b = blockIdx.y, q0 = blockIdx.x * T_ROWS;
     const float* xb = x + (int64_t)b * bstride;
     const float* xxb = sqnorm + (int64_t)b * N;
+    const unsigned lt_mask = (1u << lane) - 1u;
 
     const int nch = (C + KNN_KC - 1) / KNN_KC;
     const int ntiles = (N + T_COLS - 1) / T_COLS;
     const int S = ntiles * nch;
 
-    for (int i = tid; i < T_ROWS * 32; i += T_THREADS) {
-        s.Ld[i] = -INFINITY;
-        s.Li[i] = 0x7fffffff;
+    for (int i = tid; i < T_ROWS * 32; i += T_THREADS) s.list[i] = make_uint2(0u, 0u);
+    if (tid < T_ROWS) {
+        s.tau[tid] = -INFINITY;
+        s.fill[tid] = 0;
     }
-    if (tid < T_ROWS) s.tau[tid] = -INFINITY;
 
     // query panel (all channels) + stage 0
     load_panel_async(As, T_ROWS, xb, N, C, q0, N, tid);
@@ -106,7 +154,10 @@ knn_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int k, co
             }
             __syncthreads();
 
-            // ---- selection: warp w owns rows w*16 .. w*16+15, one sorted list entry per lane ----
+            // ---- selection: warp w owns rows w*16 .. w*16+15.  Candidates not below the row's threshold are appended
+            // to the row's buffer; the buffer is merged into the sorted list only when it would overflow. ----
+            const bool full_tile = j0 + T_COLS <= N;
+#pragma unroll 2
             for (int rr = 0; rr < 16; ++rr) {
                 const int q = warp * 16 + rr;
                 const float4 dv4 = *reinterpret_cast<const float4*>(s.Ds + q * T_COLS + lane * 4);
@@ -115,49 +166,44 @@ knn_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int k, co
                 const int jb = j0 + lane * 4;
                 bool p[4];
 #pragma unroll
-                for (int v = 0; v < 4; ++v) p[v] = (dv[v] >= tau) && (jb + v < N);
+                for (int v = 0; v < 4; ++v) p[v] = (dv[v] >= tau) && (full_tile || jb + v < N);
                 if (__ballot_sync(0xffffffffu, p[0] | p[1] | p[2] | p[3]) == 0u) continue;
-                float ld = s.Ld[q * 32 + lane];
-                int li = s.Li[q * 32 + lane];
+                int fill = s.fill[q];
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
                     unsigned m = __ballot_sync(0xffffffffu, p[v]);
-                    while (m) {
-                        const int src = __ffs(m) - 1;
-                        m &= m - 1;
-                        const float cd = __shfl_sync(0xffffffffu, dv[v], src);
-                        if (cd < tau) continue;   // tau tightened since the filter was evaluated
-                        const int cj = j0 + src * 4 + v;
-                        const bool better = (ld > cd) || (ld == cd && li < cj);
-                        const int pos = __popc(__ballot_sync(0xffffffffu, better));
-                        const float ud = __shfl_up_sync(0xffffffffu, ld, 1);
-                        const int ui = __shfl_up_sync(0xffffffffu, li, 1);
-                        if (lane == pos) {
-                            ld = cd;
-                            li = cj;
-                        } else if (lane > pos) {
-                            ld = ud;
-                            li = ui;
-                        }
-                        tau = __shfl_sync(0xffffffffu, ld, k - 1);
+                    if (m == 0u) continue;
+                    int cnt = __popc(m);
+                    if (fill + cnt > 32) {
+                        tau = knn_flush(s, q, lane, fill, k);
+                        fill = 0;
+                        __syncwarp();
+#pragma unroll
+                        for (int w = v; w < 4; ++w) p[w] = p[w] && (dv[w] >= tau);
+                        m = __ballot_sync(0xffffffffu, p[v]);
+                        cnt = __popc(m);
                     }
+                    if (p[v]) s.buf[q * 32 + fill + __popc(m & lt_mask)] = make_uint2(__float_as_uint(dv[v]), (uint32_t)(jb + v));
+                    fill += cnt;
                 }
-                s.Ld[q * 32 + lane] = ld;
-                s.Li[q * 32 + lane] = li;
-                if (lane == 0) s.tau[q] = tau;
+                if (lane == 0) s.fill[q] = fill;
             }
         }
         __syncthreads();
     }
 
-    // ---- write the k nearest (sorted nearest first) ----
+    // ---- final merge and write-out: the k nearest, sorted nearest first ----
     for (int rr = 0; rr < 16; ++rr) {
         const int q = warp * 16 + rr;
+        const int fill = s.fill[q];
+        if (fill > 0) knn_flush(s, q, lane, fill, k);
+        __syncwarp();
         const int n = q0 + q;
         if (n < N && lane < k) {
+            const uint2 e = s.list[q * 32 + lane];
             const int64_t o = ((int64_t)b * N + n) * k + lane;
-            idx_out[o] = s.Li[q * 32 + lane];
-            if (dist_out) dist_out[o] = s.Ld[q * 32 + lane];
+            idx_out[o] = (int32_t)(~e.y);
+            if (dist_out) dist_out[o] = ord_val(e.x);
         }
     }
 }

@@ -18,6 +18,7 @@ SIGNATURES = {
     "gfs_pack_weight_bf16": [_p, _p, _i, _i, _p, _p],
     "gfs_cm_to_act": [_p, _i64, _i, _i, _i, _p, _i, _i, _p],
     "gfs_linear_bf16": [_p, _i, _i, _i, _p, _p, _i, _i, _i, _i, _p, _i, _i, _p, _i64, _p],
+    "gfs_attention_fwd": [_p, _i, _i, _i, _i, _f, _p, _i64, _p, _i, _i, _p],
     "gfs_gw_project": [_p, _i64, _i, _i, _i, _p, _i, _i, _p, _i, _i, _p, _p, _p],
     "gfs_cos_logits": [_p, _i64, _i, _i, _i, _p, _i, _i, _p, _i, _p, _f, _p, _p],
     "gfs_softmax_pool": [_p, _p, _i64, _i, _i, _i, _i, _p, _p, _p, _p],

@@ -47,9 +47,11 @@ def act_rows(M: int) -> int:
     return (M + 127) // 128 * 128
 
 
-def new_act(M: int, kblocks: int, device) -> torch.Tensor:
-    """zeroed bf16 activation matrix in the tiled SWIZZLE_128B layout: [M/128][kblocks] tiles of 16 KiB"""
-    return torch.zeros(act_rows(M) // 128, kblocks, 128 * 64, dtype=torch.bfloat16, device=device)
+def new_act(M: int, kblocks: int, device, zero: bool = True) -> torch.Tensor:
+    """bf16 activation matrix in the tiled SWIZZLE_128B layout: [M/128][kblocks] tiles of 16 KiB.  zero=False skips the
+    memset when the caller's kernels overwrite every block (padding rows are still zeroed: they must not hold NaN/Inf)."""
+    alloc = torch.empty if (not zero and M % 128 == 0) else torch.zeros
+    return alloc(act_rows(M) // 128, kblocks, 128 * 64, dtype=torch.bfloat16, device=device)
 
 
 def act_to_dense(act: torch.Tensor, M: int) -> torch.Tensor:
@@ -130,6 +132,16 @@ def linear(x_act: torch.Tensor, x_kb0: int, kb_count: int, w_packed: torch.Tenso
         _ptr(x_act), x_act.shape[1], x_kb0, kb_count, _ptr(w_packed), _ptr(shift), nout, act, B, N,
         _ptr(y_act), 0 if y_act is None else y_act.shape[1], y_kb0,
         _ptr(y_cm), 0 if y_cm is None else y_cm.stride(0), _stream())
+
+
+def attention(qkv_act: torch.Tensor, kb_q: int, B: int, N: int, scale: float, y_cm: Optional[torch.Tensor] = None,
+              y_act: Optional[torch.Tensor] = None, y_kb: int = 0):
+    """flash-style softmax(q^T k * scale) v on tcgen05; q/k/v are three 64-column blocks of one bf16 act matrix"""
+    _need_cuda(qkv_act, y_cm, y_act)
+    if y_cm is not None:
+        assert y_cm.stride(2) == 1 and y_cm.stride(1) == N and y_cm.shape[1] == 64
+    _call("gfs_attention_fwd", 1, _ptr(qkv_act), qkv_act.shape[1], kb_q, B, N, float(scale), _ptr(y_cm),
+          0 if y_cm is None else y_cm.stride(0), _ptr(y_act), 0 if y_act is None else y_act.shape[1], y_kb, _stream())
 
 
 def gw_project(ec: torch.Tensor, gp_l2t: torch.Tensor, G: int, cosine_act: Optional[torch.Tensor] = None, kb0: int = 0,

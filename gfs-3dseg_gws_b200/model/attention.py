@@ -1,13 +1,11 @@
 """Self-attention block -- drop-in for the reference's model/attention.py:10-48 ("adjacent").
 
-q/k/v 1x1 maps run as ONE fused gfs_linear_bf16 call (256 -> 3*64).  The N x N softmax(q^T k / sqrt(d)) v product is the
-"next" row N1 of the scope table: until the flash-style tcgen05 kernel lands it is evaluated by
-torch.nn.functional.scaled_dot_product_attention (a LIBRARY kernel, flagged as such in DESIGN.md) -- the N x N matrix
-is still never materialised.
+q/k/v 1x1 maps run as ONE fused gfs_linear_bf16 call (256 -> 3*64) whose bf16 output tiles are consumed in place by
+gfs_attention_fwd, a flash-style tcgen05 kernel (csrc/attention.cu): the N x N softmax(q^T k / sqrt(d)) matrix is never
+materialised.  Eval mode only (dropout is the identity); N must be a multiple of 128.
 """
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from gfs3d import ops
 
@@ -37,23 +35,24 @@ class SelfAttention(nn.Module):
             self._key = key
         return self._wp
 
-    def forward_fused(self, x_act, B, N):
-        """x_act: bf16 act tiles (B*N, in_channel) -> y (B, out_channel, N) fp32 channel-major"""
+    def forward_fused(self, x_act, B, N, y_cm=None, y_act=None, y_kb=0):
+        """x_act: bf16 act tiles (B*N, in_channel).  Writes y (B, 64, N) fp32 cm and/or one bf16 act block."""
         if self.training:
             raise NotImplementedError("SelfAttention training-mode forward is not built yet in the B200 path")
+        if self.out_channel != 64:
+            raise NotImplementedError("the tcgen05 attention kernel is built for out_channel = 64")
         wp = self._prepare(x_act.device)
-        d = self.out_channel
-        qkv = torch.empty(B, 3 * d, N, dtype=torch.float32, device=x_act.device)
-        ops.linear(x_act, 0, self.in_channel // 64, wp, None, 3 * d, ops.ACT_NONE, B, N, y_cm=qkv)
-        q, k, v = (qkv[:, i * d:(i + 1) * d, :].transpose(1, 2).to(torch.bfloat16).unsqueeze(1) for i in range(3))
-        y = F.scaled_dot_product_attention(q, k, v, scale=1.0 / self.temperature)       # (B, 1, N, d)  library kernel
-        return y.squeeze(1).transpose(1, 2).float().contiguous()
+        qkv = ops.new_act(B * N, 3, x_act.device, zero=False)
+        ops.linear(x_act, 0, self.in_channel // 64, wp, None, 192, ops.ACT_NONE, B, N, y_act=qkv)
+        ops.attention(qkv, 0, B, N, 1.0 / self.temperature, y_cm=y_cm, y_act=y_act, y_kb=y_kb)
 
     def forward(self, x):
         """(B, in_channel, N) -> (B, out_channel, N)"""
         if x.dtype != torch.float32 or x.stride(2) != 1 or x.stride(1) != x.shape[2]:
             x = x.float().contiguous()
         B, C, N = x.shape
-        xa = ops.new_act(B * N, C // 64, x.device)
+        xa = ops.new_act(B * N, C // 64, x.device, zero=False)
         ops.cm_to_act(x, xa, 0)
-        return self.forward_fused(xa, B, N)
+        y = torch.empty(B, self.out_channel, N, dtype=torch.float32, device=x.device)
+        self.forward_fused(xa, B, N, y_cm=y)
+        return y

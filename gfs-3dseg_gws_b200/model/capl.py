@@ -91,11 +91,11 @@ class mpti_net_Point_GeoAsWeight_v2(nn.Module):
         x = _cm(x)
         B, _, N = x.shape
         M = B * N
-        fus_in = ops.new_act(M, hd["kblocks"], x.device)                 # [level1 | att | level3 | cosine_feat | pad]
+        fus_in = ops.new_act(M, hd["kblocks"], x.device, zero=False)                 # [level1 | att | level3 | cosine_feat | pad]
         enc = self.encoder.forward_fused(x, want_lvl2_cm=False, level1_act=fus_in, level1_kb=0)
         semantic = torch.empty(B, 192, N, dtype=torch.float32, device=x.device) if need_semantic else None
-        att = self.att_learner.forward_fused(enc.lvl2_act, B, N)                                    # (B, 64, N) fp32
-        ops.cm_to_act(att, fus_in, 1)
+        self.att_learner.forward_fused(enc.lvl2_act, B, N, y_act=fus_in, y_kb=1,
+                                       y_cm=semantic[:, 64:128, :] if need_semantic else None)
         self.base_learner.forward_fused(enc.lvl2_act, B, N, y_act=fus_in, y_kb0=2,
                                         y_cm=semantic[:, 128:192, :] if need_semantic else None)
         assignment, _ = ops.gw_project(enc.ec, hd["gp_l2t"], hd["G"], cosine_act=fus_in, kb0=3)
@@ -103,7 +103,6 @@ class mpti_net_Point_GeoAsWeight_v2(nn.Module):
         ops.linear(fus_in, 0, hd["kblocks"], hd["wp"], hd["shift"], hd["nout"], ops.ACT_LRELU02, B, N, y_cm=point_feat)
         if need_semantic:
             semantic[:, 0:64, :].copy_(enc.ec[:, 0:64, :])
-            semantic[:, 64:128, :].copy_(att)
         return point_feat, assignment, semantic
 
     def getFeatures(self, x, segment_label=None):

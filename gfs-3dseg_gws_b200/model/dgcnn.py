@@ -189,7 +189,7 @@ class DGCNN(nn.Module):
         M = B * N
         L = self.n_edgeconv
         ec = torch.empty(B, 64 * L, N, dtype=torch.float32, device=x.device)
-        cat_act = ops.new_act(M, L, x.device)
+        cat_act = ops.new_act(M, L, x.device, zero=False)
         xin = x
         for i, (wt, bias, w2p, t2) in enumerate(layers):
             idx = ops.knn(xin, self.k)
@@ -202,7 +202,7 @@ class DGCNN(nn.Module):
         lvl2_cm = None
         for j, (wp, shift, nout, kb) in enumerate(mlp):
             last = j == len(mlp) - 1
-            nxt = ops.new_act(M, nout // 64, x.device)
+            nxt = ops.new_act(M, nout // 64, x.device, zero=False)
             if last and want_lvl2_cm:
                 lvl2_cm = torch.empty(B, nout, N, dtype=torch.float32, device=x.device)
             ops.linear(cur, 0, kb, wp, shift, nout, ops.ACT_LRELU02, B, N, y_act=nxt, y_cm=lvl2_cm if last else None)
@@ -256,7 +256,7 @@ class BaseLearner(nn.Module):
             if last:
                 ops.linear(cur, 0, kb, wp, shift, nout, ops.ACT_NONE, B, N, y_act=y_act, y_kb0=y_kb0, y_cm=y_cm)
             else:
-                nxt = ops.new_act(B * N, nout // 64, x_act.device)
+                nxt = ops.new_act(B * N, nout // 64, x_act.device, zero=False)
                 ops.linear(cur, 0, kb, wp, shift, nout, ops.ACT_RELU, B, N, y_act=nxt)
                 cur = nxt
 
@@ -266,7 +266,7 @@ class BaseLearner(nn.Module):
         B, C, N = x.shape
         if C % 64 != 0:
             raise NotImplementedError("BaseLearner input width must be a multiple of 64 in the B200 build")
-        xa = ops.new_act(B * N, C // 64, x.device)
+        xa = ops.new_act(B * N, C // 64, x.device, zero=False)
         ops.cm_to_act(x, xa, 0)
         y = torch.empty(B, self.convs[-1][0].weight.shape[0], N, dtype=torch.float32, device=x.device)
         self.forward_fused(xa, B, N, y_cm=y)

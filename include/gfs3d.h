@@ -103,6 +103,13 @@ int gfs_linear_bf16(const void* x_act, int x_kblocks, int x_kb0, int kb_count,
                     void* y_act, int y_kblocks, int y_kb0,
                     float* y_cm, int64_t y_bstride, void* stream);
 
+/* ---- self-attention: model/attention.py:43-46  y = softmax(q^T k * scale) v^T, flash-style on tcgen05 ----------------
+ * qkv_act: bf16 act matrix holding three consecutive 64-column blocks [q | k | v] starting at block kb_q (the output of
+ * one fused gfs_linear_bf16 call over the concatenated q/k/v weights).  d = 64, one head, N % 128 == 0.
+ * The N x N score matrix is never written to memory.  Outputs as in gfs_edgeconv_fwd (fp32 cm and/or one bf16 act block). */
+int gfs_attention_fwd(const void* qkv_act, int kblocks, int kb_q, int B, int N, float scale,
+                      float* y_cm, int64_t y_bstride, void* y_act, int y_kblocks, int y_kb, void* stream);
+
 /* ---- geometric-word projection: model/capl.py:344-353 -----------------------------------------------------------
  * cos[g] = <gp_l2[g], ec> / max(|ec|, 1e-12); cosine_feat = softmax_g(10 cos); assignment = argmax_g (first max).
  * fp32 CUDA-core contraction in a pinned order (assignment parity), fused norm/softmax/argmax.

@@ -42,3 +42,45 @@ def test_assign_ties_lowest_index():
     xt = torch.zeros(8, 64, device="cuda")
     ct = torch.zeros(8, 8, device="cuda")
     assert int(ops.kmeans_assign(xt, ct, 5).max()) == 0
+
+
+def _fixture_X(g):
+    rs = np.random.RandomState(int(g["seed"]))
+    n, D, K = int(g["n"]), int(g["D"]), int(g["K"])
+    cent = rs.randn(K, D).astype(np.float32)
+    lab = rs.randint(0, K, size=n)
+    return (cent[lab] + 0.35 * rs.randn(n, D)).astype(np.float32)
+
+
+@pytest.mark.parametrize("name", ["kmeans_n6000_k150", "kmeans_n2000_k20"])
+def test_kmeans_dropin_vs_sklearn_fixture(golden, name):
+    """KMeans(init=<array>).fit(X).labels_ as get_basis.py:210-212 uses it, vs labels produced by sklearn 1.9.0 itself"""
+    from gfs3d.kmeans import KMeans
+    g = golden(name)
+    X = _fixture_X(g)
+    km = KMeans(n_clusters=int(g["K"]), init=g["init"], n_init=1).fit(X)
+    assert km.labels_.shape == (X.shape[0],) and km.labels_.dtype == np.int32
+    assert (km.labels_ == g["labels"]).mean() >= 0.999
+    assert np.abs(km.cluster_centers_ - g["centers"]).max() <= 1e-4
+    assert km.n_iter_ == int(g["n_iter"])
+    # and bit-exact against the pinned-order oracle's Lloyd loop
+    o_labels, o_centers, o_it = O.lloyd_reference(X, g["init"])
+    assert np.array_equal(km.labels_, o_labels)
+    # downstream of the labels: Kmean2Proto + SVD reconstruction (get_basis.py:27-71) reproduces the reference basis
+    basis = O.svd_reconstruct(O.kmean_to_proto(X, km.labels_, int(g["K"])))
+    assert np.abs(basis - g["basis"]).max() <= 1e-4
+
+
+def test_kmeans_plusplus_runs_and_is_a_fixed_point():
+    from gfs3d.kmeans import KMeans
+    X, _ = _mixture(5000, 192, 150, seed=1)
+    km = KMeans(n_clusters=150, init="k-means++", random_state=0).fit(X)
+    assert len(np.unique(km.labels_)) == 150
+    # idempotence: restarting from the converged centres reproduces the labels in one step
+    km2 = KMeans(n_clusters=150, init=km.cluster_centers_).fit(X)
+    assert (km2.labels_ == km.labels_).mean() >= 0.999
+    # size-independent property: every point is assigned to its nearest centre (checked in fp64)
+    d = ((X[:500, None, :].astype(np.float64) - km.cluster_centers_[None].astype(np.float64)) ** 2).sum(-1)
+    best = d.min(1)
+    chosen = d[np.arange(500), km.labels_[:500]]
+    assert (chosen <= best + 1e-4 * np.abs(best)).all()

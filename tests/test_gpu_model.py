@@ -189,3 +189,43 @@ def test_training_mode_raises_instead_of_falling_back(golden_sd):
     m = _load_dgcnn(golden_sd).train()
     with pytest.raises(NotImplementedError):
         m(torch.randn(1, 9, 128, device="cuda"))
+
+
+@pytest.mark.parametrize("B,N", [(2, 256), (1, 2048), (3, 128), (2, 1024)])
+def test_attention_tcgen05_vs_reference(B, N, golden_sd):
+    """model/attention.py:32-48 (eval): fused q/k/v linear + flash-style tcgen05 attention vs the oracle"""
+    from model.attention import SelfAttention
+    ops = _ops()
+    sd = golden_sd("gfs_s3dis_weights")
+    att = SelfAttention(256, 64)
+    att.load_state_dict({k[len("att_learner."):]: v for k, v in sd.items() if k.startswith("att_learner.")})
+    att = att.cuda().eval()
+    g = torch.Generator().manual_seed(N)
+    sd64 = {k: v.double() for k, v in sd.items()}
+    for gain in (1.0, 6.0):            # activation-scale inputs (what the model feeds it) and a peaked-softmax stress
+        x = torch.randn(B, 256, N, generator=g) * gain
+        with torch.no_grad():
+            y = att(x.cuda())
+        if gain == 1.0:
+            ref = O.self_attention(sd64, "att_learner", x.double())
+            tol = TOL_BF16
+        else:
+            # peaked softmax amplifies the bf16 rounding of q/k themselves; validate the kernel's arithmetic against
+            # the same formula evaluated in fp64 on the bf16-rounded x, q, k, v it actually consumes
+            xb = x.bfloat16().double()
+            w = torch.cat([sd64[f"att_learner.{n}_map.weight"] for n in "qkv"]).bfloat16().double()
+            qkv = torch.nn.functional.conv1d(xb, w).bfloat16().double()
+            q, kk, v = qkv[:, :64], qkv[:, 64:128], qkv[:, 128:]
+            attn = torch.softmax(torch.matmul(q.transpose(1, 2) / 8.0, kk), dim=-1)
+            ref = torch.matmul(attn, v.transpose(1, 2)).transpose(1, 2)
+            tol = 1e-2
+        err = rel_err(y.cpu(), ref)
+        print(f"attention B={B} N={N} gain={gain}: rel err {err:.3e}")
+        assert err <= tol
+
+
+def test_attention_rejects_ragged_n():
+    from model.attention import SelfAttention
+    att = SelfAttention(256, 64).cuda().eval()
+    with pytest.raises(RuntimeError, match="multiple of 128"):
+        att(torch.randn(1, 256, 320, device="cuda"))
