@@ -1,7 +1,9 @@
 // knn.cu -- fused fp32 kNN graph (replaces model/dgcnn.py:17-23: matmul + 4 elementwise passes + topk).
 //
 // One CTA owns 64 query points of one block and streams all N candidates in tiles of 128 through shared memory
-// (cp.async, double buffered).  Distances are formed in registers by the shared FFMA core in the pinned order
+// (cp.async, double buffered).  The CTA is warp-specialised: warps 0-3 form distance tiles with the shared FFMA core,
+// warps 4-7 run the top-k selection on the previous tile (two distance tiles in flight, mbarrier hand-off), so the
+// FMA pipe and the ALU/shuffle-bound selection overlap.  Distances are formed in registers in the pinned order
 //     dot = fma chain over c ascending;  d = fmaf(2, dot, -xx_i) - xx_j
 // and dropped into a 64x128 shared tile; each warp then scans its 16 rows against the row's threshold (the k-th best at
 // the last merge: a one-compare filter that rejects ~97 % of candidates after the first tile) and appends survivors to a
@@ -13,15 +15,19 @@
 
 namespace gfs {
 
-constexpr int KNN_KC = 32;   // channels per pipeline stage
+constexpr int KNN_KC = 32;        // channels per pipeline stage
+constexpr int KNN_SEL_WARPS = 8;
+constexpr int KNN_ROWS_PER_SEL = T_ROWS / KNN_SEL_WARPS;
+constexpr int KNN_THREADS = 128 + 32 * KNN_SEL_WARPS;  // warps 0-3: FFMA producers of distance tiles; the rest: selection consumers
 
 struct KnnSmem {
-    float Bs[2][KNN_KC * T_COLS];   // 32 KB
-    float Ds[T_ROWS * T_COLS];      // 32 KB  distance tile of the current candidate tile
+    float Bs[2][KNN_KC * T_COLS];   // 32 KB  candidate panels (cp.async double buffer)
+    float Ds[2][T_ROWS * T_COLS];   // 64 KB  distance tiles, produced by the FFMA warps, consumed by the selection warps
     uint2 list[T_ROWS * 32];        // 16 KB  per query: 32 best so far, sorted descending; (x = orderable distance, y = ~index)
     uint2 buf[T_ROWS * 32];         // 16 KB  per query: raw (distance bits, index) appended since the last merge
     float tau[T_ROWS];              // distance of the k-th best at the last merge (filter threshold, never decreases)
     int fill[T_ROWS];
+    uint64_t ds_full[2], ds_empty[2];
     // followed by As[C][64]
 };
 
@@ -69,7 +75,7 @@ __device__ __forceinline__ float knn_flush(KnnSmem& s, int q, int lane, int fill
     return tau;
 }
 
-__global__ void __launch_bounds__(T_THREADS, 2)
+__global__ void __launch_bounds__(KNN_THREADS, 1)
 knn_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int k, const float* __restrict__ sqnorm,
            int32_t* __restrict__ idx_out, float* __restrict__ dist_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -77,133 +83,169 @@ knn_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int k, co
     float* As = reinterpret_cast<float*>(smem_raw + sizeof(KnnSmem));
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int ty = tid >> 4, tx = tid & 15;
     const int b = blockIdx.y, q0 = blockIdx.x * T_ROWS;
-    const float* xb = x + (int64_t)b * bstride;
-    const float* xxb = sqnorm + (int64_t)b * N;
-    const unsigned lt_mask = (1u << lane) - 1u;
-
-    const int nch = (C + KNN_KC - 1) / KNN_KC;
     const int ntiles = (N + T_COLS - 1) / T_COLS;
-    const int S = ntiles * nch;
 
-    for (int i = tid; i < T_ROWS * 32; i += T_THREADS) s.list[i] = make_uint2(0u, 0u);
+    for (int i = tid; i < T_ROWS * 32; i += KNN_THREADS) s.list[i] = make_uint2(0u, 0u);
     if (tid < T_ROWS) {
         s.tau[tid] = -INFINITY;
         s.fill[tid] = 0;
     }
-
-    // query panel (all channels) + stage 0
-    load_panel_async(As, T_ROWS, xb, N, C, q0, N, tid);
-    {
-        const int c1 = C < KNN_KC ? C : KNN_KC;
-        load_panel_async(s.Bs[0], T_COLS, xb, N, c1, 0, N, tid);
+    if (tid == 0) {
+        mbar_init(&s.ds_full[0], 128);
+        mbar_init(&s.ds_full[1], 128);
+        mbar_init(&s.ds_empty[0], 32 * KNN_SEL_WARPS);
+        mbar_init(&s.ds_empty[1], 32 * KNN_SEL_WARPS);
+        mbar_fence_init();
     }
-    cp_async_commit();
+    __syncthreads();
 
-    float xq[8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        const int q = q0 + ty * 8 + r;
-        xq[r] = q < N ? xxb[q] : 0.0f;
-    }
+    if (warp < 4) {
+        // ======================= FFMA warps: distance tiles in the pinned order =======================
+        const int ty = tid >> 4, tx = tid & 15;
+        const float* xb = x + (int64_t)b * bstride;
+        const float* xxb = sqnorm + (int64_t)b * N;
+        const int nch = (C + KNN_KC - 1) / KNN_KC;
+        const int S = ntiles * nch;
 
-    float acc[8][8];
-    for (int st = 0; st < S; ++st) {
-        const int t = st / nch, ch = st - t * nch;
-        if (st + 1 < S) {
-            const int t1 = (st + 1) / nch, ch1 = (st + 1) - t1 * nch;
-            const int c0 = ch1 * KNN_KC;
-            const int cn = (C - c0) < KNN_KC ? (C - c0) : KNN_KC;
-            load_panel_async(s.Bs[(st + 1) & 1], T_COLS, xb + (int64_t)c0 * N, N, cn, t1 * T_COLS, N, tid);
-            cp_async_commit();
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
+        load_panel_async(As, T_ROWS, xb, N, C, q0, N, tid);
+        {
+            const int c1 = C < KNN_KC ? C : KNN_KC;
+            load_panel_async(s.Bs[0], T_COLS, xb, N, c1, 0, N, tid);
         }
-        __syncthreads();
+        cp_async_commit();
 
-        if (ch == 0) {
+        float xq[8];
 #pragma unroll
-            for (int r = 0; r < 8; ++r)
-#pragma unroll
-                for (int c = 0; c < 8; ++c) acc[r][c] = 0.0f;
+        for (int r = 0; r < 8; ++r) {
+            const int q = q0 + ty * 8 + r;
+            xq[r] = q < N ? xxb[q] : 0.0f;
         }
-        const int c0 = ch * KNN_KC;
-        const int cn = (C - c0) < KNN_KC ? (C - c0) : KNN_KC;
-        tile_fma(As + c0 * T_ROWS, s.Bs[st & 1], cn, ty, tx, acc);
 
-        if (ch == nch - 1) {
-            const int j0 = t * T_COLS;
-            float xc[8];
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-#pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    const int j = j0 + h * 64 + tx * 4 + v;
-                    xc[h * 4 + v] = j < N ? xxb[j] : 0.0f;
-                }
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                float d[8];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) d[c] = fmaf(2.0f, acc[r][c], -xq[r]) - xc[c];
-                float* row = s.Ds + (ty * 8 + r) * T_COLS;
-                *reinterpret_cast<float4*>(row + tx * 4) = make_float4(d[0], d[1], d[2], d[3]);
-                *reinterpret_cast<float4*>(row + 64 + tx * 4) = make_float4(d[4], d[5], d[6], d[7]);
+        float acc[8][8];
+        for (int st = 0; st < S; ++st) {
+            const int t = st / nch, ch = st - t * nch;
+            if (st + 1 < S) {
+                const int t1 = (st + 1) / nch, ch1 = (st + 1) - t1 * nch;
+                const int c0 = ch1 * KNN_KC;
+                const int cn = (C - c0) < KNN_KC ? (C - c0) : KNN_KC;
+                load_panel_async(s.Bs[(st + 1) & 1], T_COLS, xb + (int64_t)c0 * N, N, cn, t1 * T_COLS, N, tid);
+                cp_async_commit();
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
             }
-            __syncthreads();
+            named_bar_sync(1, 128);
 
-            // ---- selection: warp w owns rows w*16 .. w*16+15.  Candidates not below the row's threshold are appended
-            // to the row's buffer; the buffer is merged into the sorted list only when it would overflow. ----
+            if (ch == 0) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) acc[r][c] = 0.0f;
+            }
+            const int c0 = ch * KNN_KC;
+            const int cn = (C - c0) < KNN_KC ? (C - c0) : KNN_KC;
+            tile_fma(As + c0 * T_ROWS, s.Bs[st & 1], cn, ty, tx, acc);
+
+            if (ch == nch - 1) {
+                const int j0 = t * T_COLS;
+                float xc[8];
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        const int j = j0 + h * 64 + tx * 4 + v;
+                        xc[h * 4 + v] = j < N ? xxb[j] : 0.0f;
+                    }
+                const int db = t & 1;
+                mbar_wait(&s.ds_empty[db], ((t >> 1) & 1) ^ 1);
+                float* D = s.Ds[db];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    float d[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) d[c] = fmaf(2.0f, acc[r][c], -xq[r]) - xc[c];
+                    float* row = D + (ty * 8 + r) * T_COLS;
+                    *reinterpret_cast<float4*>(row + tx * 4) = make_float4(d[0], d[1], d[2], d[3]);
+                    *reinterpret_cast<float4*>(row + 64 + tx * 4) = make_float4(d[4], d[5], d[6], d[7]);
+                }
+                mbar_arrive(&s.ds_full[db]);
+            }
+            named_bar_sync(1, 128);   // everyone is done with Bs[st & 1] before the next prefetch overwrites it
+        }
+    } else {
+        // ======================= selection warps: threshold filter, append, merge on overflow =======================
+        const int w = warp - 4;
+        const unsigned lt_mask = (1u << lane) - 1u;
+        for (int t = 0; t < ntiles; ++t) {
+            const int db = t & 1;
+            const int j0 = t * T_COLS;
             const bool full_tile = j0 + T_COLS <= N;
+            mbar_wait(&s.ds_full[db], (t >> 1) & 1);
+            const float* D = s.Ds[db];
 #pragma unroll 2
-            for (int rr = 0; rr < 16; ++rr) {
-                const int q = warp * 16 + rr;
-                const float4 dv4 = *reinterpret_cast<const float4*>(s.Ds + q * T_COLS + lane * 4);
+            for (int rr = 0; rr < KNN_ROWS_PER_SEL; ++rr) {
+                const int q = w * KNN_ROWS_PER_SEL + rr;
+                const float4 dv4 = *reinterpret_cast<const float4*>(D + q * T_COLS + lane * 4);
                 const float dv[4] = {dv4.x, dv4.y, dv4.z, dv4.w};
                 float tau = s.tau[q];
                 const int jb = j0 + lane * 4;
                 bool p[4];
-#pragma unroll
-                for (int v = 0; v < 4; ++v) p[v] = (dv[v] >= tau) && (full_tile || jb + v < N);
-                if (__ballot_sync(0xffffffffu, p[0] | p[1] | p[2] | p[3]) == 0u) continue;
-                int fill = s.fill[q];
+                unsigned m[4];
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
-                    unsigned m = __ballot_sync(0xffffffffu, p[v]);
-                    if (m == 0u) continue;
-                    int cnt = __popc(m);
-                    if (fill + cnt > 32) {
-                        tau = knn_flush(s, q, lane, fill, k);
-                        fill = 0;
-                        __syncwarp();
+                    p[v] = (dv[v] >= tau) && (full_tile || jb + v < N);
+                    m[v] = __ballot_sync(0xffffffffu, p[v]);
+                }
+                if ((m[0] | m[1] | m[2] | m[3]) == 0u) continue;
+                int fill = s.fill[q];
+                const int c0 = __popc(m[0]), c1 = __popc(m[1]), c2 = __popc(m[2]), c3 = __popc(m[3]);
+                if (fill + c0 + c1 + c2 + c3 <= 32) {
+                    // common case: everything fits, one compaction per column group
+                    uint2* B = s.buf + q * 32 + fill;
+                    if (p[0]) B[__popc(m[0] & lt_mask)] = make_uint2(__float_as_uint(dv[0]), (uint32_t)jb);
+                    if (p[1]) B[c0 + __popc(m[1] & lt_mask)] = make_uint2(__float_as_uint(dv[1]), (uint32_t)(jb + 1));
+                    if (p[2]) B[c0 + c1 + __popc(m[2] & lt_mask)] = make_uint2(__float_as_uint(dv[2]), (uint32_t)(jb + 2));
+                    if (p[3]) B[c0 + c1 + c2 + __popc(m[3] & lt_mask)] = make_uint2(__float_as_uint(dv[3]), (uint32_t)(jb + 3));
+                    fill += c0 + c1 + c2 + c3;
+                } else {
 #pragma unroll
-                        for (int w = v; w < 4; ++w) p[w] = p[w] && (dv[w] >= tau);
-                        m = __ballot_sync(0xffffffffu, p[v]);
-                        cnt = __popc(m);
+                    for (int v = 0; v < 4; ++v) {
+                        unsigned mm = __ballot_sync(0xffffffffu, p[v]);
+                        if (mm == 0u) continue;
+                        int cnt = __popc(mm);
+                        if (fill + cnt > 32) {
+                            tau = knn_flush(s, q, lane, fill, k);
+                            fill = 0;
+                            __syncwarp();
+#pragma unroll
+                            for (int u = v; u < 4; ++u) p[u] = p[u] && (dv[u] >= tau);
+                            mm = __ballot_sync(0xffffffffu, p[v]);
+                            cnt = __popc(mm);
+                        }
+                        if (p[v]) s.buf[q * 32 + fill + __popc(mm & lt_mask)] = make_uint2(__float_as_uint(dv[v]), (uint32_t)(jb + v));
+                        fill += cnt;
                     }
-                    if (p[v]) s.buf[q * 32 + fill + __popc(m & lt_mask)] = make_uint2(__float_as_uint(dv[v]), (uint32_t)(jb + v));
-                    fill += cnt;
                 }
                 if (lane == 0) s.fill[q] = fill;
             }
+            __syncwarp();
+            mbar_arrive(&s.ds_empty[db]);
         }
-        __syncthreads();
-    }
 
-    // ---- final merge and write-out: the k nearest, sorted nearest first ----
-    for (int rr = 0; rr < 16; ++rr) {
-        const int q = warp * 16 + rr;
-        const int fill = s.fill[q];
-        if (fill > 0) knn_flush(s, q, lane, fill, k);
-        __syncwarp();
-        const int n = q0 + q;
-        if (n < N && lane < k) {
-            const uint2 e = s.list[q * 32 + lane];
-            const int64_t o = ((int64_t)b * N + n) * k + lane;
-            idx_out[o] = (int32_t)(~e.y);
-            if (dist_out) dist_out[o] = ord_val(e.x);
+        // ---- final merge and write-out: the k nearest, sorted nearest first ----
+        for (int rr = 0; rr < KNN_ROWS_PER_SEL; ++rr) {
+            const int q = w * KNN_ROWS_PER_SEL + rr;
+            const int fill = s.fill[q];
+            if (fill > 0) knn_flush(s, q, lane, fill, k);
+            __syncwarp();
+            const int n = q0 + q;
+            if (n < N && lane < k) {
+                const uint2 e = s.list[q * 32 + lane];
+                const int64_t o = ((int64_t)b * N + n) * k + lane;
+                idx_out[o] = (int32_t)(~e.y);
+                if (dist_out) dist_out[o] = ord_val(e.x);
+            }
         }
     }
 }
@@ -225,7 +267,7 @@ extern "C" int gfs_knn_f32(const float* x, int64_t x_bstride, int B, int C, int 
     GFS_LAUNCH_OK("sqnorm_kernel");
     const size_t smem = sizeof(KnnSmem) + (size_t)C * T_ROWS * sizeof(float);
     GFS_CUDA_OK(allow_smem(reinterpret_cast<const void*>(knn_kernel), sizeof(KnnSmem) + 64 * T_ROWS * sizeof(float)));
-    knn_kernel<<<dim3((N + T_ROWS - 1) / T_ROWS, B), T_THREADS, smem, st>>>(x, x_bstride, C, N, k, sqnorm, idx_out, dist_out);
+    knn_kernel<<<dim3((N + T_ROWS - 1) / T_ROWS, B), KNN_THREADS, smem, st>>>(x, x_bstride, C, N, k, sqnorm, idx_out, dist_out);
     GFS_LAUNCH_OK("knn_kernel");
     return GFS_OK;
 }
