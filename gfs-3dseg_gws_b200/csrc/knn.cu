@@ -16,7 +16,7 @@
 namespace gfs {
 
 constexpr int KNN_KC = 32;        // channels per pipeline stage
-constexpr int KNN_SEL_WARPS = 8;
+constexpr int KNN_SEL_WARPS = 16;
 constexpr int KNN_ROWS_PER_SEL = T_ROWS / KNN_SEL_WARPS;
 constexpr int KNN_THREADS = 128 + 32 * KNN_SEL_WARPS;  // warps 0-3: FFMA producers of distance tiles; the rest: selection consumers
 
@@ -102,6 +102,7 @@ knn_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int k, co
 
     if (warp < 4) {
         // ======================= FFMA warps: distance tiles in the pinned order =======================
+        reg_alloc<168>();
         const int ty = tid >> 4, tx = tid & 15;
         const float* xb = x + (int64_t)b * bstride;
         const float* xxb = sqnorm + (int64_t)b * N;
@@ -175,6 +176,7 @@ knn_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int k, co
         }
     } else {
         // ======================= selection warps: threshold filter, append, merge on overflow =======================
+        reg_dealloc<72>();
         const int w = warp - 4;
         const unsigned lt_mask = (1u << lane) - 1u;
         for (int t = 0; t < ntiles; ++t) {
