@@ -52,7 +52,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
 attention_kernel(const uint8_t* __restrict__ qkv, int kblocks, int kb_q, int tiles_per_block, int n_items, float scale_log2,
                  int N, float* __restrict__ y_cm, int64_t y_bstride, uint8_t* __restrict__ y_act, int y_kblocks, int y_kb) {
     extern __shared__ unsigned char smem_raw[];
-    AtSmem& s = *reinterpret_cast<AtSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // align inside the shared window with pointer arithmetic on smem_raw (keeps the .shared address space: LDS/STS, not generic LD/ST)
+    AtSmem& s = *reinterpret_cast<AtSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int T = tiles_per_block;
 

@@ -7,8 +7,9 @@
 // scale is folded into W2 the remaining "+shift, LeakyReLU" is monotone and is applied once after the max.
 //
 // Warp roles (persistent CTA, one per SM):
-//   warps 0-3  producers : gather P'[idx] (256 B contiguous per edge) + Q' (registers) -> LReLU -> bf16 -> SWIZZLE_128B
-//                          A tile in shared memory -> fence.proxy.async -> arrive full[stage]
+//   warps 0-3  producers : cp.async gather of P'[idx] (256 B contiguous per edge) into a shared-memory ring, two slots
+//                          ahead; + Q' (registers) -> LReLU -> bf16 -> SWIZZLE_128B A tile in shared memory ->
+//                          fence.proxy.async -> arrive full[stage]
 //   warp  8    MMA       : one thread issues 4 x tcgen05.mma (128x64x16) per A tile into TMEM stage acc;
 //                          tcgen05.commit -> empty[stage], accf[acc].  W2 (8 KB image) arrives once by TMA bulk copy.
 //   warps 4-7  epilogue  : tcgen05.ld 32x32b, running max in registers, arrive acce[acc]; after slot k-1:
@@ -23,8 +24,11 @@ constexpr int EC_NACC = 4;
 constexpr int EC_THREADS = 288;
 constexpr uint32_t EC_TMEM_COLS = 256;
 
+constexpr int EC_NG = 3;           // gather ring depth (slots of 128 rows x 256 B of fp32 P')
+
 struct EcSmem {
     uint8_t A[EC_NST][16384];
+    uint8_t G[EC_NG][32768];
     uint8_t W[8192];
     float shift[64];
     uint64_t full[EC_NST], empty[EC_NST], accf[EC_NACC], acce[EC_NACC], wbar;
@@ -38,7 +42,8 @@ edgeconv_kernel(const float* __restrict__ pq, const int32_t* __restrict__ idx, c
                 int64_t y_bstride, uint8_t* __restrict__ y_act, int act_kblocks, int act_kb, uint8_t* __restrict__ y_act2,
                 int act2_kblocks, int act2_kb, uint8_t* __restrict__ argmax) {
     extern __shared__ unsigned char smem_raw[];
-    EcSmem& s = *reinterpret_cast<EcSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // align inside the shared window with pointer arithmetic on smem_raw (keeps the .shared address space: LDS/STS, not generic LD/ST)
+    EcSmem& s = *reinterpret_cast<EcSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid < 64) s.shift[tid] = shift2[tid];
@@ -67,10 +72,20 @@ edgeconv_kernel(const float* __restrict__ pq, const int32_t* __restrict__ idx, c
 
     if (warp < 4) {
         // =============================== producers ===============================
+        // Gathers are cp.async (LDGSTS) copies into a 3-deep shared-memory ring, two neighbour slots ahead of the slot
+        // being converted, so ~64 KB of P' rows are in flight per SM without holding them in registers.  Each thread
+        // converts exactly the 32-byte pieces it copied itself, so cp.async.wait_group is the only synchronisation.
         const int q = tid & 7, rsub = tid >> 3;
+        int* idxs = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(&s) + sizeof(EcSmem));   // [128][k]
         int stage = 0, phase = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int64_t m0 = (int64_t)tile * EC_TM;
+            named_bar_sync(2, 128);                              // previous tile's idx no longer needed
+            {
+                const int64_t lim = (M - m0) * k;                // valid ints of this tile
+                const int32_t* src = idx + m0 * k;
+                for (int i = tid; i < EC_TM * k; i += 128) idxs[i] = i < lim ? __ldg(src + i) : 0;
+            }
             float4 Q[8][2];
             int64_t base[8];   // b*N of the row's block, or -1 for rows past M
 #pragma unroll
@@ -86,43 +101,48 @@ edgeconv_kernel(const float* __restrict__ pq, const int32_t* __restrict__ idx, c
                     Q[p][0] = Q[p][1] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
+            named_bar_sync(2, 128);                              // idx tile visible to all producer threads
+
+            auto issue = [&](int kk) {
+                if (kk < k) {
+                    unsigned char* G = s.G[kk % EC_NG];
+#pragma unroll
+                    for (int p = 0; p < 8; ++p) {
+                        if (base[p] >= 0) {
+                            const int r = p * 16 + rsub;
+                            const int j = idxs[r * k + kk];
+                            const float* src = pq + (base[p] + j) * 128 + q * 8;
+                            unsigned char* dst = G + r * 256;
+                            cp_async16(dst + (((2 * q) ^ (r & 3)) << 4), src, 16);
+                            cp_async16(dst + (((2 * q + 1) ^ (r & 3)) << 4), src + 4, 16);
+                        }
+                    }
+                }
+                cp_async_commit();                               // always commit: keeps the group count uniform
+            };
+            issue(0);
+            issue(1);
             for (int kk = 0; kk < k; ++kk) {
-                bool waited = false;
+                issue(kk + 2);
+                cp_async_wait<2>();                              // this thread's copies of slot kk have landed
+                mbar_wait(&s.empty[stage], phase ^ 1);
+                uint8_t* A = s.A[stage];
+                const unsigned char* G = s.G[kk % EC_NG];
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {   // two batches of 4 rows: 8 x LDG.128 in flight per thread
-                    float4 v[4][2];
-#pragma unroll
-                    for (int pp = 0; pp < 4; ++pp) {
-                        const int p = half * 4 + pp;
-                        if (base[p] >= 0) {
-                            const int64_t m = m0 + p * 16 + rsub;
-                            const int j = __ldg(idx + m * k + kk);
-                            const float4* src = reinterpret_cast<const float4*>(pq + (base[p] + j) * 128 + q * 8);
-                            v[pp][0] = __ldg(src);
-                            v[pp][1] = __ldg(src + 1);
-                        } else {
-                            v[pp][0] = v[pp][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        }
+                for (int p = 0; p < 8; ++p) {
+                    const int r = p * 16 + rsub;
+                    uint4 o;
+                    if (base[p] >= 0) {
+                        const float4 v0 = *reinterpret_cast<const float4*>(G + r * 256 + (((2 * q) ^ (r & 3)) << 4));
+                        const float4 v1 = *reinterpret_cast<const float4*>(G + r * 256 + (((2 * q + 1) ^ (r & 3)) << 4));
+                        o.x = pack_bf16x2(lrelu02(v0.x + Q[p][0].x), lrelu02(v0.y + Q[p][0].y));
+                        o.y = pack_bf16x2(lrelu02(v0.z + Q[p][0].z), lrelu02(v0.w + Q[p][0].w));
+                        o.z = pack_bf16x2(lrelu02(v1.x + Q[p][1].x), lrelu02(v1.y + Q[p][1].y));
+                        o.w = pack_bf16x2(lrelu02(v1.z + Q[p][1].z), lrelu02(v1.w + Q[p][1].w));
+                    } else {
+                        o = make_uint4(0u, 0u, 0u, 0u);
                     }
-                    if (!waited) {
-                        mbar_wait(&s.empty[stage], phase ^ 1);
-                        waited = true;
-                    }
-                    uint8_t* A = s.A[stage];
-#pragma unroll
-                    for (int pp = 0; pp < 4; ++pp) {
-                        const int p = half * 4 + pp;
-                        uint4 o;
-                        if (base[p] >= 0) {
-                            o.x = pack_bf16x2(lrelu02(v[pp][0].x + Q[p][0].x), lrelu02(v[pp][0].y + Q[p][0].y));
-                            o.y = pack_bf16x2(lrelu02(v[pp][0].z + Q[p][0].z), lrelu02(v[pp][0].w + Q[p][0].w));
-                            o.z = pack_bf16x2(lrelu02(v[pp][1].x + Q[p][1].x), lrelu02(v[pp][1].y + Q[p][1].y));
-                            o.w = pack_bf16x2(lrelu02(v[pp][1].z + Q[p][1].z), lrelu02(v[pp][1].w + Q[p][1].w));
-                        } else {
-                            o = make_uint4(0u, 0u, 0u, 0u);
-                        }
-                        *reinterpret_cast<uint4*>(A + sw128(p * 16 + rsub, q)) = o;
-                    }
+                    *reinterpret_cast<uint4*>(A + sw128(r, q)) = o;
                 }
                 fence_proxy_async();
                 mbar_arrive(&s.full[stage]);
@@ -131,6 +151,7 @@ edgeconv_kernel(const float* __restrict__ pq, const int32_t* __restrict__ idx, c
                     phase ^= 1;
                 }
             }
+            cp_async_wait<0>();
         }
     } else if (warp == 8) {
         // =============================== MMA issuer ===============================
@@ -259,7 +280,7 @@ extern "C" int gfs_edgeconv_fwd(const float* pq, const int32_t* idx, const void*
     using namespace gfs;
     GFS_REQUIRE(pq && idx && w2_packed && shift2, GFS_ERR_BAD_ARG, "gfs_edgeconv_fwd: null pointer");
     GFS_REQUIRE(B > 0 && N > 0 && k > 0, GFS_ERR_BAD_ARG, "gfs_edgeconv_fwd: non-positive size");
-    GFS_REQUIRE(k <= 255, GFS_ERR_UNSUPPORTED, "gfs_edgeconv_fwd: k=%d > 255", k);
+    GFS_REQUIRE(k <= 64, GFS_ERR_UNSUPPORTED, "gfs_edgeconv_fwd: k=%d > 64 is not built", k);
     GFS_REQUIRE(y_cm || y_act || y_act2, GFS_ERR_BAD_ARG, "gfs_edgeconv_fwd: no output requested");
     GFS_REQUIRE((reinterpret_cast<uintptr_t>(pq) & 15) == 0 && (reinterpret_cast<uintptr_t>(w2_packed) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(y_act) & 15) == 0 && (reinterpret_cast<uintptr_t>(y_act2) & 15) == 0 &&
@@ -270,16 +291,16 @@ extern "C" int gfs_edgeconv_fwd(const float* pq, const int32_t* idx, const void*
     const int sms = sm_count();
     GFS_REQUIRE(sms > 0, GFS_ERR_CUDA, "gfs_edgeconv_fwd: cannot query the device");
     const int grid = ntiles < sms ? ntiles : sms;
-    const size_t smem = sizeof(EcSmem) + 1024;
+    const size_t smem = sizeof(EcSmem) + 1024 + (size_t)EC_TM * k * sizeof(int);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (argmax) {
-        GFS_CUDA_OK(allow_smem(reinterpret_cast<const void*>(edgeconv_kernel<true>), smem));
+        GFS_CUDA_OK(allow_smem(reinterpret_cast<const void*>(edgeconv_kernel<true>), sizeof(EcSmem) + 1024 + EC_TM * 64 * sizeof(int)));
         edgeconv_kernel<true><<<grid, EC_THREADS, smem, st>>>(
             pq, idx, static_cast<const uint8_t*>(w2_packed), shift2, N, k, M, ntiles, y_cm, y_bstride,
             static_cast<uint8_t*>(y_act), y_act_kblocks, y_act_kb, static_cast<uint8_t*>(y_act2), y_act2_kblocks, y_act2_kb,
             argmax);
     } else {
-        GFS_CUDA_OK(allow_smem(reinterpret_cast<const void*>(edgeconv_kernel<false>), smem));
+        GFS_CUDA_OK(allow_smem(reinterpret_cast<const void*>(edgeconv_kernel<false>), sizeof(EcSmem) + 1024 + EC_TM * 64 * sizeof(int)));
         edgeconv_kernel<false><<<grid, EC_THREADS, smem, st>>>(
             pq, idx, static_cast<const uint8_t*>(w2_packed), shift2, N, k, M, ntiles, y_cm, y_bstride,
             static_cast<uint8_t*>(y_act), y_act_kblocks, y_act_kb, static_cast<uint8_t*>(y_act2), y_act2_kblocks, y_act2_kb,

@@ -31,7 +31,8 @@ linear_kernel(const uint8_t* __restrict__ x_act, int x_kblocks, int x_kb0, int k
               const float* __restrict__ shift, int Nout, int NT, int act, int N, int64_t M, int n_mtiles,
               uint8_t* __restrict__ y_act, int y_kblocks, int y_kb0, float* __restrict__ y_cm, int64_t y_bstride) {
     extern __shared__ unsigned char smem_raw[];
-    LnSmem& s = *reinterpret_cast<LnSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // align inside the shared window with pointer arithmetic on smem_raw (keeps the .shared address space: LDS/STS, not generic LD/ST)
+    LnSmem& s = *reinterpret_cast<LnSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_ntiles = Nout / NT;
     const int n_items = n_mtiles * n_ntiles;
