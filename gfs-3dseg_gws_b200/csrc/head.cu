@@ -26,7 +26,20 @@ cos_logits_kernel(const float* __restrict__ feat, int64_t bstride, int D, int N,
 #pragma unroll
     for (int c = 0; c < CL_MAXC; ++c) acc[c] = 0.0f;
     float nrm = 0.0f;
-    for (int d = 0; d < D; ++d) {
+    int d = 0;
+    for (; d + 8 <= D; d += 8) {          // 8 independent, coalesced loads in flight per thread
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldg(f + (int64_t)(d + u) * N);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            nrm = fmaf(v[u], v[u], nrm);
+#pragma unroll
+            for (int c = 0; c < CL_MAXC; ++c)
+                if (c < CLS) acc[c] = fmaf(v[u], sp[c * D + d + u], acc[c]);
+        }
+    }
+    for (; d < D; ++d) {
         const float v = f[(int64_t)d * N];
         nrm = fmaf(v, v, nrm);
 #pragma unroll

@@ -23,7 +23,8 @@ constexpr int KNN_THREADS = 128 + 32 * KNN_SEL_WARPS;  // warps 0-3: FFMA produc
 struct KnnSmem {
     float Bs[2][KNN_KC * T_COLS];   // 32 KB  candidate panels (cp.async double buffer)
     float Ds[2][T_ROWS * T_COLS];   // 64 KB  distance tiles, produced by the FFMA warps, consumed by the selection warps
-    uint2 list[T_ROWS * 32];        // 16 KB  per query: 32 best so far, sorted descending; (x = orderable distance, y = ~index)
+    uint2 list[T_ROWS * 64];        // 32 KB  per query: best 32 (k <= 32) or 64 (k <= 64) so far, sorted descending;
+                                    //        (x = orderable distance, y = ~index); rank r lives at [q*64 + r]
     uint2 buf[T_ROWS * 32];         // 16 KB  per query: raw (distance bits, index) appended since the last merge
     float tau[T_ROWS];              // distance of the k-th best at the last merge (filter threshold, never decreases)
     int fill[T_ROWS];
@@ -50,6 +51,7 @@ __device__ __forceinline__ u64 cmpex(u64 k, int j2, bool keep_max) {
 // Merge the row's append buffer into its sorted list (one warp; key = (orderable d << 32) | ~index, larger = better, so
 // equal distances order by ascending index).  Bitonic sort of the <=32 buffered keys, then the classic
 // "max(list, reverse(sorted buffer))" + 5-stage bitonic merge keeps the 32 largest of the union, sorted descending.
+template <int LR>   // LR = list registers per lane: 1 -> 32-entry list (k <= 32), 2 -> 64-entry list (k <= 64)
 __device__ __forceinline__ float knn_flush(KnnSmem& s, int q, int lane, int fill, int k) {
     const uint2 raw = s.buf[q * 32 + lane];
     u64 key = lane < fill ? (((u64)ord_key(__uint_as_float(raw.x)) << 32) | (u64)(~raw.y)) : 0ull;
@@ -62,19 +64,41 @@ __device__ __forceinline__ float knn_flush(KnnSmem& s, int q, int lane, int fill
             key = cmpex(key, j2, lower == desc);
         }
     }
-    const uint2 l2 = s.list[q * 32 + lane];
-    const u64 lst = ((u64)l2.x << 32) | (u64)l2.y;
     const u64 rev = __shfl_sync(0xffffffffu, key, 31 - lane);
-    key = lst > rev ? lst : rev;
+    uint32_t kth;
+    if (LR == 1) {
+        const uint2 l2 = s.list[q * 64 + lane];
+        const u64 lst = ((u64)l2.x << 32) | (u64)l2.y;
+        key = lst > rev ? lst : rev;
 #pragma unroll
-    for (int j2 = 16; j2 > 0; j2 >>= 1) key = cmpex(key, j2, (lane & j2) == 0);
-    s.list[q * 32 + lane] = make_uint2((uint32_t)(key >> 32), (uint32_t)key);
-    const uint32_t kth = __shfl_sync(0xffffffffu, (uint32_t)(key >> 32), k - 1);
+        for (int j2 = 16; j2 > 0; j2 >>= 1) key = cmpex(key, j2, (lane & j2) == 0);
+        s.list[q * 64 + lane] = make_uint2((uint32_t)(key >> 32), (uint32_t)key);
+        kth = __shfl_sync(0xffffffffu, (uint32_t)(key >> 32), k - 1);
+    } else {
+        // 64-entry list: ranks 0..31 in m0, 32..63 in m1.  union top-64 = bitonic merge of [L0, max(L1, reverse(S))]
+        const uint2 a2 = s.list[q * 64 + lane], b2 = s.list[q * 64 + 32 + lane];
+        u64 m0 = ((u64)a2.x << 32) | (u64)a2.y;
+        u64 m1 = ((u64)b2.x << 32) | (u64)b2.y;
+        m1 = m1 > rev ? m1 : rev;
+        const u64 hi = m0 > m1 ? m0 : m1, lo = m0 > m1 ? m1 : m0;
+        m0 = hi;
+        m1 = lo;
+#pragma unroll
+        for (int j2 = 16; j2 > 0; j2 >>= 1) {
+            m0 = cmpex(m0, j2, (lane & j2) == 0);
+            m1 = cmpex(m1, j2, (lane & j2) == 0);
+        }
+        s.list[q * 64 + lane] = make_uint2((uint32_t)(m0 >> 32), (uint32_t)m0);
+        s.list[q * 64 + 32 + lane] = make_uint2((uint32_t)(m1 >> 32), (uint32_t)m1);
+        kth = k <= 32 ? __shfl_sync(0xffffffffu, (uint32_t)(m0 >> 32), k - 1)
+                      : __shfl_sync(0xffffffffu, (uint32_t)(m1 >> 32), k - 33);
+    }
     const float tau = kth ? ord_val(kth) : -INFINITY;
     if (lane == 0) s.tau[q] = tau;
     return tau;
 }
 
+template <int LR>
 __global__ void __launch_bounds__(KNN_THREADS, 1)
 knn_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int k, const float* __restrict__ sqnorm,
            int32_t* __restrict__ idx_out, float* __restrict__ dist_out) {
@@ -86,7 +110,7 @@ knn_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int k, co
     const int b = blockIdx.y, q0 = blockIdx.x * T_ROWS;
     const int ntiles = (N + T_COLS - 1) / T_COLS;
 
-    for (int i = tid; i < T_ROWS * 32; i += KNN_THREADS) s.list[i] = make_uint2(0u, 0u);
+    for (int i = tid; i < T_ROWS * 64; i += KNN_THREADS) s.list[i] = make_uint2(0u, 0u);
     if (tid < T_ROWS) {
         s.tau[tid] = -INFINITY;
         s.fill[tid] = 0;
@@ -217,7 +241,7 @@ knn_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int k, co
                         if (mm == 0u) continue;
                         int cnt = __popc(mm);
                         if (fill + cnt > 32) {
-                            tau = knn_flush(s, q, lane, fill, k);
+                            tau = knn_flush<LR>(s, q, lane, fill, k);
                             fill = 0;
                             __syncwarp();
 #pragma unroll
@@ -239,14 +263,20 @@ knn_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int k, co
         for (int rr = 0; rr < KNN_ROWS_PER_SEL; ++rr) {
             const int q = w * KNN_ROWS_PER_SEL + rr;
             const int fill = s.fill[q];
-            if (fill > 0) knn_flush(s, q, lane, fill, k);
+            if (fill > 0) knn_flush<LR>(s, q, lane, fill, k);
             __syncwarp();
             const int n = q0 + q;
-            if (n < N && lane < k) {
-                const uint2 e = s.list[q * 32 + lane];
-                const int64_t o = ((int64_t)b * N + n) * k + lane;
-                idx_out[o] = (int32_t)(~e.y);
-                if (dist_out) dist_out[o] = ord_val(e.x);
+            if (n < N) {
+#pragma unroll
+                for (int h = 0; h < LR; ++h) {
+                    const int r = h * 32 + lane;
+                    if (r < k) {
+                        const uint2 e = s.list[q * 64 + r];
+                        const int64_t o = ((int64_t)b * N + n) * k + r;
+                        idx_out[o] = (int32_t)(~e.y);
+                        if (dist_out) dist_out[o] = ord_val(e.x);
+                    }
+                }
             }
         }
     }
@@ -260,7 +290,7 @@ extern "C" int gfs_knn_f32(const float* x, int64_t x_bstride, int B, int C, int 
     GFS_REQUIRE(x && sqnorm && idx_out, GFS_ERR_BAD_ARG, "gfs_knn_f32: null pointer");
     GFS_REQUIRE(B > 0 && C > 0 && N > 0 && k > 0, GFS_ERR_BAD_ARG, "gfs_knn_f32: non-positive size (B=%d C=%d N=%d k=%d)", B, C, N, k);
     GFS_REQUIRE(k <= N, GFS_ERR_BAD_ARG, "gfs_knn_f32: k=%d exceeds N=%d", k, N);
-    GFS_REQUIRE(k <= 32, GFS_ERR_UNSUPPORTED, "gfs_knn_f32: k=%d > 32 is not built (warp-level list holds 32)", k);
+    GFS_REQUIRE(k <= 64, GFS_ERR_UNSUPPORTED, "gfs_knn_f32: k=%d > 64 is not built (the warp-level list holds 64)", k);
     GFS_REQUIRE(C <= 64, GFS_ERR_UNSUPPORTED, "gfs_knn_f32: C=%d > 64 is not built", C);
     GFS_REQUIRE(N % 4 == 0 && x_bstride % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, GFS_ERR_UNSUPPORTED,
                 "gfs_knn_f32: needs N %% 4 == 0 and 16-byte aligned rows (N=%d)", N);
@@ -268,8 +298,14 @@ extern "C" int gfs_knn_f32(const float* x, int64_t x_bstride, int B, int C, int 
     sqnorm_kernel<<<dim3((N + 255) / 256, B), 256, 0, st>>>(x, x_bstride, C, N, sqnorm);
     GFS_LAUNCH_OK("sqnorm_kernel");
     const size_t smem = sizeof(KnnSmem) + (size_t)C * T_ROWS * sizeof(float);
-    GFS_CUDA_OK(allow_smem(reinterpret_cast<const void*>(knn_kernel), sizeof(KnnSmem) + 64 * T_ROWS * sizeof(float)));
-    knn_kernel<<<dim3((N + T_ROWS - 1) / T_ROWS, B), KNN_THREADS, smem, st>>>(x, x_bstride, C, N, k, sqnorm, idx_out, dist_out);
+    const dim3 grid((N + T_ROWS - 1) / T_ROWS, B);
+    if (k <= 32) {
+        GFS_CUDA_OK(allow_smem(reinterpret_cast<const void*>(knn_kernel<1>), sizeof(KnnSmem) + 64 * T_ROWS * sizeof(float)));
+        knn_kernel<1><<<grid, KNN_THREADS, smem, st>>>(x, x_bstride, C, N, k, sqnorm, idx_out, dist_out);
+    } else {
+        GFS_CUDA_OK(allow_smem(reinterpret_cast<const void*>(knn_kernel<2>), sizeof(KnnSmem) + 64 * T_ROWS * sizeof(float)));
+        knn_kernel<2><<<grid, KNN_THREADS, smem, st>>>(x, x_bstride, C, N, k, sqnorm, idx_out, dist_out);
+    }
     GFS_LAUNCH_OK("knn_kernel");
     return GFS_OK;
 }

@@ -52,7 +52,7 @@ int gfs_device_sm_count(void);
  * row, nearest first, ties -> ascending index.  The N x N matrix is never written to memory.
  *   x        cm fp32, channel stride N, batch stride x_bstride (elements); C <= 64, N % 4 == 0
  *   sqnorm   workspace, B*N floats (per-point |x|^2, written by the call)
- *   idx_out  (B, N, k) int32, neighbour index inside its own block;  k <= 32, k <= N
+ *   idx_out  (B, N, k) int32, neighbour index inside its own block;  k <= 64, k <= N
  *   dist_out optional (B, N, k) fp32 (may be NULL)                                                              */
 int gfs_knn_f32(const float* x, int64_t x_bstride, int B, int C, int N, int k,
                 float* sqnorm, int32_t* idx_out, float* dist_out, void* stream);

@@ -40,8 +40,8 @@ def test_error_convention_without_gpu():
     assert rc == 1 and b"null pointer" in l.gfs_last_error_string()
     buf = (ctypes.c_float * 64)()
     p = ctypes.cast(buf, ctypes.c_void_p)
-    rc = l.gfs_knn_f32(p, 0, 1, 9, 128, 40, p, p, None, None)
-    assert rc == 2 and b"k=40" in l.gfs_last_error_string()
+    rc = l.gfs_knn_f32(p, 0, 1, 9, 128, 65, p, p, None, None)
+    assert rc == 2 and b"k=65" in l.gfs_last_error_string()
     rc = l.gfs_knn_f32(p, 0, 1, 9, 16, 20, p, p, None, None)
     assert rc == 1 and b"exceeds N" in l.gfs_last_error_string()
     rc = l.gfs_linear_bf16(p, 3, 0, 3, p, None, 100, 1, 1, 128, p, 2, 0, None, 0, None)

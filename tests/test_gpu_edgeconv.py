@@ -16,7 +16,8 @@ def _ops():
 
 @pytest.mark.parametrize("B,C,N,k,dup", [(2, 9, 256, 20, 0.0), (1, 9, 2048, 20, 0.0), (2, 64, 512, 20, 0.0),
                                          (1, 9, 256, 20, 0.25), (3, 9, 320, 32, 0.0), (2, 64, 192, 7, 0.0),
-                                         (1, 33, 128, 20, 0.0), (1, 9, 64, 20, 0.0)])
+                                         (1, 33, 128, 20, 0.0), (1, 9, 64, 20, 0.0), (2, 9, 320, 40, 0.0), (1, 64, 1024, 40, 0.0),
+                                         (1, 9, 256, 64, 0.25), (1, 9, 4096, 20, 0.0)])
 def test_knn_bit_exact_vs_oracle(B, C, N, k, dup):
     ops = _ops()
     if C == 9:
@@ -42,8 +43,8 @@ def test_knn_on_strided_slice_of_concat_buffer():
 
 def test_knn_rejects_unsupported():
     ops = _ops()
-    with pytest.raises(RuntimeError, match="k=40"):
-        ops.knn(torch.randn(1, 9, 128, device="cuda"), 40)
+    with pytest.raises(RuntimeError, match="k=65"):
+        ops.knn(torch.randn(1, 9, 128, device="cuda"), 65)
     with pytest.raises(RuntimeError, match="C=65"):
         ops.knn(torch.randn(1, 65, 128, device="cuda"), 20)
     with pytest.raises(RuntimeError):

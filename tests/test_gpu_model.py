@@ -117,11 +117,11 @@ def _load_dgcnn(golden_sd, k=20):
     return m.cuda().eval()
 
 
-@pytest.mark.parametrize("name", ["dgcnn_b2_n256", "dgcnn_dup_b1_n256", "dgcnn_b1_n2048"])
+@pytest.mark.parametrize("name", ["dgcnn_b2_n256", "dgcnn_dup_b1_n256", "dgcnn_b1_n2048", "dgcnn_b1_n320_k40"])
 def test_dgcnn_dropin_vs_reference_fixture(golden, golden_sd, name):
     """BASELINE.json configs[0] (N=2048) and small cases: the drop-in DGCNN against outputs of the real reference."""
     g = golden(name)
-    m = _load_dgcnn(golden_sd)
+    m = _load_dgcnn(golden_sd, k=int(g["k"]))
     x = torch.from_numpy(g["x"])
     s = int(g["subsample"])
     with torch.no_grad():
