@@ -156,18 +156,33 @@ class KMeans:
         return self
 
     def _relocate_empty(self, Xc, n, labels, centers, sums, counts):
-        """sklearn _k_means_common.pyx:167-211 -- rare path, plain device ops (single-shard semantics per rank 0)."""
-        if self.shard:
-            raise NotImplementedError("empty-cluster relocation across shards is not built (pass a better init)")
+        """sklearn _k_means_common.pyx:167-211: every empty cluster is moved onto one of the points farthest from its own
+        (old) centre, and that point is taken out of its old cluster's sum.  Rare path, plain device ops.  Sharded: each
+        rank offers its n_empty farthest points (distance, old label, coordinates), the candidates are all-gathered and
+        every rank applies the same global choice to the (already all-reduced) sums / counts."""
         empty = (counts == 0).nonzero().flatten()
+        ne = int(empty.numel())
+        D = Xc.shape[1]
         dist = ((Xc - centers[labels[:n].long()]) ** 2).sum(1)
-        if float(dist.max()) == 0:
+        m = min(ne, n)
+        vals, idxs = torch.topk(dist, m)
+        cand = torch.full((ne, 2 + D), float("-inf"), dtype=torch.float64, device=Xc.device)
+        cand[:m, 0] = vals.double()
+        cand[:m, 1] = labels[idxs].double()
+        cand[:m, 2:] = Xc[idxs].double()
+        if self.shard:
+            world = _dist().get_world_size(self.process_group)
+            gathered = [torch.empty_like(cand) for _ in range(world)]
+            _dist().all_gather(gathered, cand, group=self.process_group)
+            cand = torch.cat(gathered, 0)
+        if float(cand[:, 0].max()) <= 0:
             return sums, counts
-        far = torch.topk(dist, len(empty)).indices
-        for e, fi in zip(empty.tolist(), far.tolist()):
-            old = int(labels[fi])
-            sums[old] -= Xc[fi].double()
-            sums[e] = Xc[fi].double()
+        order = torch.argsort(cand[:, 0], descending=True, stable=True)[:ne]
+        for e, row in zip(empty.tolist(), order.tolist()):
+            old = int(cand[row, 1])
+            x = cand[row, 2:]
+            sums[old] -= x
+            sums[e] = x
             counts[e] = 1
             counts[old] -= 1
         return sums, counts
