@@ -84,3 +84,24 @@ def test_kmeans_plusplus_runs_and_is_a_fixed_point():
     best = d.min(1)
     chosen = d[np.arange(500), km.labels_[:500]]
     assert (chosen <= best + 1e-4 * np.abs(best)).all()
+
+
+def test_gw_basis_pipeline_end_to_end(golden_sd):
+    """get_basis.py:162-222 on synthetic blocks: EdgeConv123 features -> per-class subsample -> GPU k-means -> Kmean2Proto ->
+    SVD reconstruction, then the basis drives the GW projection of the model.  Checked against the oracle's numpy pieces."""
+    from gfs3d.basis import build_gw_basis, collect_edgeconv_features, kmean_to_proto, svd_reconstruct
+    from gfs3d.synthetic import synthetic_blocks
+    from model.dgcnn import DGCNN
+    enc = DGCNN([[64, 64]] * 3, [512, 256], 9, k=20, return_edgeconvs=True)
+    enc.load_state_dict(golden_sd("dgcnn_weights"))
+    enc = enc.cuda().eval()
+    g = torch.Generator().manual_seed(0)
+    blocks = [(synthetic_blocks(4, 512, seed=10 * i), torch.randint(0, 4, (4, 512), generator=g)) for i in range(3)]
+    feat = collect_edgeconv_features(enc, blocks, num_classes=4, max_num=1200, rng=np.random.RandomState(1))
+    assert feat.shape[1] == 192 and feat.shape[0] <= 3 * 1200 and feat.is_cuda
+    basis, km = build_gw_basis(feat, num_cnt=40, random_state=0)
+    assert basis.shape == (40, 192) and basis.dtype == np.float32
+    X = feat.cpu().numpy()
+    assert np.array_equal(kmean_to_proto(X, km.labels_, 40), O.kmean_to_proto(X, km.labels_, 40))
+    assert np.abs(svd_reconstruct(O.kmean_to_proto(X, km.labels_, 40)) - O.svd_reconstruct(O.kmean_to_proto(X, km.labels_, 40))).max() < 1e-5
+    assert np.linalg.matrix_rank(basis.astype(np.float64), tol=1e-4) < 40          # rank-truncated at 95 % energy
