@@ -84,6 +84,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// same, but a polling warp gives its issue slots away between polls (for waits that are long and not latency critical:
+// a spinning try_wait loop otherwise competes for the scheduler with the warps doing the work)
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, unsigned ns) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
 
 // ---- TMA bulk copies (cp.async.bulk -> UBLKCP) ----
 __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {

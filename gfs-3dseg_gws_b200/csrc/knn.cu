@@ -183,7 +183,7 @@ knn_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int k, co
                         xc[h * 4 + v] = j < N ? xxb[j] : 0.0f;
                     }
                 const int db = t & 1;
-                mbar_wait(&s.ds_empty[db], ((t >> 1) & 1) ^ 1);
+                mbar_wait_backoff(&s.ds_empty[db], ((t >> 1) & 1) ^ 1, 64);
                 float* D = s.Ds[db];
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
@@ -207,7 +207,7 @@ knn_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int k, co
             const int db = t & 1;
             const int j0 = t * T_COLS;
             const bool full_tile = j0 + T_COLS <= N;
-            mbar_wait(&s.ds_full[db], (t >> 1) & 1);
+            mbar_wait_backoff(&s.ds_full[db], (t >> 1) & 1, 256);
             const float* D = s.Ds[db];
 #pragma unroll 2
             for (int rr = 0; rr < KNN_ROWS_PER_SEL; ++rr) {
