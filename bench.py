@@ -249,8 +249,13 @@ def main():
     ec123_ms = knn_ms + ec_ms + prof.get("gfs_pointwise_f32", 0.0)
     ec123_bytes = 1316 * NPTS * B                                                        # compulsory bytes
     gbs = lambda byt, ms: (byt / 1e9) / (ms / 1e3) if ms > 0 else None
+    traffic = None          # dram__bytes_read+write of the three knn_kernel launches of a step, from the committed ncu capture
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["knn_kernel_bytes_per_step_b32"] * B / 32.0
+    except Exception:
+        pass
     roof = {"kernel": "knn_kernel (gfs_knn_f32, 3 launches/step)", "bound": "hbm", "achieved": gbs(knn_bytes, knn_ms), "peak": hbm_peak,
-            "unit": "GB/s", "frac": (gbs(knn_bytes, knn_ms) or 0) / hbm_peak, "traffic": None, "peak_source": peak_src,
+            "unit": "GB/s", "frac": (gbs(knn_bytes, knn_ms) or 0) / hbm_peak, "traffic": traffic, "peak_source": peak_src,
             "ms_per_step": knn_ms, "share_of_step": knn_ms / (sum(prof.values()) or 1),
             "binding_roof": "fp32 FFMA + top-k selection (not HBM): see fp32_tflops", "fp32_tflops": knn_flops / 1e12 / (knn_ms / 1e3) if knn_ms else None,
             "fp32_peak_tflops_nominal": 74.4,
@@ -281,7 +286,7 @@ def main():
                                    f"{CLASSES} classes, {G} GWs, random-init weights", "blocks_per_gpu_per_step": B,
                        "l2": "flushed between steps (256 MiB write outside the per-step event pair); 4 rotating input batches",
                        "parallelism": f"block-sharded x{world}, no data-path collective",
-                       "attention": "torch SDPA (library) -- SURVEY 8f row N1"},
+                       "attention": "hand-written tcgen05 flash kernel (gfs_attention_fwd)"},
             "clocks": clk, "e2e": {"value": total_blocks / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                                    "ms_per_step": e2e_ms / a.steps},
             "gpu_launches": launches, "roofline": roof, "roofline_detail": extra, "cpu_baseline": cpu, "wall_s_timed_region": wall}

@@ -1,46 +1,97 @@
 // kmeans.cu -- deterministic M-step sums for the global k-means of get_basis.py:210 (sklearn _k_means_lloyd.pyx:209-218).
 //
-// Each persistent CTA owns a contiguous range of points and adds them, in ascending point order, into a private
-// (K x D) fp32 table in shared memory: thread d owns column d, so there are no atomics and no bank conflicts.  The
+// Each persistent CTA owns a contiguous range of points, streams it through shared memory with TMA bulk copies and adds
+// the points, in ascending point order, into a private (K x D) fp32 table in shared memory: thread d owns column d, so
+// there are no floating-point atomics and no bank conflicts.  The
 // per-CTA tables are then reduced in CTA order in fp64.  The result does not depend on scheduling, and across GPU
 // counts it differs only by the (fp64) order of the partial sums.
 #include "common.cuh"
 
 namespace gfs {
 
-__global__ void __launch_bounds__(256)
+constexpr int KM_CH = 32;          // points per TMA chunk
+constexpr int KM_THREADS = 288;    // warps 0-7: one thread per feature column; warp 8: TMA issue, label staging, counts
+
+// X is row-major, so a chunk of 32 points is ONE contiguous cp.async.bulk (TMA) of 32*D*4 bytes; two chunks are in flight
+// while the column threads add the current one into the shared-memory table.
+__global__ void __launch_bounds__(KM_THREADS, 1)
 kmeans_partial_kernel(const float* __restrict__ X, int64_t n, int D, const int32_t* __restrict__ labels, int K,
                       float* __restrict__ partial, int32_t* __restrict__ pcount) {
-    extern __shared__ float tab[];                       // [K][D]
-    int* cnt = reinterpret_cast<int*>(tab + (size_t)K * D);   // [K]
-    const int d = threadIdx.x;
-    for (int i = d; i < K * D; i += 256) tab[i] = 0.0f;
-    for (int i = d; i < K; i += 256) cnt[i] = 0;
+    extern __shared__ __align__(128) unsigned char sm_raw[];
+    float* stg = reinterpret_cast<float*>(sm_raw);                          // [2][KM_CH][D]   (first: keeps 128 B alignment)
+    float* tab = stg + 2 * KM_CH * D;                                       // [K][D]
+    int* cnt = reinterpret_cast<int*>(tab + (size_t)K * D);                 // [K]
+    int* lab = cnt + ((K + 3) & ~3);                                        // [2][KM_CH]
+    uint64_t* full = reinterpret_cast<uint64_t*>(lab + 2 * KM_CH);          // [2]
+    const int tid = threadIdx.x, lane = tid & 31;
+    const bool helper = tid >= 256;
+
+    for (int i = tid; i < K * D; i += KM_THREADS) tab[i] = 0.0f;
+    for (int i = tid; i < K; i += KM_THREADS) cnt[i] = 0;
+    if (tid == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        mbar_fence_init();
+    }
     __syncthreads();
-    const int64_t per = (n + gridDim.x - 1) / gridDim.x;
+
+    int64_t per = (n + gridDim.x - 1) / gridDim.x;
+    per = (per + KM_CH - 1) / KM_CH * KM_CH;
     const int64_t i0 = per * blockIdx.x;
     const int64_t i1 = (i0 + per) < n ? (i0 + per) : n;
-    if (d < D) {
-        int64_t i = i0;
-        for (; i + 4 <= i1; i += 4) {
-            int l[4];
-            float v[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                l[u] = labels[i + u];
-                v[u] = X[(i + u) * D + d];
+    const int nchunks = i0 < i1 ? (int)((i1 - i0 + KM_CH - 1) / KM_CH) : 0;
+
+    auto issue = [&](int c) {   // helper warp only
+        if (c < nchunks) {
+            const int64_t p0 = i0 + (int64_t)c * KM_CH;
+            const int cc = (int)((i1 - p0) < KM_CH ? (i1 - p0) : KM_CH);
+            lab[(c & 1) * KM_CH + lane] = lane < cc ? labels[p0 + lane] : 0;
+            if (lane == 0) {
+                const uint32_t bytes = (uint32_t)cc * (uint32_t)D * 4u;
+                mbar_arrive_expect_tx(&full[c & 1], bytes);
+                tma_load_1d(stg + (size_t)(c & 1) * KM_CH * D, X + p0 * D, bytes, &full[c & 1]);
             }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) tab[l[u] * D + d] += v[u];
         }
-        for (; i < i1; ++i) tab[labels[i] * D + d] += X[i * D + d];
-    } else if (d == 255) {
-        for (int64_t i = i0; i < i1; ++i) cnt[labels[i]] += 1;
+    };
+    if (helper) {
+        issue(0);
+        issue(1);
+    }
+    __syncthreads();
+
+    for (int c = 0; c < nchunks; ++c) {
+        const int64_t p0 = i0 + (int64_t)c * KM_CH;
+        const int cc = (int)((i1 - p0) < KM_CH ? (i1 - p0) : KM_CH);
+        const int* L = lab + (c & 1) * KM_CH;
+        mbar_wait(&full[c & 1], (c >> 1) & 1);
+        if (!helper) {
+            const int d = tid;
+            if (d < D) {
+                const float* S = stg + (size_t)(c & 1) * KM_CH * D + d;
+                int j = 0;
+                for (; j + 1 < cc; j += 2) {      // ascending point order; two independent read-modify-writes when labels differ
+                    const int l0 = L[j], l1 = L[j + 1];
+                    const float v0 = S[j * D], v1 = S[(j + 1) * D];
+                    if (l0 != l1) {
+                        const float a = tab[l0 * D + d], b = tab[l1 * D + d];
+                        tab[l0 * D + d] = a + v0;
+                        tab[l1 * D + d] = b + v1;
+                    } else {
+                        tab[l0 * D + d] = (tab[l0 * D + d] + v0) + v1;
+                    }
+                }
+                if (j < cc) tab[L[j] * D + d] += S[j * D];
+            }
+        } else if (lane < cc) {
+            atomicAdd(&cnt[L[lane]], 1);
+        }
+        __syncthreads();                          // chunk buffer and its labels are free again
+        if (helper) issue(c + 2);
     }
     __syncthreads();
     float* o = partial + (size_t)blockIdx.x * K * D;
-    for (int i = d; i < K * D; i += 256) o[i] = tab[i];
-    for (int i = d; i < K; i += 256) pcount[(size_t)blockIdx.x * K + i] = cnt[i];
+    for (int i = tid; i < K * D; i += KM_THREADS) o[i] = tab[i];
+    for (int i = tid; i < K; i += KM_THREADS) pcount[(size_t)blockIdx.x * K + i] = cnt[i];
 }
 
 __global__ void kmeans_reduce_kernel(const float* __restrict__ partial, const int32_t* __restrict__ pcount, int P, int KD, int K,
@@ -67,14 +118,15 @@ extern "C" int gfs_kmeans_accumulate(const float* X, int64_t n, int D, const int
     using namespace gfs;
     GFS_REQUIRE(X && labels && partial && pcount && sums && counts, GFS_ERR_BAD_ARG, "gfs_kmeans_accumulate: null pointer");
     GFS_REQUIRE(n > 0 && D > 0 && K > 0, GFS_ERR_BAD_ARG, "gfs_kmeans_accumulate: non-positive size");
-    GFS_REQUIRE(D <= 254, GFS_ERR_UNSUPPORTED, "gfs_kmeans_accumulate: D=%d > 254 is not built", D);
-    const size_t smem = (size_t)K * D * sizeof(float) + (size_t)K * sizeof(int);
+    GFS_REQUIRE(D <= 256 && D % 4 == 0, GFS_ERR_UNSUPPORTED, "gfs_kmeans_accumulate: D=%d must be a multiple of 4, <= 256", D);
+    GFS_REQUIRE((reinterpret_cast<uintptr_t>(X) & 15) == 0, GFS_ERR_BAD_ARG, "gfs_kmeans_accumulate: X must be 16-byte aligned");
+    const size_t smem = (size_t)(2 * KM_CH + K) * D * sizeof(float) + (size_t)((K + 3) & ~3) * sizeof(int) + 2 * KM_CH * sizeof(int) + 64;
     GFS_REQUIRE(smem <= 220 * 1024, GFS_ERR_UNSUPPORTED, "gfs_kmeans_accumulate: K*D=%d does not fit shared memory", K * D);
     const int P = sm_count();
     GFS_REQUIRE(P > 0, GFS_ERR_CUDA, "gfs_kmeans_accumulate: cannot query the device");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     GFS_CUDA_OK(allow_smem(reinterpret_cast<const void*>(kmeans_partial_kernel), 220 * 1024));
-    kmeans_partial_kernel<<<P, 256, smem, st>>>(X, n, D, labels, K, partial, pcount);
+    kmeans_partial_kernel<<<P, KM_THREADS, smem, st>>>(X, n, D, labels, K, partial, pcount);
     GFS_LAUNCH_OK("kmeans_partial_kernel");
     kmeans_reduce_kernel<<<(K * D + 255) / 256, 256, 0, st>>>(partial, pcount, P, K * D, K, sums, counts);
     GFS_LAUNCH_OK("kmeans_reduce_kernel");

@@ -17,10 +17,11 @@ def _ops():
 @pytest.mark.parametrize("B,C,N,k,dup", [(2, 9, 256, 20, 0.0), (1, 9, 2048, 20, 0.0), (2, 64, 512, 20, 0.0),
                                          (1, 9, 256, 20, 0.25), (3, 9, 320, 32, 0.0), (2, 64, 192, 7, 0.0),
                                          (1, 33, 128, 20, 0.0), (1, 9, 64, 20, 0.0), (2, 9, 320, 40, 0.0), (1, 64, 1024, 40, 0.0),
-                                         (1, 9, 256, 64, 0.25), (1, 9, 4096, 20, 0.0)])
+                                         (1, 9, 256, 64, 0.25), (1, 9, 4096, 20, 0.0),
+                                         (2, 9, 20, 20, 0.0), (1, 3, 4, 1, 0.0), (1, 9, 100, 20, 0.5), (5, 9, 132, 33, 0.0)])
 def test_knn_bit_exact_vs_oracle(B, C, N, k, dup):
     ops = _ops()
-    if C == 9:
+    if C == 9 and N >= 64:
         x = O.synthetic_blocks(B, N, seed=100 + N, dup_frac=dup)
     else:
         x = torch.randn(B, C, N, generator=torch.Generator().manual_seed(N + C)) * 0.3
