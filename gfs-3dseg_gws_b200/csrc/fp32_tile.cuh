@@ -13,8 +13,15 @@ constexpr int T_COLS = 128;
 constexpr int T_THREADS = 128;
 
 // acc[r][s] += sum_{c in [0,nc)} As[c][ty*8+r] * Bs[c][col(s)]
+// Issued as packed FFMA2 (fma.rn.f32x2, new on sm_100): two IEEE fp32 fmas per instruction on adjacent columns, which
+// halves the issue slots of the inner product (each element is still its own fma chain, so the pinned order holds).
 __device__ __forceinline__ void tile_fma(const float* __restrict__ As, const float* __restrict__ Bs, int nc, int ty, int tx,
                                          float (&acc)[8][8]) {
+    float2 acc2[8][4];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int s = 0; s < 4; ++s) acc2[r][s] = make_float2(acc[r][2 * s], acc[r][2 * s + 1]);
 #pragma unroll 4
     for (int c = 0; c < nc; ++c) {
         const float4 a0 = *reinterpret_cast<const float4*>(As + c * T_ROWS + ty * 8);
@@ -22,12 +29,21 @@ __device__ __forceinline__ void tile_fma(const float* __restrict__ As, const flo
         const float4 b0 = *reinterpret_cast<const float4*>(Bs + c * T_COLS + tx * 4);
         const float4 b1 = *reinterpret_cast<const float4*>(Bs + c * T_COLS + 64 + tx * 4);
         const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        const float2 b[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
 #pragma unroll
-        for (int r = 0; r < 8; ++r)
+        for (int r = 0; r < 8; ++r) {
+            const float2 aa = make_float2(a[r], a[r]);
 #pragma unroll
-            for (int s = 0; s < 8; ++s) acc[r][s] = fmaf(a[r], b[s], acc[r][s]);
+            for (int s = 0; s < 4; ++s) acc2[r][s] = __ffma2_rn(aa, b[s], acc2[r][s]);
+        }
     }
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            acc[r][2 * s] = acc2[r][s].x;
+            acc[r][2 * s + 1] = acc2[r][s].y;
+        }
 }
 
 // cp.async a (nrows x width) fp32 panel: dst[r][0..width) <- src[r*src_ld + col0 .. ), zero-filled past `limit` columns.

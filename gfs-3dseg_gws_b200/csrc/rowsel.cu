@@ -43,13 +43,13 @@ rowsel_kernel(const float* __restrict__ x, int64_t bstride, int D, int N, const 
         cp_async_commit();
     };
 
-    float acc[8][12];
+    float2 acc2[8][6];     // packed FFMA2 accumulators: (column 2j, column 2j+1)
     float nrm[8];
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         nrm[r] = 0.0f;
 #pragma unroll
-        for (int c = 0; c < 12; ++c) acc[r][c] = 0.0f;
+        for (int c = 0; c < 6; ++c) acc2[r][c] = make_float2(0.0f, 0.0f);
     }
 
     load_stage(0, 0);
@@ -70,24 +70,31 @@ rowsel_kernel(const float* __restrict__ x, int64_t bstride, int D, int N, const 
             const float4 a0 = *reinterpret_cast<const float4*>(As + c * T_ROWS + ty * 8);
             const float4 a1 = *reinterpret_cast<const float4*>(As + c * T_ROWS + ty * 8 + 4);
             const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            float bb[12];
+            float2 bb[6];
 #pragma unroll
             for (int h = 0; h < 3; ++h) {
                 const float4 t = *reinterpret_cast<const float4*>(Bs + c * RS_COLS + h * 64 + tx * 4);
-                bb[h * 4 + 0] = t.x;
-                bb[h * 4 + 1] = t.y;
-                bb[h * 4 + 2] = t.z;
-                bb[h * 4 + 3] = t.w;
+                bb[h * 2 + 0] = make_float2(t.x, t.y);
+                bb[h * 2 + 1] = make_float2(t.z, t.w);
             }
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
                 if (MODE == RS_GW) nrm[r] = fmaf(a[r], a[r], nrm[r]);
+                const float2 aa = make_float2(a[r], a[r]);
 #pragma unroll
-                for (int j = 0; j < 12; ++j) acc[r][j] = fmaf(a[r], bb[j], acc[r][j]);
+                for (int j = 0; j < 6; ++j) acc2[r][j] = __ffma2_rn(aa, bb[j], acc2[r][j]);
             }
         }
         __syncthreads();
     }
+    float acc[8][12];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            acc[r][2 * j] = acc2[r][j].x;
+            acc[r][2 * j + 1] = acc2[r][j].y;
+        }
 
     // ------------------------------- epilogue -------------------------------
     int col[12];

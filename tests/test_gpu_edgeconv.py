@@ -113,3 +113,17 @@ def test_edgeconv_fused_vs_reference_formula(B, C, N, k):
     assert torch.equal(y2, y), "argmax and plain variants disagree"
     agree = (amax.cpu().reshape(B, N, 64).permute(0, 2, 1).long() == ref_arg).float().mean()
     assert agree >= 0.98
+
+
+@pytest.mark.parametrize("N,k,frac", [(512, 20, 1.0), (2048, 20, 0.5), (1024, 40, 0.9)])
+def test_knn_tie_floods_take_the_exact_fallback(N, k, frac):
+    """floods of exact ties at the threshold (many identical points) overflow the per-tile survivor buffer; the kernel must
+    fall back to its brute-force pass and still return the oracle's answer (ties -> ascending index)"""
+    ops = _ops()
+    g = torch.Generator().manual_seed(N)
+    x = torch.rand(2, 9, N, generator=g)
+    nd = int(N * frac)
+    x[:, :, torch.randperm(N, generator=g)[:nd]] = x[:, :, :1]          # nd copies of point 0
+    idx_ref, d_ref = O.knn_exact(x, k, return_dist=True)
+    idx, d = ops.knn(x.cuda(), k, return_dist=True)
+    assert torch.equal(idx.cpu(), idx_ref) and torch.equal(d.cpu(), d_ref)
