@@ -106,16 +106,20 @@ knn_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int k, co
     KnnSmem& s = *reinterpret_cast<KnnSmem*>(smem_raw);
     float* As = reinterpret_cast<float*>(smem_raw + sizeof(KnnSmem));
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // FFMA warps are the LAST four warps: the warp scheduler's arbitration favours higher warp ids, and the FFMA warps
+    // are the critical path (the selection warps mostly wait)
+    const bool is_fma = warp >= KNN_SEL_WARPS;
+    const int tid = is_fma ? (int)threadIdx.x - 32 * KNN_SEL_WARPS : (int)threadIdx.x;
     const int b = blockIdx.y, q0 = blockIdx.x * T_ROWS;
     const int ntiles = (N + T_COLS - 1) / T_COLS;
 
-    for (int i = tid; i < T_ROWS * 64; i += KNN_THREADS) s.list[i] = make_uint2(0u, 0u);
-    if (tid < T_ROWS) {
-        s.tau[tid] = -INFINITY;
-        s.fill[tid] = 0;
+    for (int i = threadIdx.x; i < T_ROWS * 64; i += KNN_THREADS) s.list[i] = make_uint2(0u, 0u);
+    if (threadIdx.x < T_ROWS) {
+        s.tau[threadIdx.x] = -INFINITY;
+        s.fill[threadIdx.x] = 0;
     }
-    if (tid == 0) {
+    if (threadIdx.x == 0) {
         mbar_init(&s.ds_full[0], 128);
         mbar_init(&s.ds_full[1], 128);
         mbar_init(&s.ds_empty[0], 32 * KNN_SEL_WARPS);
@@ -124,7 +128,7 @@ knn_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int k, co
     }
     __syncthreads();
 
-    if (warp < 4) {
+    if (is_fma) {
         // ======================= FFMA warps: distance tiles in the pinned order =======================
         reg_alloc<168>();
         const int ty = tid >> 4, tx = tid & 15;
@@ -201,7 +205,7 @@ knn_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int k, co
     } else {
         // ======================= selection warps: threshold filter, append, merge on overflow =======================
         reg_dealloc<72>();
-        const int w = warp - 4;
+        const int w = warp;
         const unsigned lt_mask = (1u << lane) - 1u;
         for (int t = 0; t < ntiles; ++t) {
             const int db = t & 1;

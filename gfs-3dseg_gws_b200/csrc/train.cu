@@ -1,0 +1,315 @@
+// train.cu -- kernels of the TRAINING path besides the GEMM (gemm_f32.cu): batch-statistics BatchNorm forward/backward,
+// the EdgeConv edge gather / scatter, max-over-k with argmax and its backward, and row softmax forward/backward.
+//
+// Reference semantics (model.train(), train.py:614): every BatchNorm normalises with the statistics of the current batch
+// (biased variance; over B*N*k edge elements for the EdgeConv BatchNorm2d layers, model/dgcnn.py:54-55), LeakyReLU(0.2),
+// max over the k neighbours (model/dgcnn.py:118) routes its gradient to the arg-max edge, and the gather of
+// model/dgcnn.py:35-41 back-propagates as a scatter-add.  Training tensors are fp32, channel-major (C, M) with M = points
+// (or E = points * k edges, e = i*k + slot); this first version materialises the per-edge tensors (the reference does too).
+#include "common.cuh"
+
+namespace gfs {
+
+// ------------------------------------------------------------------------------------------------------------------
+// BatchNorm (batch statistics): one CTA per channel, fp64 accumulation, fixed order -> deterministic
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum(double v, double* red) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    return t;
+}
+
+__global__ void __launch_bounds__(512)
+bn_stats_kernel(const float* __restrict__ x, int64_t ld, int64_t M, float* __restrict__ mean, float* __restrict__ var) {
+    __shared__ double red[16];
+    const float* row = x + (int64_t)blockIdx.x * ld;
+    double s = 0.0, q = 0.0;
+    for (int64_t i = threadIdx.x; i < M; i += blockDim.x) {
+        const double v = row[i];
+        s += v;
+        q += v * v;
+    }
+    s = block_sum(s, red);
+    q = block_sum(q, red);
+    if (threadIdx.x == 0) {
+        const double m = s / (double)M;
+        mean[blockIdx.x] = (float)m;
+        var[blockIdx.x] = (float)fmax(q / (double)M - m * m, 0.0);
+    }
+}
+
+// y = act(x * scale[c] + shift[c]),  act(u) = u > 0 ? u : slope * u   (slope 0.2 LeakyReLU, 0 ReLU, 1 identity)
+__global__ void bn_act_fwd_kernel(const float* __restrict__ x, int64_t ldx, float* __restrict__ y, int64_t ldy, int64_t M,
+                                  const float* __restrict__ scale, const float* __restrict__ shift, float slope) {
+    const int c = blockIdx.y;
+    const float sc = scale[c], sh = shift[c];
+    const float* xr = x + (int64_t)c * ldx;
+    float* yr = y + (int64_t)c * ldy;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (int64_t)gridDim.x * blockDim.x) {
+        const float u = fmaf(xr[i], sc, sh);
+        yr[i] = u > 0.0f ? u : slope * u;
+    }
+}
+
+// g = dy * act'(u), u = gamma * xhat + beta;  sums[c] = (sum g, sum g * xhat)
+__global__ void __launch_bounds__(512)
+bn_bwd_reduce_kernel(const float* __restrict__ dy, int64_t lddy, const float* __restrict__ x, int64_t ldx, int64_t M,
+                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, float slope, float* __restrict__ sum_g, float* __restrict__ sum_gx) {
+    __shared__ double red[16];
+    const int c = blockIdx.x;
+    const float mu = mean[c], is = invstd[c], ga = gamma[c], be = beta[c];
+    const float* dr = dy + (int64_t)c * lddy;
+    const float* xr = x + (int64_t)c * ldx;
+    double s = 0.0, q = 0.0;
+    for (int64_t i = threadIdx.x; i < M; i += blockDim.x) {
+        const float xh = (xr[i] - mu) * is;
+        const float u = fmaf(ga, xh, be);
+        const float g = dr[i] * (u > 0.0f ? 1.0f : slope);
+        s += g;
+        q += (double)g * xh;
+    }
+    s = block_sum(s, red);
+    q = block_sum(q, red);
+    if (threadIdx.x == 0) {
+        sum_g[c] = (float)s;
+        sum_gx[c] = (float)q;
+    }
+}
+
+// dx = gamma * invstd * (g - sum_g / M - xhat * sum_gx / M)
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, int64_t lddy, const float* __restrict__ x, int64_t ldx,
+                                    float* __restrict__ dx, int64_t lddx, int64_t M, const float* __restrict__ mean,
+                                    const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    float slope, const float* __restrict__ sum_g, const float* __restrict__ sum_gx) {
+    const int c = blockIdx.y;
+    const float mu = mean[c], is = invstd[c], ga = gamma[c], be = beta[c];
+    const float a = sum_g[c] / (float)M, b = sum_gx[c] / (float)M, k = ga * is;
+    const float* dr = dy + (int64_t)c * lddy;
+    const float* xr = x + (int64_t)c * ldx;
+    float* o = dx + (int64_t)c * lddx;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (int64_t)gridDim.x * blockDim.x) {
+        const float xh = (xr[i] - mu) * is;
+        const float u = fmaf(ga, xh, be);
+        const float g = dr[i] * (u > 0.0f ? 1.0f : slope);
+        o[i] = k * (g - a - xh * b);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// EdgeConv edge tensor: H[c, e] = P[j(e), c] + Q[i(e), c],  e = i*k + slot,  j = block(i)*N + idx[i, slot]
+// pq: (M, 128) point-major [P | Q];  H: (64, E) channel-major.  CTA = 128 consecutive edges, transposed through smem.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+edge_gather_kernel(const float* __restrict__ pq, const int32_t* __restrict__ idx, int N, int k, int64_t E, float* __restrict__ H) {
+    __shared__ float T[64][129];
+    const int64_t e0 = (int64_t)blockIdx.x * 128;
+    const int q = threadIdx.x & 7, sub = threadIdx.x >> 3;
+#pragma unroll 2
+    for (int p = 0; p < 8; ++p) {
+        const int el = p * 16 + sub;
+        const int64_t e = e0 + el;
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+        if (e < E) {
+            const int64_t i = e / k;
+            const int64_t j = (i / N) * N + idx[e];
+            const float4* P = reinterpret_cast<const float4*>(pq + j * 128 + q * 8);
+            const float4* Q = reinterpret_cast<const float4*>(pq + i * 128 + 64 + q * 8);
+            const float4 p0 = __ldg(P), p1 = __ldg(P + 1), q0 = __ldg(Q), q1 = __ldg(Q + 1);
+            a0 = make_float4(p0.x + q0.x, p0.y + q0.y, p0.z + q0.z, p0.w + q0.w);
+            a1 = make_float4(p1.x + q1.x, p1.y + q1.y, p1.z + q1.z, p1.w + q1.w);
+        }
+        const int c = q * 8;
+        T[c + 0][el] = a0.x; T[c + 1][el] = a0.y; T[c + 2][el] = a0.z; T[c + 3][el] = a0.w;
+        T[c + 4][el] = a1.x; T[c + 5][el] = a1.y; T[c + 6][el] = a1.z; T[c + 7][el] = a1.w;
+    }
+    __syncthreads();
+    const int64_t e = e0 + threadIdx.x;
+    if (e < E)
+        for (int c = 0; c < 64; ++c) H[(int64_t)c * E + e] = T[c][threadIdx.x];
+}
+
+// backward of the gather: dP[j] += dH[:, e], dQ[i] += dH[:, e]   (dpq must be zeroed; fp32 atomics -> order not fixed)
+__global__ void __launch_bounds__(128)
+edge_scatter_kernel(const float* __restrict__ dH, const int32_t* __restrict__ idx, int N, int k, int64_t E, float* __restrict__ dpq) {
+    __shared__ float T[64][129];
+    const int64_t e0 = (int64_t)blockIdx.x * 128;
+    {
+        const int64_t e = e0 + threadIdx.x;
+        for (int c = 0; c < 64; ++c) T[c][threadIdx.x] = e < E ? dH[(int64_t)c * E + e] : 0.0f;
+    }
+    __syncthreads();
+    const int q = threadIdx.x & 7, sub = threadIdx.x >> 3;
+    for (int p = 0; p < 8; ++p) {
+        const int el = p * 16 + sub;
+        const int64_t e = e0 + el;
+        if (e >= E) continue;
+        const int64_t i = e / k;
+        const int64_t j = (i / N) * N + idx[e];
+        float* P = dpq + j * 128 + q * 8;
+        float* Q = dpq + i * 128 + 64 + q * 8;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float v = T[q * 8 + u][el];
+            atomicAdd(P + u, v);
+            atomicAdd(Q + u, v);
+        }
+    }
+}
+
+// y[c, i] = max_slot a[c, i*k + slot] (first maximum), arg[c, i] = slot
+__global__ void max_over_k_fwd_kernel(const float* __restrict__ a, int64_t M, int k, float* __restrict__ y, int64_t ldy,
+                                      uint8_t* __restrict__ arg) {
+    const int c = blockIdx.y;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    const float* r = a + (int64_t)c * M * k + i * k;
+    float best = r[0];
+    int bi = 0;
+    for (int s = 1; s < k; ++s) {
+        const float v = r[s];
+        if (v > best) {
+            best = v;
+            bi = s;
+        }
+    }
+    y[(int64_t)c * ldy + i] = best;
+    arg[(int64_t)c * M + i] = (uint8_t)bi;
+}
+
+__global__ void max_over_k_bwd_kernel(const float* __restrict__ dy, int64_t lddy, const uint8_t* __restrict__ arg, int64_t M, int k,
+                                      float* __restrict__ da) {
+    const int c = blockIdx.y;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    const float g = dy[(int64_t)c * lddy + i];
+    const int w = arg[(int64_t)c * M + i];
+    float* r = da + (int64_t)c * M * k + i * k;
+    for (int s = 0; s < k; ++s) r[s] = s == w ? g : 0.0f;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// row softmax (attention, model/attention.py:45):  p = softmax(s * scale) [* mask];  one warp per row
+// backward: ds = scale * p0 * (dp*mask - sum(dp*mask*p0)),  p0 = softmax without the mask
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void softmax_rows_fwd_kernel(const float* __restrict__ s, int64_t rows, int n, float scale, const float* __restrict__ mask,
+                                        float* __restrict__ p0, float* __restrict__ p) {
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    const float* sr = s + r * n;
+    float mx = -INFINITY;
+    for (int j = lane; j < n; j += 32) mx = fmaxf(mx, sr[j] * scale);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.0f;
+    for (int j = lane; j < n; j += 32) sum += expf(sr[j] * scale - mx);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.0f / sum;
+    for (int j = lane; j < n; j += 32) {
+        const float v = expf(sr[j] * scale - mx) * inv;
+        p0[r * n + j] = v;
+        if (p != p0) p[r * n + j] = mask ? v * mask[r * n + j] : v;
+    }
+}
+
+__global__ void softmax_rows_bwd_kernel(const float* __restrict__ p0, const float* __restrict__ dp, const float* __restrict__ mask,
+                                        int64_t rows, int n, float scale, float* __restrict__ ds) {
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    const float* pr = p0 + r * n;
+    const float* dr = dp + r * n;
+    const float* mr = mask ? mask + r * n : nullptr;
+    float dot = 0.0f;
+    for (int j = lane; j < n; j += 32) dot += pr[j] * dr[j] * (mr ? mr[j] : 1.0f);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    for (int j = lane; j < n; j += 32) ds[r * n + j] = scale * pr[j] * (dr[j] * (mr ? mr[j] : 1.0f) - dot);
+}
+
+}  // namespace gfs
+
+using namespace gfs;
+
+extern "C" int gfs_bn_stats(const float* x, int64_t ld, int C, int64_t M, float* mean, float* var, void* stream) {
+    GFS_REQUIRE(x && mean && var && C > 0 && M > 0, GFS_ERR_BAD_ARG, "gfs_bn_stats: bad argument");
+    bn_stats_kernel<<<C, 512, 0, static_cast<cudaStream_t>(stream)>>>(x, ld, M, mean, var);
+    GFS_LAUNCH_OK("bn_stats_kernel");
+    return GFS_OK;
+}
+
+extern "C" int gfs_bn_act_fwd(const float* x, int64_t ldx, float* y, int64_t ldy, int C, int64_t M, const float* scale,
+                              const float* shift, float slope, void* stream) {
+    GFS_REQUIRE(x && y && scale && shift && C > 0 && M > 0, GFS_ERR_BAD_ARG, "gfs_bn_act_fwd: bad argument");
+    const unsigned gx = (unsigned)((M + 1023) / 1024 < 1024 ? (M + 1023) / 1024 : 1024);
+    bn_act_fwd_kernel<<<dim3(gx, C), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, ldx, y, ldy, M, scale, shift, slope);
+    GFS_LAUNCH_OK("bn_act_fwd_kernel");
+    return GFS_OK;
+}
+
+extern "C" int gfs_bn_act_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, float* dx, int64_t lddx, int C, int64_t M,
+                              const float* mean, const float* invstd, const float* gamma, const float* beta, float slope,
+                              float* sum_g, float* sum_gx, void* stream) {
+    GFS_REQUIRE(dy && x && dx && mean && invstd && gamma && beta && sum_g && sum_gx && C > 0 && M > 0, GFS_ERR_BAD_ARG,
+                "gfs_bn_act_bwd: bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    bn_bwd_reduce_kernel<<<C, 512, 0, st>>>(dy, lddy, x, ldx, M, mean, invstd, gamma, beta, slope, sum_g, sum_gx);
+    GFS_LAUNCH_OK("bn_bwd_reduce_kernel");
+    const unsigned gx = (unsigned)((M + 1023) / 1024 < 1024 ? (M + 1023) / 1024 : 1024);
+    bn_bwd_apply_kernel<<<dim3(gx, C), 256, 0, st>>>(dy, lddy, x, ldx, dx, lddx, M, mean, invstd, gamma, beta, slope, sum_g, sum_gx);
+    GFS_LAUNCH_OK("bn_bwd_apply_kernel");
+    return GFS_OK;
+}
+
+extern "C" int gfs_edge_gather(const float* pq, const int32_t* idx, int B, int N, int k, float* H, void* stream) {
+    GFS_REQUIRE(pq && idx && H && B > 0 && N > 0 && k > 0, GFS_ERR_BAD_ARG, "gfs_edge_gather: bad argument");
+    const int64_t E = (int64_t)B * N * k;
+    edge_gather_kernel<<<(unsigned)((E + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(pq, idx, N, k, E, H);
+    GFS_LAUNCH_OK("edge_gather_kernel");
+    return GFS_OK;
+}
+
+extern "C" int gfs_edge_scatter(const float* dH, const int32_t* idx, int B, int N, int k, float* dpq, void* stream) {
+    GFS_REQUIRE(dH && idx && dpq && B > 0 && N > 0 && k > 0, GFS_ERR_BAD_ARG, "gfs_edge_scatter: bad argument");
+    const int64_t E = (int64_t)B * N * k;
+    edge_scatter_kernel<<<(unsigned)((E + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(dH, idx, N, k, E, dpq);
+    GFS_LAUNCH_OK("edge_scatter_kernel");
+    return GFS_OK;
+}
+
+extern "C" int gfs_max_over_k_fwd(const float* a, int C, int64_t M, int k, float* y, int64_t ldy, uint8_t* arg, void* stream) {
+    GFS_REQUIRE(a && y && arg && C > 0 && M > 0 && k > 0 && k <= 255, GFS_ERR_BAD_ARG, "gfs_max_over_k_fwd: bad argument");
+    max_over_k_fwd_kernel<<<dim3((unsigned)((M + 255) / 256), C), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, M, k, y, ldy, arg);
+    GFS_LAUNCH_OK("max_over_k_fwd_kernel");
+    return GFS_OK;
+}
+
+extern "C" int gfs_max_over_k_bwd(const float* dy, int64_t lddy, const uint8_t* arg, int C, int64_t M, int k, float* da, void* stream) {
+    GFS_REQUIRE(dy && arg && da && C > 0 && M > 0 && k > 0, GFS_ERR_BAD_ARG, "gfs_max_over_k_bwd: bad argument");
+    max_over_k_bwd_kernel<<<dim3((unsigned)((M + 255) / 256), C), 256, 0, static_cast<cudaStream_t>(stream)>>>(dy, lddy, arg, M, k, da);
+    GFS_LAUNCH_OK("max_over_k_bwd_kernel");
+    return GFS_OK;
+}
+
+extern "C" int gfs_softmax_rows_fwd(const float* s, int64_t rows, int n, float scale, const float* mask, float* p0, float* p, void* stream) {
+    GFS_REQUIRE(s && p0 && p && rows > 0 && n > 0, GFS_ERR_BAD_ARG, "gfs_softmax_rows_fwd: bad argument");
+    softmax_rows_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(s, rows, n, scale, mask, p0, p);
+    GFS_LAUNCH_OK("softmax_rows_fwd_kernel");
+    return GFS_OK;
+}
+
+extern "C" int gfs_softmax_rows_bwd(const float* p0, const float* dp, const float* mask, int64_t rows, int n, float scale, float* ds,
+                                    void* stream) {
+    GFS_REQUIRE(p0 && dp && ds && rows > 0 && n > 0, GFS_ERR_BAD_ARG, "gfs_softmax_rows_bwd: bad argument");
+    softmax_rows_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(p0, dp, mask, rows, n, scale, ds);
+    GFS_LAUNCH_OK("softmax_rows_bwd_kernel");
+    return GFS_OK;
+}

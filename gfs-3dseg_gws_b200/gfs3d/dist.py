@@ -38,3 +38,22 @@ def all_same(flag_local: bool, device, group=None) -> bool:
     t = torch.tensor([0.0 if flag_local else 1.0], dtype=torch.float64, device=device)
     dist.all_reduce(t, group=group)
     return float(t[0]) == 0.0
+
+
+def allreduce_gradients(params, group=None):
+    """data-parallel training: ONE all-reduce per step over a flat fp32 bucket of all gradients
+    (398 144 floats = 1.6 MB for the S3DIS model: latency-bound on NVLink), averaged over the world.  BatchNorm statistics
+    stay per replica (the reference has no SyncBN)."""
+    import torch.distributed as dist
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads or not (dist.is_available() and dist.is_initialized()):
+        return 0
+    flat = torch.cat([g.reshape(-1).float() for g in grads])
+    dist.all_reduce(flat, group=group)
+    flat.div_(dist.get_world_size(group))
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n
+    return flat.numel()

@@ -221,3 +221,110 @@ def kmeans_accumulate(X: torch.Tensor, labels: torch.Tensor, K: int, n_valid: Op
     _call("gfs_kmeans_accumulate", 2, _ptr(X), n, D, _ptr(labels), K, _ptr(partial), _ptr(pcount), _ptr(sums), _ptr(counts),
                                       _stream())
     return sums, counts
+
+
+# =====================================================================================================================
+# training path: raw wrappers (fp32, channel-major (C, M) 2-D tensors)
+# =====================================================================================================================
+def gemm_f32(A, lda, a_trans, B, ldb, b_trans, R, Ncols, K, C, ldc, c_trans=False, bias=None, batch=1, a_bs=0, b_bs=0, c_bs=0,
+             splitk=1, accumulate=False):
+    _need_cuda(A, B, C, bias)
+    ws = torch.empty(splitk * R * Ncols, dtype=torch.float32, device=C.device) if splitk > 1 else None
+    _call("gfs_gemm_f32", 2 if splitk > 1 else 1, _ptr(A), lda, int(a_trans), a_bs, _ptr(B), ldb, int(b_trans), b_bs, _ptr(C), ldc,
+          int(c_trans), c_bs, _ptr(bias), R, Ncols, K, batch, splitk, _ptr(ws), int(accumulate), _stream())
+    return C
+
+
+def _splitk(K):
+    return int(max(1, min(96, K // 8192)))
+
+
+def conv_fwd(W, x, bias=None):
+    """z (O, M) = W (O, I) . x (I, M) [+ bias]"""
+    O, I = W.shape
+    M = x.shape[1]
+    z = torch.empty(O, M, dtype=torch.float32, device=x.device)
+    return gemm_f32(W, I, True, x, x.stride(0), False, O, M, I, z, M, bias=bias)
+
+
+def conv_dgrad(W, dz):
+    """dx (I, M) = W^T . dz (O, M)"""
+    O, I = W.shape
+    M = dz.shape[1]
+    dx = torch.empty(I, M, dtype=torch.float32, device=dz.device)
+    return gemm_f32(W, I, False, dz, dz.stride(0), False, I, M, O, dx, M)
+
+
+def conv_wgrad(dz, x):
+    """dW (O, I) = dz (O, M) . x (I, M)^T   (contraction over the M points: split-K, fixed-order reduction)"""
+    O, M = dz.shape
+    I = x.shape[0]
+    dW = torch.empty(O, I, dtype=torch.float32, device=x.device)
+    return gemm_f32(dz, dz.stride(0), True, x, x.stride(0), True, O, I, M, dW, I, splitk=_splitk(M))
+
+
+def bn_stats(x):
+    C, M = x.shape
+    mean = torch.empty(C, dtype=torch.float32, device=x.device)
+    var = torch.empty(C, dtype=torch.float32, device=x.device)
+    _call("gfs_bn_stats", 1, _ptr(x), x.stride(0), C, M, _ptr(mean), _ptr(var), _stream())
+    return mean, var
+
+
+def bn_act_fwd(x, scale, shift, slope, out=None):
+    C, M = x.shape
+    y = torch.empty(C, M, dtype=torch.float32, device=x.device) if out is None else out
+    _call("gfs_bn_act_fwd", 1, _ptr(x), x.stride(0), _ptr(y), y.stride(0), C, M, _ptr(scale), _ptr(shift), float(slope), _stream())
+    return y
+
+
+def bn_act_bwd(dy, x, mean, invstd, gamma, beta, slope):
+    C, M = x.shape
+    dx = torch.empty(C, M, dtype=torch.float32, device=x.device)
+    sg = torch.empty(C, dtype=torch.float32, device=x.device)
+    sgx = torch.empty(C, dtype=torch.float32, device=x.device)
+    _call("gfs_bn_act_bwd", 2, _ptr(dy), dy.stride(0), _ptr(x), x.stride(0), _ptr(dx), M, C, M, _ptr(mean), _ptr(invstd), _ptr(gamma),
+          _ptr(beta), float(slope), _ptr(sg), _ptr(sgx), _stream())
+    return dx, sg, sgx
+
+
+def edge_gather(pq, idx, B, N, k):
+    H = torch.empty(64, B * N * k, dtype=torch.float32, device=pq.device)
+    _call("gfs_edge_gather", 1, _ptr(pq), _ptr(idx), B, N, k, _ptr(H), _stream())
+    return H
+
+
+def edge_scatter(dH, idx, B, N, k):
+    dpq = torch.zeros(B * N, 128, dtype=torch.float32, device=dH.device)
+    _call("gfs_edge_scatter", 1, _ptr(dH), _ptr(idx), B, N, k, _ptr(dpq), _stream())
+    return dpq
+
+
+def max_over_k_fwd(a, M, k):
+    C = a.shape[0]
+    y = torch.empty(C, M, dtype=torch.float32, device=a.device)
+    arg = torch.empty(C, M, dtype=torch.uint8, device=a.device)
+    _call("gfs_max_over_k_fwd", 1, _ptr(a), C, M, k, _ptr(y), M, _ptr(arg), _stream())
+    return y, arg
+
+
+def max_over_k_bwd(dy, arg, k):
+    C, M = arg.shape
+    da = torch.empty(C, M * k, dtype=torch.float32, device=dy.device)
+    _call("gfs_max_over_k_bwd", 1, _ptr(dy), dy.stride(0), _ptr(arg), C, M, k, _ptr(da), _stream())
+    return da
+
+
+def softmax_rows_fwd(s, scale, mask=None):
+    rows, n = s.shape[0] * s.shape[1], s.shape[2]
+    p0 = torch.empty_like(s)
+    p = torch.empty_like(s) if mask is not None else p0
+    _call("gfs_softmax_rows_fwd", 1, _ptr(s), rows, n, float(scale), _ptr(mask), _ptr(p0), _ptr(p), _stream())
+    return p0, p
+
+
+def softmax_rows_bwd(p0, dp, scale, mask=None):
+    rows, n = p0.shape[0] * p0.shape[1], p0.shape[2]
+    ds = torch.empty_like(p0)
+    _call("gfs_softmax_rows_bwd", 1, _ptr(p0), _ptr(dp), _ptr(mask), rows, n, float(scale), _ptr(ds), _stream())
+    return ds

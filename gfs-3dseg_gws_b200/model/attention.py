@@ -35,10 +35,21 @@ class SelfAttention(nn.Module):
             self._key = key
         return self._wp
 
+    def forward_train(self, x_cm, B, N):
+        """training mode: x_cm (in_channel, M) -> (64, M); dropout on the attention weights as model/attention.py:45"""
+        from gfs3d.train_ops import AttentionTrain, ConvOnly
+        w = torch.cat([self.q_map.weight, self.k_map.weight, self.v_map.weight], dim=0).reshape(3 * self.out_channel, self.in_channel)
+        qkv = ConvOnly.apply(x_cm, w)
+        mask = None
+        if self.dropout.p > 0:
+            keep = 1.0 - self.dropout.p
+            mask = (torch.rand(B, N, N, device=x_cm.device) < keep).float() / keep
+        return AttentionTrain.apply(qkv, B, N, 1.0 / self.temperature, mask)
+
     def forward_fused(self, x_act, B, N, y_cm=None, y_act=None, y_kb=0):
         """x_act: bf16 act tiles (B*N, in_channel).  Writes y (B, 64, N) fp32 cm and/or one bf16 act block."""
         if self.training:
-            raise NotImplementedError("SelfAttention training-mode forward is not built yet in the B200 path")
+            raise RuntimeError("forward_fused is the inference path; training mode goes through forward_train")
         if self.out_channel != 64:
             raise NotImplementedError("the tcgen05 attention kernel is built for out_channel = 64")
         wp = self._prepare(x_act.device)
@@ -48,6 +59,11 @@ class SelfAttention(nn.Module):
 
     def forward(self, x):
         """(B, in_channel, N) -> (B, out_channel, N)"""
+        if self.training:
+            from gfs3d.train_ops import from_cm, to_cm
+            if self.out_channel != 64:
+                raise NotImplementedError("the attention kernels are built for out_channel = 64")
+            return from_cm(self.forward_train(to_cm(x.float()), x.shape[0], x.shape[2]), x.shape[0], x.shape[2])
         if x.dtype != torch.float32 or x.stride(2) != 1 or x.stride(1) != x.shape[2]:
             x = x.float().contiguous()
         B, C, N = x.shape

@@ -82,9 +82,7 @@ class mpti_net_Point_GeoAsWeight_v2(nn.Module):
     def _features(self, x, need_semantic=False):
         """-> (point_feat (B,128,N) fp32 cm, assignment (B,N) int32, semantic (B,192,N) fp32 or None)"""
         if self.training:
-            raise NotImplementedError(
-                "training-mode forward of the GW model is not built yet in the B200 path (eval / inference only); "
-                "there is deliberately no PyTorch fallback")
+            return self._features_train(x, need_semantic)
         if not x.is_cuda:
             raise RuntimeError("the GW model needs CUDA tensors: the hot path has no CPU fallback")
         hd = self._prepare(x.device)
@@ -104,6 +102,30 @@ class mpti_net_Point_GeoAsWeight_v2(nn.Module):
         if need_semantic:
             semantic[:, 0:64, :].copy_(enc.ec[:, 0:64, :])
         return point_feat, assignment, semantic
+
+    def _features_train(self, x, need_semantic=False):
+        """training mode (model/capl.py:324-362 under model.train()): fp32, batch-statistics BatchNorm, differentiable through
+        the hand-written training kernels (gfs3d/train_ops.py).  Same return convention as _features."""
+        from gfs3d.train_ops import ConvBNAct, ConvConstW, from_cm, update_running_stats
+        if not x.is_cuda:
+            raise RuntimeError("the GW model needs CUDA tensors: the hot path has no CPU fallback")
+        B, _, N = x.shape
+        M = B * N
+        ecs, lvl2 = self.encoder.forward_train(x)                        # channel-major (64, M) x3, (256, M)
+        lvl3 = self.base_learner.forward_train(lvl2)
+        att = self.att_learner.forward_train(lvl2, B, N)
+        ec = torch.cat(ecs, dim=0)                                       # (192, M)
+        semantic = torch.cat([ecs[0], att, lvl3], dim=0)                 # (192, M)
+        ec_l2 = ec / ec.norm(dim=0, keepdim=True).clamp_min(1e-12)
+        gp_l2 = F.normalize(self.gp.detach().float().to(x.device), p=2, dim=1)
+        cos = ConvConstW.apply(ec_l2, gp_l2)                             # (G, M)
+        cosine_feat = torch.softmax(10 * cos, dim=0)
+        assignment = cosine_feat.argmax(dim=0).reshape(B, N).int()
+        conv, bn = self.fusion[0], self.fusion[1]
+        w = conv.weight.reshape(conv.weight.shape[0], conv.weight.shape[1])
+        pf, m, v = ConvBNAct.apply(torch.cat([cosine_feat, semantic], dim=0), w, conv.bias, bn.weight, bn.bias, None, None, 0.2, True)
+        update_running_stats(bn, m, v, M)
+        return from_cm(pf, B, N), assignment, (from_cm(semantic, B, N) if need_semantic else None)
 
     def getFeatures(self, x, segment_label=None):
         """(B, C_in, N) -> point_feat (B,128,N), semantic_feat (B,192,N), one_hot_feat (B,G,N) float 0/1"""
@@ -129,12 +151,18 @@ class mpti_net_Point_GeoAsWeight_v2(nn.Module):
             if use_bg_proto:
                 proto = torch.cat([self.bg_proto, proto], dim=0)
             pn = F.normalize(proto, p=2, dim=1)
+        if torch.is_grad_enabled() and (x.requires_grad or pn.requires_grad):
+            # training branch: O(B * cls * N) prototype algebra stays in differentiable torch ops
+            return torch.matmul(pn if pn.dim() == 3 else pn.unsqueeze(0), F.normalize(x, p=2, dim=1)) * 10
         return ops.cos_logits(_cm(x), pn.detach())
 
     def post_refine_proto_v2(self, proto, x, point_feat, use_bg_proto=False):
         """query-adaptive prototype refinement (eqn. 6) -> (b, classes, c)"""
         pred = self.get_pred(x, proto, use_bg_proto)
-        pred_proto = ops.softmax_pool(pred, _cm(point_feat))
+        if pred.requires_grad or point_feat.requires_grad:
+            pred_proto = torch.softmax(pred, dim=2) @ point_feat.permute(0, 2, 1)
+        else:
+            pred_proto = ops.softmax_pool(pred, _cm(point_feat))
         if use_bg_proto:
             pred_proto = pred_proto[:, 1:, :]
         w = (F.normalize(pred_proto, 2, -1) * F.normalize(proto, 2, -1).unsqueeze(0)).sum(-1, keepdim=True)
@@ -167,8 +195,7 @@ class mpti_net_Point_GeoAsWeight_v2(nn.Module):
                 geo2sem_proto=None, base_class_coding=None, novel_class_coding=None, bg_class_coding=None):
         base_num = self.base_num
         if not eval_model:
-            raise NotImplementedError(
-                "the training branch (model/capl.py:194-242) is not built yet in the B200 path; eval_model=True only")
+            return self._forward_train(x, y)
         point_feat, assignment, _ = self._features(x)
         if gened_proto.dim() == 3:
             gened_proto = gened_proto[0]
@@ -189,8 +216,44 @@ class mpti_net_Point_GeoAsWeight_v2(nn.Module):
                 gp_acc, gp_novel_acc = 0., 0.
         return x_pre, gp_acc, gp_novel_acc
 
+    def _forward_train(self, x, y):
+        """model/capl.py:194-242: episodic base training.  Second half of the batch plays the support set for the fake-novel
+        prototypes (eqn. 8), whole batch is the query; loss = 0.5 * (CE(pred with fake protos) + CE(pred with refined protos))."""
+        base_num = self.base_num
+        point_feat, _, _ = self._features(x)
+        fake_num = x.size(0) // 2
+        ori_proto, fake_novel = self.generate_fake_proto(x=point_feat[fake_num:], y=y[fake_num:], main_proto=self.main_proto.clone())
+        x_pre_1 = self.get_pred(x=point_feat, proto=ori_proto, use_bg_proto=True)
+        loss_ce_1 = self.criterion(x_pre_1, y)
+        refine_proto = self.post_refine_proto_v2(proto=self.main_proto.clone(), x=point_feat, point_feat=point_feat, use_bg_proto=True)
+        post_refine_proto = refine_proto.clone()
+        post_refine_proto[:, :base_num] = post_refine_proto[:, :base_num] + ori_proto[:base_num].unsqueeze(0)
+        post_refine_proto[:, base_num:] = post_refine_proto[:, base_num:] * 0 + ori_proto[base_num:].unsqueeze(0)
+        x_pre_2 = self.get_pred(x=point_feat, proto=post_refine_proto, use_bg_proto=True)
+        loss_ce_2 = self.criterion(x_pre_2, y)
+        return x_pre_2.max(1)[1], 0.5 * loss_ce_2 + 0.5 * loss_ce_1
+
     def generate_fake_proto(self, x, y, main_proto, fake_novel=None, post_processing=False):
-        raise NotImplementedError("training-only episodic helper (model/capl.py:364-411): training branch not built yet")
+        """model/capl.py:364-411 (training only): half of the classes present in the support half-batch are declared
+        'fake novel'; their classifier rows are replaced by the masked mean of the L2-normalised support features."""
+        tmp_y = y.unsqueeze(1)
+        unique_y = list(tmp_y.unique())
+        if fake_novel is None:
+            if 0 in unique_y:
+                unique_y.remove(0)
+            novel_num = len(unique_y) // 2
+            fake_novel = random.sample(unique_y, novel_num)
+        new_proto = main_proto / (torch.norm(main_proto, 2, 1, True) + 1e-12)
+        x = x / (torch.norm(x, 2, 1, True) + 1e-12)
+        for fn in fake_novel:
+            tmp_mask = (tmp_y == fn).float()
+            tmp_feat = (x * tmp_mask).sum(0).sum(-1) / (tmp_mask.sum(0).sum(-1) + 1e-12)
+            if post_processing:
+                tmp_feat = self.post_processing_hard_coding(tmp_feat)
+            fake_vec = torch.zeros(new_proto.size(0), 1, device=new_proto.device)
+            fake_vec[fn.long() - 1] = 1
+            new_proto = new_proto * (1 - fake_vec) + tmp_feat.unsqueeze(0) * fake_vec
+        return new_proto, fake_novel
 
     def post_processing_hard_coding(self, coding):
         """keep the most frequent geometric words up to `energy` of the mass -> multi-hot (model/capl.py:413-433)"""

@@ -177,12 +177,10 @@ class DGCNN(nn.Module):
     def forward_fused(self, x, want_lvl2_cm=True, level1_act=None, level1_kb=0) -> EncoderOutput:
         """x (B, nfeat, N) CUDA fp32.  Runs the whole backbone in the sm_100a kernels and returns device buffers:
         ec (B, 64*L, N) fp32, cat_act / lvl2_act bf16 act tiles, lvl2_cm (B, mlp[-1], N) fp32 if requested."""
-        if self.training:
-            raise NotImplementedError(
-                "DGCNN training-mode forward (batch-statistics BatchNorm + backward) is not built yet in the B200 path; "
-                "call .eval() -- there is deliberately no PyTorch fallback")
         if not x.is_cuda:
             raise RuntimeError("DGCNN needs CUDA tensors: the hot path has no CPU fallback")
+        if self.training:
+            raise RuntimeError("forward_fused is the inference path; training mode goes through forward_train")
         layers, mlp = self._prepare(x.device)
         x = _cm(x)
         B, _, N = x.shape
@@ -209,7 +207,41 @@ class DGCNN(nn.Module):
             cur, cur_kb = nxt, nout // 64
         return EncoderOutput(ec, cat_act, cur, lvl2_cm, B, N)
 
+    def forward_train(self, x):
+        """training mode (model.train(), train.py:614): batch-statistics BatchNorm, fp32, autograd through the hand-written
+        forward/backward kernels of gfs3d/train_ops.py.  Returns channel-major tensors: ([ec_i (64, M)], out (mlp[-1], M))."""
+        from gfs3d.train_ops import ConvBNAct, EdgeConvTrain, from_cm, to_cm, update_running_stats
+        if not x.is_cuda:
+            raise RuntimeError("DGCNN needs CUDA tensors: the hot path has no CPU fallback")
+        self._check_supported()
+        x = x.float()
+        B, _, N = x.shape
+        M = B * N
+        cur_bcn, cur_cm = x.detach().contiguous(), to_cm(x)
+        outs = []
+        for blk in self.edge_convs:
+            (c1, b1), (c2, b2) = blk.stages()
+            idx = ops.knn(cur_bcn, self.k)                       # integer graph: not differentiated (as in the reference)
+            y, m1, v1, m2, v2 = EdgeConvTrain.apply(cur_cm, idx, c1.weight, b1.weight, b1.bias, c2.weight, b2.weight, b2.bias,
+                                                    B, N, self.k)
+            update_running_stats(b1, m1, v1, M * self.k)
+            update_running_stats(b2, m2, v2, M * self.k)
+            outs.append(y)
+            cur_cm, cur_bcn = y, from_cm(y.detach(), B, N)
+        cur = torch.cat(outs, dim=0)
+        for conv, bn in self.conv.stages():
+            w = conv.weight.reshape(conv.weight.shape[0], conv.weight.shape[1])
+            cur, m, v = ConvBNAct.apply(cur, w, None, bn.weight, bn.bias, None, None, 0.2, True)
+            update_running_stats(bn, m, v, M)
+        return outs, cur
+
     def forward(self, x):
+        if self.training:
+            from gfs3d.train_ops import from_cm
+            B, _, N = x.shape
+            outs, cur = self.forward_train(x)
+            ecs = [from_cm(o, B, N) for o in outs]
+            return (ecs, from_cm(cur, B, N)) if self.return_edgeconvs else (ecs[0], from_cm(cur, B, N))
         out = self.forward_fused(x, want_lvl2_cm=True)
         edgeconv_outputs: List[torch.Tensor] = [out.ec[:, 64 * i:64 * (i + 1), :] for i in range(self.n_edgeconv)]
         if self.return_edgeconvs:
@@ -245,10 +277,22 @@ class BaseLearner(nn.Module):
             self._folded.key, self._folded.data = key, out
         return self._folded.data
 
+    def forward_train(self, x_cm):
+        """x_cm (in_channels, M) -> (params[-1], M); Conv1d(+bias)+BN with ReLU between layers, batch statistics"""
+        from gfs3d.train_ops import ConvBNAct, update_running_stats
+        M = x_cm.shape[1]
+        cur = x_cm
+        for i, seq in enumerate(self.convs):
+            conv, bn = seq[0], seq[1]
+            w = conv.weight.reshape(conv.weight.shape[0], conv.weight.shape[1])
+            cur, m, v = ConvBNAct.apply(cur, w, conv.bias, bn.weight, bn.bias, None, None, 0.0 if i != self.num_convs - 1 else 1.0, True)
+            update_running_stats(bn, m, v, M)
+        return cur
+
     def forward_fused(self, x_act, B, N, y_act=None, y_kb0=0, y_cm=None):
         """x_act: bf16 act tiles of the (B*N, in_channels) input.  Last layer writes y_act / y_cm."""
         if self.training:
-            raise NotImplementedError("BaseLearner training-mode forward is not built yet in the B200 path")
+            raise RuntimeError("forward_fused is the inference path; training mode goes through forward_train")
         stages = self._prepare(x_act.device)
         cur = x_act
         for i, (wp, shift, nout, kb) in enumerate(stages):
@@ -262,6 +306,9 @@ class BaseLearner(nn.Module):
 
     def forward(self, x):
         """(B, C, N) fp32 -> (B, params[-1], N) fp32"""
+        if self.training:
+            from gfs3d.train_ops import from_cm, to_cm
+            return from_cm(self.forward_train(to_cm(x.float())), x.shape[0], x.shape[2])
         x = _cm(x)
         B, C, N = x.shape
         if C % 64 != 0:

@@ -151,6 +151,43 @@ int gfs_kmeans_partials(void);
 int gfs_kmeans_accumulate(const float* X, int64_t n, int D, const int32_t* labels, int K,
                           float* partial, int32_t* pcount, double* sums, int64_t* counts, void* stream);
 
+/* =====================================================================================================================
+ * TRAINING path (model.train(), train.py:614-631).  fp32 end to end, activations channel-major (C, M) with M = B*N points
+ * or E = B*N*k edges (e = i*k + slot).  Round-1 version: correct first -- the per-edge tensors are materialised.
+ * ===================================================================================================================== */
+
+/* generic fp32 GEMM on the packed-FFMA2 core: every 1x1 conv forward (A = W^T), data gradient (A = W) and weight gradient
+ * (both operands transposed, contraction over the points, split-K with a fixed-order reduction) of model/dgcnn.py:53-58,
+ * 63-80 and model/capl.py:63-65,435-457; also the batched q^T k / p v products of model/attention.py:43-46.
+ *   C[r, n] = bias[r] + sum_k Aop(k, r) * Bop(k, n);  Aop(k, r) = a_trans ? A[r*lda + k] : A[k*lda + r]  (B likewise with n)
+ *   C stored [r*ldc + n] or, with c_trans, [n*ldc + r];  batch > 1 uses the element strides *_bstride
+ *   splitk > 1 (batch == 1): workspace of splitk*R*Ncols floats; accumulate != 0 adds into C instead of overwriting      */
+int gfs_gemm_f32(const float* A, int64_t lda, int a_trans, int64_t a_bstride,
+                 const float* B, int64_t ldb, int b_trans, int64_t b_bstride,
+                 float* C, int64_t ldc, int c_trans, int64_t c_bstride,
+                 const float* bias, int R, int Ncols, int K, int batch, int splitk, float* workspace, int accumulate, void* stream);
+
+/* BatchNorm with batch statistics (nn.BatchNorm1d/2d in training mode, model/dgcnn.py:54-55,73-74): biased variance      */
+int gfs_bn_stats(const float* x, int64_t ld, int C, int64_t M, float* mean, float* var, void* stream);
+/* y = act(x*scale[c] + shift[c]);  act(u) = u > 0 ? u : slope*u  (0.2 LeakyReLU, 0 ReLU, 1 identity)                      */
+int gfs_bn_act_fwd(const float* x, int64_t ldx, float* y, int64_t ldy, int C, int64_t M,
+                   const float* scale, const float* shift, float slope, void* stream);
+/* backward of y = act(gamma*xhat + beta): dx, and sum_g = dbeta, sum_gx = dgamma (per channel)                           */
+int gfs_bn_act_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, float* dx, int64_t lddx, int C, int64_t M,
+                   const float* mean, const float* invstd, const float* gamma, const float* beta, float slope,
+                   float* sum_g, float* sum_gx, void* stream);
+
+/* edge tensor of model/dgcnn.py:35-41 after the split first conv: H[c, e] = P[j(e), c] + Q[i(e), c]  (pq point-major (M,128)) */
+int gfs_edge_gather(const float* pq, const int32_t* idx, int B, int N, int k, float* H, void* stream);
+/* its backward: dP[j] += dH[:, e], dQ[i] += dH[:, e]  (dpq (M,128) must be zeroed by the caller; fp32 atomics)            */
+int gfs_edge_scatter(const float* dH, const int32_t* idx, int B, int N, int k, float* dpq, void* stream);
+/* model/dgcnn.py:118: y[c, i] = max over the k slots of a[c, i*k + slot] (first maximum) + arg-max slot; and its backward  */
+int gfs_max_over_k_fwd(const float* a, int C, int64_t M, int k, float* y, int64_t ldy, uint8_t* arg, void* stream);
+int gfs_max_over_k_bwd(const float* dy, int64_t lddy, const uint8_t* arg, int C, int64_t M, int k, float* da, void* stream);
+/* model/attention.py:45: p0 = softmax(s*scale) per row, p = p0 * mask (dropout mask, may be NULL with p == p0); backward   */
+int gfs_softmax_rows_fwd(const float* s, int64_t rows, int n, float scale, const float* mask, float* p0, float* p, void* stream);
+int gfs_softmax_rows_bwd(const float* p0, const float* dp, const float* mask, int64_t rows, int n, float scale, float* ds, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

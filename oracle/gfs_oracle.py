@@ -207,11 +207,11 @@ def base_learner(sd: SD, prefix: str, x: torch.Tensor, training: bool = False) -
 # GW head  (model/capl.py)
 # ----------------------------------------------------------------------------------------
 def get_features(sd: SD, gp: torch.Tensor, x: torch.Tensor, k: int = 20,
-                 idx_list=None, knn: str = "formula"):
+                 idx_list=None, knn: str = "formula", training: bool = False):
     """model/capl.py:324-362.  Returns dict with point_feat, semantic_feat, one_hot_feat and
     the intermediates the parity tests look at."""
-    ecs, lvl2, used = dgcnn_forward(sd, x, k, "encoder.", idx_list, knn)
-    lvl3 = base_learner(sd, "base_learner", lvl2)
+    ecs, lvl2, used = dgcnn_forward(sd, x, k, "encoder.", idx_list, knn, training)
+    lvl3 = base_learner(sd, "base_learner", lvl2, training)
     att = self_attention(sd, "att_learner", lvl2)
     ec = torch.cat(ecs, dim=1)
     semantic = torch.cat([ecs[0], att, lvl3], dim=1)
@@ -221,7 +221,7 @@ def get_features(sd: SD, gp: torch.Tensor, x: torch.Tensor, k: int = 20,
     one_hot = F.one_hot(assignment, num_classes=gp.shape[0]).transpose(2, 1).float()
     z = torch.cat([cosine_feat, semantic], dim=1)
     z = F.conv1d(z, sd["fusion.0.weight"], sd["fusion.0.bias"])
-    z = F.leaky_relu(_bn(sd, "fusion.1", z), 0.2)
+    z = F.leaky_relu(_bn(sd, "fusion.1", z, training), 0.2)
     return dict(point_feat=z, semantic_feat=semantic, one_hot_feat=one_hot, edge_convs=ec,
                 feat_level2=lvl2, att_feat=att, feat_level3=lvl3, cos=cos,
                 cosine_feat=cosine_feat, assignment=assignment, idx=used)
@@ -288,6 +288,40 @@ def forward_eval(sd: SD, gp: torch.Tensor, x: torch.Tensor, gened_proto: torch.T
     logits = logits * get_gp_weight(coding, f["one_hot_feat"], eval_weight)
     f["refine_proto"] = rp
     return logits, f
+
+
+def generate_fake_proto(x: torch.Tensor, y: torch.Tensor, main_proto: torch.Tensor, fake_novel: Sequence[int]) -> torch.Tensor:
+    """model/capl.py:364-411 with the sampled fake-novel class ids given (the reference draws them with random.sample)."""
+    ty = y.unsqueeze(1)
+    proto = main_proto / (main_proto.norm(2, 1, True) + 1e-12)
+    xn = x / (x.norm(2, 1, True) + 1e-12)
+    for fn in fake_novel:
+        m = (ty == fn).to(x.dtype)
+        feat = (xn * m).sum(0).sum(-1) / (m.sum(0).sum(-1) + 1e-12)
+        sel = torch.zeros(proto.shape[0], 1, dtype=x.dtype)
+        sel[int(fn) - 1] = 1
+        proto = proto * (1 - sel) + feat.unsqueeze(0) * sel
+    return proto
+
+
+def forward_train(sd: SD, gp: torch.Tensor, x: torch.Tensor, y: torch.Tensor, base_num: int, fake_novel: Sequence[int],
+                  k: int = 20, idx_list=None, knn: str = "formula", ignore_index: int = 255):
+    """model/capl.py:194-242 (training branch, attention dropout off): returns (pred labels, loss, features dict).
+    sd may hold tensors with requires_grad=True: the loss is differentiable w.r.t. them (autograd is the gradient oracle)."""
+    f = get_features(sd, gp, x, k, idx_list, knn, training=True)
+    pf = f["point_feat"]
+    half = x.shape[0] // 2
+    main = sd["main_proto"]
+    ori = generate_fake_proto(pf[half:], y[half:], main.clone(), fake_novel)
+    bg = sd["bg_proto"]
+    l1 = F.cross_entropy(get_pred(pf, ori, bg), y, ignore_index=ignore_index)
+    rp = post_refine_proto_v2(main.clone(), pf, bg)
+    rp2 = rp.clone()
+    rp2[:, :base_num] = rp2[:, :base_num] + ori[:base_num].unsqueeze(0)
+    rp2[:, base_num:] = rp2[:, base_num:] * 0 + ori[base_num:].unsqueeze(0)
+    logits2 = get_pred(pf, rp2, bg)
+    l2 = F.cross_entropy(logits2, y, ignore_index=ignore_index)
+    return logits2.max(1)[1], 0.5 * l2 + 0.5 * l1, f
 
 
 # ----------------------------------------------------------------------------------------

@@ -105,6 +105,60 @@ def make_gfs(name, B, N, classes, base_num, G, seed, wname):
          idx0=idx[0], idx1=idx[1], idx2=idx[2], feat_level2=f["feat_level2"].numpy())
 
 
+def make_train(name, B, N, seed):
+    """one training step of the real reference on CPU (model/capl.py:194-242): loss, predictions, gradients, updated BN
+    running statistics.  capl.py:406 hard-codes .cuda(); it is neutralised HERE (not in the reference) by making
+    Tensor.cuda the identity for the duration of the call.  Attention dropout is set to p = 0."""
+    import random
+    torch.manual_seed(321)
+    args = ref_args()
+    classes, base_num, G = 13, 7, 150
+    gp = torch.randn(G, 192, generator=torch.Generator().manual_seed(7))
+    m = mpti_net_Point_GeoAsWeight_v2(classes=classes, criterion=torch.nn.CrossEntropyLoss(ignore_index=255), args=args,
+                                      base_num=base_num, gp=gp.clone(), energy=0.9)
+    sd0 = {k_: v.clone() for k_, v in m.state_dict().items()}
+    sd0 = O.randomize_bn_(sd0, seed=6)
+    m.load_state_dict(sd0)
+    m.train()
+    m.att_learner.dropout.p = 0.0
+    x = O.synthetic_blocks(B, N, seed=seed)
+    y = torch.randint(0, base_num + 1, (B, N), generator=torch.Generator().manual_seed(seed))
+    orig_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        random.seed(99)
+        pred, loss = m(x=x, y=y)
+        loss.backward()
+    finally:
+        torch.Tensor.cuda = orig_cuda
+    # which fake-novel classes did random.sample pick?  replay the same draw
+    random.seed(99)
+    uy = [int(v) for v in y[B // 2:].unique() if int(v) != 0]
+    fake_novel = random.sample(uy, len(uy) // 2)
+    # oracle replay (fp32 autograd on the restated formulas)
+    sdg = {k_: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k_ else v.clone()) for k_, v in sd0.items()}
+    o_pred, o_loss, _ = O.forward_train(sdg, gp, x, y, base_num, fake_novel)
+    o_loss.backward()
+    grads = {k_: p.grad for k_, p in m.named_parameters()}
+    dmax = max(float((grads[k_] - sdg[k_].grad).abs().max()) for k_ in grads if sdg[k_].grad is not None)
+    print(f"{name}: loss ref {float(loss):.6f} oracle {float(o_loss):.6f}; max |grad diff| {dmax:.3e}; pred agree "
+          f"{float((pred == o_pred).float().mean()):.4f}; fake_novel {fake_novel}")
+    assert abs(float(loss) - float(o_loss)) < 1e-6 and dmax < 1e-5
+    keep = ["main_proto", "bg_proto", "fusion.0.weight", "fusion.0.bias", "fusion.1.weight", "encoder.edge_convs.0.layer.0.weight",
+            "encoder.edge_convs.0.layer.1.weight", "encoder.edge_convs.1.layer.3.weight", "encoder.edge_convs.2.layer.4.bias",
+            "encoder.conv.layer.0.weight", "encoder.conv.layer.4.weight", "att_learner.q_map.weight", "att_learner.v_map.weight",
+            "base_learner.convs.0.0.weight", "base_learner.convs.1.1.bias"]
+    after = m.state_dict()
+    save(name, x=x.numpy(), y=y.numpy().astype(np.int16), gp=gp.numpy(), fake_novel=np.array(fake_novel, np.int32), loss=np.float32(float(loss)),
+         pred=pred.numpy().astype(np.int16), base_num=np.int32(base_num), classes=np.int32(classes),
+         **{"grad." + k_: grads[k_].numpy() for k_ in keep},
+         **{"gradnorm." + k_: np.float32(g_.norm()) for k_, g_ in grads.items()},
+         **{"after." + k_: after[k_].numpy() for k_ in after if "running" in k_ and ("edge_convs.0" in k_ or "fusion" in k_ or "conv.layer.4" in k_)})
+    # weights: identical to gfs_s3dis_weights.npz (same seeds), not stored twice
+    ref_w = np.load(os.path.join(HERE, "gfs_s3dis_weights.npz"))
+    assert all((ref_w[k_] == sd0[k_].numpy()).all() for k_ in ref_w.files)
+
+
 def make_kmeans(name, n, D, K, seed):
     """sklearn KMeans driven exactly as get_basis.py:210 does, with an injected init (pins the Lloyd part)."""
     import sklearn
@@ -139,7 +193,7 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="")
     a = ap.parse_args()
-    todo = a.only.split(",") if a.only else ["dgcnn", "gfs", "kmeans"]
+    todo = a.only.split(",") if a.only else ["dgcnn", "gfs", "kmeans", "train"]
     if "dgcnn" in todo:
         sd = make_dgcnn("dgcnn_b2_n256", 2, 256, 20, seed=1234)
         save("dgcnn_weights", **np_sd(sd))
@@ -149,6 +203,8 @@ if __name__ == "__main__":
     if "gfs" in todo:
         make_gfs("gfs_s3dis_b2_n256", 2, 256, 13, 7, 150, seed=4321, wname="gfs_s3dis_weights")
         make_gfs("gfs_scannet_b2_n128", 2, 128, 21, 15, 180, seed=8765, wname="gfs_scannet_weights")
+    if "train" in todo:
+        make_train("train_s3dis_b4_n128", 4, 128, seed=2468)
     if "kmeans" in todo:
         make_kmeans("kmeans_n6000_k150", 6000, 192, 150, seed=99)
         make_kmeans("kmeans_n2000_k20", 2000, 192, 20, seed=3)

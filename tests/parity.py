@@ -44,3 +44,11 @@ def knn_classify_mismatches(x: torch.Tensor, idx_a, idx_b, k: int):
         near += ok
         real += (not ok)
     return len(rows), near, real
+
+
+def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
+    """relative Frobenius error ||a-b|| / ||b|| -- for gradients, where an fp32-vs-fp64 arg-max near-tie legitimately re-routes
+    a single element's gradient (a large max-norm difference at isolated elements, negligible in norm)"""
+    a = a.double().cpu()
+    b = b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))

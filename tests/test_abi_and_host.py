@@ -123,6 +123,14 @@ def _worker(rank, world, port, out):
     ok = np.allclose(gs.numpy(), ref) and gc.tolist() == np.bincount(labels, minlength=K).tolist()
     ok = ok and max_over_ranks(float(rank + 1), "cpu") == float(world)
     ok = ok and all_same(True, "cpu") and not all_same(rank == 0, "cpu")
+    # flat-bucket gradient all-reduce (data-parallel training): average over ranks, written back in place
+    from gfs3d.dist import allreduce_gradients
+    ps = [torch.nn.Parameter(torch.zeros(3, 4)), torch.nn.Parameter(torch.zeros(5)), torch.nn.Parameter(torch.zeros(2))]
+    ps[0].grad = torch.full((3, 4), float(rank + 1))
+    ps[1].grad = torch.arange(5.0) * (rank + 1)
+    n = allreduce_gradients(ps)
+    ok = ok and n == 17 and torch.allclose(ps[0].grad, torch.full((3, 4), 1.5)) and torch.allclose(ps[1].grad, torch.arange(5.0) * 1.5)
+    ok = ok and ps[2].grad is None
     out[rank] = bool(ok)
     dist.destroy_process_group()
 

@@ -1,0 +1,182 @@
+"""GPU suite, training path: every autograd.Function (forward AND backward in the hand-written kernels) against PyTorch
+autograd of the reference formulas in fp64 (model/dgcnn.py:35-58,118; model/attention.py:32-48), tolerance 1e-3 (fp32 path)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import gfs_oracle as O
+from parity import rel_err, rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+@pytest.mark.parametrize("R,N,K,at,bt,ct,batch,splitk", [(64, 128, 32, 0, 0, 0, 1, 1), (100, 300, 70, 1, 0, 0, 1, 1),
+                                                          (64, 9, 5000, 1, 1, 0, 1, 4), (37, 129, 33, 0, 1, 1, 1, 1),
+                                                          (256, 256, 64, 0, 0, 0, 3, 1), (64, 256, 256, 1, 1, 0, 2, 1)])
+def test_gemm_f32_all_layouts(R, N, K, at, bt, ct, batch, splitk):
+    from gfs3d import ops
+    g = torch.Generator().manual_seed(R * N + K)
+    A = torch.randn(batch, *((R, K) if at else (K, R)), generator=g)
+    Bm = torch.randn(batch, *((N, K) if bt else (K, N)), generator=g)
+    bias = torch.randn(R, generator=g)
+    Aop = A.transpose(1, 2) if at else A            # (batch, K, R)
+    Bop = Bm.transpose(1, 2) if bt else Bm          # (batch, K, N)
+    ref = torch.einsum("bkr,bkn->brn", Aop.double(), Bop.double()) + bias.double().view(1, -1, 1)
+    C = torch.empty(batch, *((N, R) if ct else (R, N)), device="cuda")
+    Ad, Bd = A.cuda(), Bm.cuda()
+    ops.gemm_f32(Ad, A.shape[2], at, Bd, Bm.shape[2], bt, R, N, K, C, C.shape[2], c_trans=bool(ct), bias=bias.cuda(), batch=batch,
+                 a_bs=A[0].numel(), b_bs=Bm[0].numel(), c_bs=C[0].numel(), splitk=splitk)
+    got = C.cpu().transpose(1, 2) if ct else C.cpu()
+    assert rel_err(got, ref) <= 1e-5
+
+
+def test_conv_bn_act_function_vs_autograd():
+    from gfs3d.train_ops import ConvBNAct
+    g = torch.Generator().manual_seed(0)
+    I, Oc, M = 192, 128, 3000
+    x = torch.randn(I, M, generator=g)
+    W = torch.randn(Oc, I, generator=g) / I ** 0.5
+    b = torch.randn(Oc, generator=g)
+    ga, be = 1 + 0.3 * torch.randn(Oc, generator=g), 0.2 * torch.randn(Oc, generator=g)
+    dy = torch.randn(Oc, M, generator=g)
+    for slope in (0.2, 0.0, 1.0):
+        xs = [t.clone().double().requires_grad_(True) for t in (x, W, b, ga, be)]
+        z = xs[1] @ xs[0] + xs[2][:, None]
+        zn = F.batch_norm(z.t(), None, None, xs[3], xs[4], True, 0.1, 1e-5).t()
+        ref = torch.where(zn > 0, zn, slope * zn)
+        ref.backward(dy.double())
+        xc = [t.clone().cuda().requires_grad_(True) for t in (x, W, b, ga, be)]
+        y, mean, var = ConvBNAct.apply(xc[0], xc[1], xc[2], xc[3], xc[4], None, None, slope, True)
+        y.backward(dy.cuda())
+        assert rel_err(y.detach().cpu(), ref.detach()) <= TOL
+        assert rel_err(mean.cpu(), z.detach().mean(1)) <= TOL and rel_err(var.cpu(), z.detach().var(1, unbiased=False)) <= TOL
+        for got, want, name in zip(xc, xs, ("dx", "dW", "dbias", "dgamma", "dbeta")):
+            if name == "dbias":      # gradient of a bias in front of a batch-statistics BN is identically zero
+                assert float(got.grad.abs().max()) <= 1e-3 * float(dy.abs().sum() / M)
+                continue
+            assert rel_err(got.grad.cpu(), want.grad) <= TOL, (name, slope)
+
+
+@pytest.mark.parametrize("B,C,N,k", [(2, 9, 128, 20), (1, 64, 256, 20), (3, 64, 100, 7)])
+def test_edgeconv_train_function_vs_autograd(B, C, N, k):
+    from gfs3d import ops
+    from gfs3d.train_ops import EdgeConvTrain, from_cm, to_cm
+    g = torch.Generator().manual_seed(B + N)
+    x = torch.randn(B, C, N, generator=g) * 0.5
+    idx = torch.stack([torch.stack([torch.randperm(N, generator=g)[:k] for _ in range(N)]) for _ in range(B)])
+    W1 = torch.randn(64, 2 * C, 1, 1, generator=g) / (2 * C) ** 0.5
+    W2 = torch.randn(64, 64, 1, 1, generator=g) / 8
+    g1, b1 = 1 + 0.3 * torch.randn(64, generator=g), 0.2 * torch.randn(64, generator=g)
+    g2, b2 = 1 + 0.3 * torch.randn(64, generator=g), 0.2 * torch.randn(64, generator=g)
+    dy = torch.randn(B, 64, N, generator=g)
+    ps = [t.clone().double().requires_grad_(True) for t in (x, W1, g1, b1, W2, g2, b2)]
+    e = O.edge_feature(ps[0], idx)
+    h = F.leaky_relu(F.batch_norm(F.conv2d(e, ps[1]), None, None, ps[2], ps[3], True, 0.1, 1e-5), 0.2)
+    a = F.leaky_relu(F.batch_norm(F.conv2d(h, ps[4]), None, None, ps[5], ps[6], True, 0.1, 1e-5), 0.2)
+    ref = a.max(dim=-1).values
+    ref.backward(dy.double())
+    pc = [t.clone().cuda().requires_grad_(True) for t in (x, W1, g1, b1, W2, g2, b2)]
+    y, m1, v1, m2, v2 = EdgeConvTrain.apply(to_cm(pc[0]), idx.int().cuda(), pc[1], pc[2], pc[3], pc[4], pc[5], pc[6], B, N, k)
+    from_cm(y, B, N).backward(dy.cuda())
+    assert rel_err(from_cm(y, B, N).detach().cpu(), ref.detach()) <= TOL
+    for got, want, name in zip(pc, ps, ("dx", "dW1", "dg1", "db1", "dW2", "dg2", "db2")):
+        # max over k: an fp32/fp64 near-tie may route one element's gradient to another edge -> norm-wise tolerance,
+        # plus a loose max-norm bound
+        assert rel_l2(got.grad.cpu(), want.grad) <= TOL, name
+        assert rel_err(got.grad.cpu(), want.grad) <= 2e-2, name
+
+
+@pytest.mark.parametrize("B,N,drop", [(2, 128, False), (1, 256, True), (3, 100, False)])
+def test_attention_train_function_vs_autograd(B, N, drop):
+    from gfs3d.train_ops import AttentionTrain, from_cm, to_cm
+    g = torch.Generator().manual_seed(N)
+    qkv = torch.randn(B, 192, N, generator=g)
+    dy = torch.randn(B, 64, N, generator=g)
+    mask = ((torch.rand(B, N, N, generator=g) >= 0.1).float() / 0.9) if drop else None
+    t = qkv.clone().double().requires_grad_(True)
+    q, k, v = t[:, :64], t[:, 64:128], t[:, 128:]
+    attn = torch.softmax(torch.matmul(q.transpose(1, 2) / 8.0, k), dim=-1)
+    if drop:
+        attn = attn * mask.double()
+    ref = torch.matmul(attn, v.transpose(1, 2)).transpose(1, 2)
+    ref.backward(dy.double())
+    tc = qkv.clone().cuda().requires_grad_(True)
+    y = AttentionTrain.apply(to_cm(tc), B, N, 1.0 / 8.0, mask.cuda() if drop else None)
+    from_cm(y, B, N).backward(dy.cuda())
+    assert rel_err(from_cm(y, B, N).detach().cpu(), ref.detach()) <= TOL
+    assert rel_err(tc.grad.cpu(), t.grad) <= TOL
+
+
+def _train_model(golden, golden_sd):
+    import random
+    from types import SimpleNamespace
+    from model.capl import mpti_net_Point_GeoAsWeight_v2
+    g = golden("train_s3dis_b4_n128")
+    args = SimpleNamespace(edgeconv_widths=[[64, 64]] * 3, dgcnn_mlp_widths=[512, 256], pc_in_dim=9, dgcnn_k=20,
+                           base_widths=[128, 64], output_dim=64, eval_weight=1.2)
+    m = mpti_net_Point_GeoAsWeight_v2(classes=int(g["classes"]), criterion=torch.nn.CrossEntropyLoss(ignore_index=255), args=args,
+                                      base_num=int(g["base_num"]), gp=torch.from_numpy(g["gp"]).cuda(), energy=0.9)
+    m.load_state_dict(golden_sd("gfs_s3dis_weights"), strict=True)
+    m = m.cuda().train()
+    m.att_learner.dropout.p = 0.0                     # dropout off for parity
+    random.seed(99)                                   # generate_fake_proto draws with random.sample (model/capl.py:386)
+    return m, g
+
+
+def test_training_step_vs_reference_fixture(golden, golden_sd):
+    """BASELINE.json configs[2] shape in miniature: one training step (forward + backward) of the full GFS model through the
+    hand-written training kernels, against loss / predictions / gradients / BN running statistics of the REAL reference."""
+    m, g = _train_model(golden, golden_sd)
+    x, y = torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["y"]).long().cuda()
+    pred, loss = m(x=x, y=y)
+    loss.backward()
+    torch.cuda.synchronize()
+    print(f"train step: loss {float(loss.detach()):.6f} (reference {float(g['loss']):.6f}); "
+          f"pred agreement {float((pred.cpu().numpy() == g['pred']).mean()):.4f}")
+    assert abs(float(loss) - float(g["loss"])) <= 1e-3 * abs(float(g["loss"]))
+    assert (pred.cpu().numpy() == g["pred"]).mean() >= 0.99
+    grads = dict(m.named_parameters())
+    worst = 0.0
+    for key in [k for k in g if k.startswith("grad.")]:
+        name = key[5:]
+        ref = torch.from_numpy(g[key])
+        if float(ref.norm()) < 1e-5:          # a bias in front of a batch-statistics BatchNorm: the true gradient is 0
+            assert float(grads[name].grad.norm()) < 1e-4, name
+            continue
+        e = rel_l2(grads[name].grad.cpu(), ref)
+        worst = max(worst, e)
+        assert e <= 2e-2, (name, e)
+    for key in [k for k in g if k.startswith("gradnorm.")]:
+        name = key[9:]
+        gn = float(grads[name].grad.norm())
+        assert abs(gn - float(g[key])) <= 2e-2 * float(g[key]) + 1e-4, (name, gn, float(g[key]))
+    print(f"worst relative L2 gradient error vs reference: {worst:.3e}")
+    sd = m.state_dict()
+    for key in [k for k in g if k.startswith("after.")]:
+        assert rel_err(sd[key[6:]].float().cpu(), torch.from_numpy(g[key]).float()) <= 1e-3, key
+
+
+def test_training_step_vs_oracle_with_pinned_graph(golden, golden_sd):
+    """tighter: the oracle (autograd on the restated formulas, CPU fp32) is given the neighbour sets the CUDA path used, so
+    kNN near-ties cannot blur the comparison"""
+    from gfs3d import ops
+    m, g = _train_model(golden, golden_sd)
+    x, y = torch.from_numpy(g["x"]), torch.from_numpy(g["y"]).long()
+    pred, loss = m(x=x.cuda(), y=y.cuda())
+    loss.backward()
+    # neighbour sets of the three layers as the CUDA path saw them (features of the training forward, same weights)
+    m2, _ = _train_model(golden, golden_sd)
+    with torch.no_grad():
+        outs, _ = m2.encoder.forward_train(x.cuda())
+        from gfs3d.train_ops import from_cm
+        feats = [x.cuda()] + [from_cm(o, x.shape[0], x.shape[2]) for o in outs[:2]]
+        idx_list = [ops.knn(f.contiguous(), 20).cpu() for f in feats]
+    sd = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.clone())
+          for k, v in golden_sd("gfs_s3dis_weights").items()}
+    o_pred, o_loss, _ = O.forward_train(sd, torch.from_numpy(g["gp"]), x, y, int(g["base_num"]), g["fake_novel"].tolist(), idx_list=idx_list)
+    o_loss.backward()
+    assert abs(float(loss) - float(o_loss)) <= 2e-4 * abs(float(o_loss))
+    worst = max(rel_l2(p.grad.cpu(), sd[n].grad) for n, p in m.named_parameters() if float(sd[n].grad.norm()) >= 1e-5)
+    print(f"loss {float(loss):.6f} vs oracle {float(o_loss):.6f}; worst relative L2 gradient error over all {len(sd)} tensors: {worst:.3e}")
+    assert worst <= 1e-2     # fp32 (GPU) vs fp32 (CPU): summation order + arg-max near-tie routing of single elements
