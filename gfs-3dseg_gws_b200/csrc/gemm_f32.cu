@@ -41,16 +41,23 @@ __device__ __forceinline__ void gm_load_panel(float* panel, int width, const flo
             *reinterpret_cast<float4*>(panel + kk * width + q * 4) = v;
         }
     } else {
-        // source row j holds consecutive k: each thread walks 4 k of one j; lanes vary along j -> conflict-free stores
+        // source row j holds consecutive k: each thread takes 4 consecutive k of one j (one float4 when aligned); lanes vary
+        // along j -> conflict-free shared-memory stores
+        const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((k0 & 3) == 0);
         for (int i = tid; i < (GM_KC / 4) * width; i += T_THREADS) {
             const int kq = i / width, jj = i - kq * width;
             const int j = j0 + jj, k = k0 + kq * 4;
             float v[4] = {0.f, 0.f, 0.f, 0.f};
             if (j < lim) {
                 const float* p = src + (int64_t)j * ld + k;
+                if (vec && k + 3 < K) {
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+                    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+                } else {
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    if (k + e < K) v[e] = __ldg(p + e);
+                    for (int e = 0; e < 4; ++e)
+                        if (k + e < K) v[e] = __ldg(p + e);
+                }
             }
 #pragma unroll
             for (int e = 0; e < 4; ++e) panel[(kq * 4 + e) * width + jj] = v[e];

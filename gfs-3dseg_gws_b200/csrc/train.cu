@@ -25,12 +25,16 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
     return t;
 }
 
+constexpr int BN_SPLIT = 16;   // CTAs per channel; partials are combined in index order -> deterministic
+
 __global__ void __launch_bounds__(512)
-bn_stats_kernel(const float* __restrict__ x, int64_t ld, int64_t M, float* __restrict__ mean, float* __restrict__ var) {
+bn_stats_kernel(const float* __restrict__ x, int64_t ld, int64_t M, double* __restrict__ part) {
     __shared__ double red[16];
     const float* row = x + (int64_t)blockIdx.x * ld;
+    const int64_t per = (M + gridDim.y - 1) / gridDim.y;
+    const int64_t i0 = per * blockIdx.y, i1 = (i0 + per) < M ? (i0 + per) : M;
     double s = 0.0, q = 0.0;
-    for (int64_t i = threadIdx.x; i < M; i += blockDim.x) {
+    for (int64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
         const double v = row[i];
         s += v;
         q += v * v;
@@ -38,10 +42,23 @@ bn_stats_kernel(const float* __restrict__ x, int64_t ld, int64_t M, float* __res
     s = block_sum(s, red);
     q = block_sum(q, red);
     if (threadIdx.x == 0) {
-        const double m = s / (double)M;
-        mean[blockIdx.x] = (float)m;
-        var[blockIdx.x] = (float)fmax(q / (double)M - m * m, 0.0);
+        part[((int64_t)blockIdx.x * gridDim.y + blockIdx.y) * 2 + 0] = s;
+        part[((int64_t)blockIdx.x * gridDim.y + blockIdx.y) * 2 + 1] = q;
     }
+}
+
+__global__ void bn_stats_finish_kernel(const double* __restrict__ part, int C, int S, int64_t M, float* __restrict__ mean,
+                                       float* __restrict__ var) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0, q = 0.0;
+    for (int i = 0; i < S; ++i) {
+        s += part[((int64_t)c * S + i) * 2 + 0];
+        q += part[((int64_t)c * S + i) * 2 + 1];
+    }
+    const double m = s / (double)M;
+    mean[c] = (float)m;
+    var[c] = (float)fmax(q / (double)M - m * m, 0.0);
 }
 
 // y = act(x * scale[c] + shift[c]),  act(u) = u > 0 ? u : slope * u   (slope 0.2 LeakyReLU, 0 ReLU, 1 identity)
@@ -61,14 +78,16 @@ __global__ void bn_act_fwd_kernel(const float* __restrict__ x, int64_t ldx, floa
 __global__ void __launch_bounds__(512)
 bn_bwd_reduce_kernel(const float* __restrict__ dy, int64_t lddy, const float* __restrict__ x, int64_t ldx, int64_t M,
                      const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
-                     const float* __restrict__ beta, float slope, float* __restrict__ sum_g, float* __restrict__ sum_gx) {
+                     const float* __restrict__ beta, float slope, double* __restrict__ part) {
     __shared__ double red[16];
     const int c = blockIdx.x;
     const float mu = mean[c], is = invstd[c], ga = gamma[c], be = beta[c];
     const float* dr = dy + (int64_t)c * lddy;
     const float* xr = x + (int64_t)c * ldx;
+    const int64_t per = (M + gridDim.y - 1) / gridDim.y;
+    const int64_t i0 = per * blockIdx.y, i1 = (i0 + per) < M ? (i0 + per) : M;
     double s = 0.0, q = 0.0;
-    for (int64_t i = threadIdx.x; i < M; i += blockDim.x) {
+    for (int64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
         const float xh = (xr[i] - mu) * is;
         const float u = fmaf(ga, xh, be);
         const float g = dr[i] * (u > 0.0f ? 1.0f : slope);
@@ -78,9 +97,21 @@ bn_bwd_reduce_kernel(const float* __restrict__ dy, int64_t lddy, const float* __
     s = block_sum(s, red);
     q = block_sum(q, red);
     if (threadIdx.x == 0) {
-        sum_g[c] = (float)s;
-        sum_gx[c] = (float)q;
+        part[((int64_t)c * gridDim.y + blockIdx.y) * 2 + 0] = s;
+        part[((int64_t)c * gridDim.y + blockIdx.y) * 2 + 1] = q;
     }
+}
+
+__global__ void bn_bwd_finish_kernel(const double* __restrict__ part, int C, int S, float* __restrict__ sum_g, float* __restrict__ sum_gx) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0, q = 0.0;
+    for (int i = 0; i < S; ++i) {
+        s += part[((int64_t)c * S + i) * 2 + 0];
+        q += part[((int64_t)c * S + i) * 2 + 1];
+    }
+    sum_g[c] = (float)s;
+    sum_gx[c] = (float)q;
 }
 
 // dx = gamma * invstd * (g - sum_g / M - xhat * sum_gx / M)
@@ -239,10 +270,14 @@ __global__ void softmax_rows_bwd_kernel(const float* __restrict__ p0, const floa
 
 using namespace gfs;
 
-extern "C" int gfs_bn_stats(const float* x, int64_t ld, int C, int64_t M, float* mean, float* var, void* stream) {
-    GFS_REQUIRE(x && mean && var && C > 0 && M > 0, GFS_ERR_BAD_ARG, "gfs_bn_stats: bad argument");
-    bn_stats_kernel<<<C, 512, 0, static_cast<cudaStream_t>(stream)>>>(x, ld, M, mean, var);
+extern "C" int gfs_bn_stats(const float* x, int64_t ld, int C, int64_t M, double* workspace, float* mean, float* var, void* stream) {
+    GFS_REQUIRE(x && mean && var && workspace && C > 0 && M > 0, GFS_ERR_BAD_ARG, "gfs_bn_stats: bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int S = M >= 65536 ? BN_SPLIT : 1;
+    bn_stats_kernel<<<dim3(C, S), 512, 0, st>>>(x, ld, M, workspace);
     GFS_LAUNCH_OK("bn_stats_kernel");
+    bn_stats_finish_kernel<<<(C + 127) / 128, 128, 0, st>>>(workspace, C, S, M, mean, var);
+    GFS_LAUNCH_OK("bn_stats_finish_kernel");
     return GFS_OK;
 }
 
@@ -257,12 +292,15 @@ extern "C" int gfs_bn_act_fwd(const float* x, int64_t ldx, float* y, int64_t ldy
 
 extern "C" int gfs_bn_act_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, float* dx, int64_t lddx, int C, int64_t M,
                               const float* mean, const float* invstd, const float* gamma, const float* beta, float slope,
-                              float* sum_g, float* sum_gx, void* stream) {
-    GFS_REQUIRE(dy && x && dx && mean && invstd && gamma && beta && sum_g && sum_gx && C > 0 && M > 0, GFS_ERR_BAD_ARG,
+                              double* workspace, float* sum_g, float* sum_gx, void* stream) {
+    GFS_REQUIRE(dy && x && dx && mean && invstd && gamma && beta && workspace && sum_g && sum_gx && C > 0 && M > 0, GFS_ERR_BAD_ARG,
                 "gfs_bn_act_bwd: bad argument");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    bn_bwd_reduce_kernel<<<C, 512, 0, st>>>(dy, lddy, x, ldx, M, mean, invstd, gamma, beta, slope, sum_g, sum_gx);
+    const int S = M >= 65536 ? BN_SPLIT : 1;
+    bn_bwd_reduce_kernel<<<dim3(C, S), 512, 0, st>>>(dy, lddy, x, ldx, M, mean, invstd, gamma, beta, slope, workspace);
     GFS_LAUNCH_OK("bn_bwd_reduce_kernel");
+    bn_bwd_finish_kernel<<<(C + 127) / 128, 128, 0, st>>>(workspace, C, S, sum_g, sum_gx);
+    GFS_LAUNCH_OK("bn_bwd_finish_kernel");
     const unsigned gx = (unsigned)((M + 1023) / 1024 < 1024 ? (M + 1023) / 1024 : 1024);
     bn_bwd_apply_kernel<<<dim3(gx, C), 256, 0, st>>>(dy, lddy, x, ldx, dx, lddx, M, mean, invstd, gamma, beta, slope, sum_g, sum_gx);
     GFS_LAUNCH_OK("bn_bwd_apply_kernel");

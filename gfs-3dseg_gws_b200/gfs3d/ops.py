@@ -236,7 +236,7 @@ def gemm_f32(A, lda, a_trans, B, ldb, b_trans, R, Ncols, K, C, ldc, c_trans=Fals
 
 
 def _splitk(K):
-    return int(max(1, min(96, K // 8192)))
+    return int(max(1, min(512, K // 2048)))
 
 
 def conv_fwd(W, x, bias=None):
@@ -267,7 +267,8 @@ def bn_stats(x):
     C, M = x.shape
     mean = torch.empty(C, dtype=torch.float32, device=x.device)
     var = torch.empty(C, dtype=torch.float32, device=x.device)
-    _call("gfs_bn_stats", 1, _ptr(x), x.stride(0), C, M, _ptr(mean), _ptr(var), _stream())
+    ws = torch.empty(2 * 16 * C, dtype=torch.float64, device=x.device)
+    _call("gfs_bn_stats", 2, _ptr(x), x.stride(0), C, M, _ptr(ws), _ptr(mean), _ptr(var), _stream())
     return mean, var
 
 
@@ -283,8 +284,9 @@ def bn_act_bwd(dy, x, mean, invstd, gamma, beta, slope):
     dx = torch.empty(C, M, dtype=torch.float32, device=x.device)
     sg = torch.empty(C, dtype=torch.float32, device=x.device)
     sgx = torch.empty(C, dtype=torch.float32, device=x.device)
-    _call("gfs_bn_act_bwd", 2, _ptr(dy), dy.stride(0), _ptr(x), x.stride(0), _ptr(dx), M, C, M, _ptr(mean), _ptr(invstd), _ptr(gamma),
-          _ptr(beta), float(slope), _ptr(sg), _ptr(sgx), _stream())
+    ws = torch.empty(2 * 16 * C, dtype=torch.float64, device=x.device)
+    _call("gfs_bn_act_bwd", 3, _ptr(dy), dy.stride(0), _ptr(x), x.stride(0), _ptr(dx), M, C, M, _ptr(mean), _ptr(invstd), _ptr(gamma),
+          _ptr(beta), float(slope), _ptr(ws), _ptr(sg), _ptr(sgx), _stream())
     return dx, sg, sgx
 
 

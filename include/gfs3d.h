@@ -168,14 +168,15 @@ int gfs_gemm_f32(const float* A, int64_t lda, int a_trans, int64_t a_bstride,
                  const float* bias, int R, int Ncols, int K, int batch, int splitk, float* workspace, int accumulate, void* stream);
 
 /* BatchNorm with batch statistics (nn.BatchNorm1d/2d in training mode, model/dgcnn.py:54-55,73-74): biased variance      */
-int gfs_bn_stats(const float* x, int64_t ld, int C, int64_t M, float* mean, float* var, void* stream);
+/* workspace: 2*16*C doubles (per-channel partial sums, combined in a fixed order)                                          */
+int gfs_bn_stats(const float* x, int64_t ld, int C, int64_t M, double* workspace, float* mean, float* var, void* stream);
 /* y = act(x*scale[c] + shift[c]);  act(u) = u > 0 ? u : slope*u  (0.2 LeakyReLU, 0 ReLU, 1 identity)                      */
 int gfs_bn_act_fwd(const float* x, int64_t ldx, float* y, int64_t ldy, int C, int64_t M,
                    const float* scale, const float* shift, float slope, void* stream);
 /* backward of y = act(gamma*xhat + beta): dx, and sum_g = dbeta, sum_gx = dgamma (per channel)                           */
 int gfs_bn_act_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, float* dx, int64_t lddx, int C, int64_t M,
                    const float* mean, const float* invstd, const float* gamma, const float* beta, float slope,
-                   float* sum_g, float* sum_gx, void* stream);
+                   double* workspace, float* sum_g, float* sum_gx, void* stream);
 
 /* edge tensor of model/dgcnn.py:35-41 after the split first conv: H[c, e] = P[j(e), c] + Q[i(e), c]  (pq point-major (M,128)) */
 int gfs_edge_gather(const float* pq, const int32_t* idx, int B, int N, int k, float* H, void* stream);

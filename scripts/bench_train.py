@@ -76,6 +76,12 @@ if dist:
     dist.barrier()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / a.steps
+ops.PROFILE = {}
+step(0)
+torch.cuda.synchronize()
+prof = {k: round(sum(s_.elapsed_time(e_) for s_, e_ in v), 3) for k, v in ops.PROFILE.items()}
+calls = {k: len(v) for k, v in ops.PROFILE.items()}
+ops.PROFILE = None
 t = torch.tensor([ms], dtype=torch.float64, device=dev)
 if dist:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -84,6 +90,6 @@ if rank == 0:
                       "ms_per_step": float(t[0]), "n_gpus": world, "batch_per_gpu": a.batch, "npts": a.npts, "classes": CLASSES, "gws": G,
                       "loss_last": float(loss.detach()), "gpu_launches_per_step": (ops.LAUNCHES - l0) / a.steps,
                       "allreduce_floats_per_step": nred, "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9,
-                      "dtype": "f32", "config": "ScanNet-shaped: 21 classes, 180 GWs, base_num 15, fwd+bwd+Adam, attention dropout 0.1"}))
+                      "entry_point_ms": prof, "entry_point_calls": calls, "dtype": "f32", "config": "ScanNet-shaped: 21 classes, 180 GWs, base_num 15, fwd+bwd+Adam, attention dropout 0.1"}))
 if dist:
     dist.destroy_process_group()
