@@ -185,10 +185,23 @@ def test_gfs_model_eval_vs_reference_fixture(golden, golden_sd, name, wname, cla
     assert rel_err(fg_gp.sum(0).cpu(), t("fg_gp_sum")) <= 0.05
 
 
-def test_training_mode_raises_instead_of_falling_back(golden_sd):
+def test_training_mode_dgcnn_runs_the_training_kernels(golden_sd):
+    """model.train(): batch-statistics forward through gfs3d/train_ops.py (no PyTorch fallback), running stats are updated"""
+    from gfs3d import ops
     m = _load_dgcnn(golden_sd).train()
-    with pytest.raises(NotImplementedError):
-        m(torch.randn(1, 9, 128, device="cuda"))
+    before = m.edge_convs[0].layer[1].running_mean.clone()
+    n0 = ops.LAUNCHES
+    x = torch.randn(2, 9, 128, device="cuda")
+    ecs, out = m(x)
+    assert ops.LAUNCHES > n0, "the training forward must run in the hand-written kernels"
+    assert [tuple(e.shape) for e in ecs] == [(2, 64, 128)] * 3 and tuple(out.shape) == (2, 256, 128)
+    assert out.requires_grad and torch.isfinite(out).all()
+    out.sum().backward()
+    assert m.conv.layer[0].weight.grad is not None and torch.isfinite(m.conv.layer[0].weight.grad).all()
+    assert not torch.equal(before, m.edge_convs[0].layer[1].running_mean)
+    assert int(m.edge_convs[0].layer[1].num_batches_tracked) == 1
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.randn(1, 9, 128))
 
 
 @pytest.mark.parametrize("B,N", [(2, 256), (1, 2048), (3, 128), (2, 1024)])
