@@ -15,7 +15,7 @@
 
 namespace gfs {
 
-constexpr int KNN_KC = 32;        // channels per pipeline stage
+constexpr int KNN_KC = 64;        // channels per pipeline stage (all of C <= 64: one stage per candidate tile)
 constexpr int KNN_SEL_WARPS = 16;
 constexpr int KNN_ROWS_PER_SEL = T_ROWS / KNN_SEL_WARPS;
 constexpr int KNN_THREADS = 128 + 32 * KNN_SEL_WARPS;  // warps 0-3: FFMA producers of distance tiles; the rest: selection consumers
