@@ -51,8 +51,10 @@ __device__ __forceinline__ u64 cmpex(u64 k, int j2, bool keep_max) {
 // Merge the row's append buffer into its sorted list (one warp; key = (orderable d << 32) | ~index, larger = better, so
 // equal distances order by ascending index).  Bitonic sort of the <=32 buffered keys, then the classic
 // "max(list, reverse(sorted buffer))" + 5-stage bitonic merge keeps the 32 largest of the union, sorted descending.
+// (__noinline__: the merge is ~400 instructions and is reached from several places of the selection loop; one shared copy
+// keeps the kernel's code footprint small, the FFMA warps' loop competes for the same instruction cache)
 template <int LR>   // LR = list registers per lane: 1 -> 32-entry list (k <= 32), 2 -> 64-entry list (k <= 64)
-__device__ __forceinline__ float knn_flush(KnnSmem& s, int q, int lane, int fill, int k) {
+__device__ __noinline__ float knn_flush(KnnSmem& s, int q, int lane, int fill, int k) {
     const uint2 raw = s.buf[q * 32 + lane];
     u64 key = lane < fill ? (((u64)ord_key(__uint_as_float(raw.x)) << 32) | (u64)(~raw.y)) : 0ull;
 #pragma unroll
@@ -213,7 +215,6 @@ knn_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int k, co
             const bool full_tile = j0 + T_COLS <= N;
             mbar_wait_backoff(&s.ds_full[db], (t >> 1) & 1, 256);
             const float* D = s.Ds[db];
-#pragma unroll 2
             for (int rr = 0; rr < KNN_ROWS_PER_SEL; ++rr) {
                 const int q = w * KNN_ROWS_PER_SEL + rr;
                 const float4 dv4 = *reinterpret_cast<const float4*>(D + q * T_COLS + lane * 4);

@@ -180,3 +180,23 @@ def test_training_step_vs_oracle_with_pinned_graph(golden, golden_sd):
     worst = max(rel_l2(p.grad.cpu(), sd[n].grad) for n, p in m.named_parameters() if float(sd[n].grad.norm()) >= 1e-5)
     print(f"loss {float(loss):.6f} vs oracle {float(o_loss):.6f}; worst relative L2 gradient error over all {len(sd)} tensors: {worst:.3e}")
     assert worst <= 1e-2     # fp32 (GPU) vs fp32 (CPU): summation order + arg-max near-tie routing of single elements
+
+
+def test_adam_steps_reduce_the_loss(golden, golden_sd):
+    """train.py:616-631 in miniature: zero_grad / forward / backward / Adam on a fixed batch -- the loss must go down and
+    every parameter must receive a finite gradient"""
+    import random
+    m, g = _train_model(golden, golden_sd)
+    x, y = torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["y"]).long().cuda()
+    opt = torch.optim.Adam(m.parameters(), lr=2e-3)
+    losses = []
+    for it in range(8):
+        random.seed(7)                       # same fake-novel draw every step
+        opt.zero_grad()
+        _, loss = m(x=x, y=y)
+        loss.backward()
+        assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
+        opt.step()
+        losses.append(float(loss.detach()))
+    print("losses:", " ".join(f"{v:.4f}" for v in losses))
+    assert losses[-1] < losses[0] - 0.05
