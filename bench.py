@@ -142,6 +142,7 @@ def main():
     ap.add_argument("--impl", default="gfs3d", choices=["gfs3d", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="blocks per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     a = ap.parse_args()
     if a.impl == "reference":
         return run_reference(a)
@@ -181,6 +182,14 @@ def main():
     for i in range(a.warmup):
         step(xs[i % NROT])
     barrier()
+    graphed = None
+    if not a.no_graph:
+        from gfs3d.graph import GraphedEval
+        graphed = GraphedEval(step, xs[0])
+        for i in range(a.warmup):
+            graphed(xs[i % NROT])
+        barrier()
+    run = graphed if graphed is not None else step
 
     # ---- timed region 1: inputs resident in HBM; per-step CUDA events, L2 flushed between steps ----
     clocks = ClockSampler(local) if rank == 0 else None
@@ -191,11 +200,11 @@ def main():
     for i in range(a.steps):
         flush.zero_()
         ev[i][0].record()
-        step(xs[i % NROT])
+        run(xs[i % NROT])
         ev[i][1].record()
     barrier()
     wall = time.perf_counter() - w0
-    launches = ops.LAUNCHES - l0
+    launches = (ops.LAUNCHES - l0) if graphed is None else graphed.kernels_per_replay * a.steps
     dev_ms = sum(s.elapsed_time(e) for s, e in ev)
 
     # ---- timed region 2: end to end through the public module API with HOST buffers (H2D + forward + D2H labels) ----
@@ -205,8 +214,11 @@ def main():
     for i in range(a.steps):
         flush.zero_()
         ev2[i][0].record()
-        xdev.copy_(host[i % NROT], non_blocking=True)
-        lg = step(xdev)
+        if graphed is not None:
+            lg = graphed(host[i % NROT])                     # pinned host -> static device input, then one graph launch
+        else:
+            xdev.copy_(host[i % NROT], non_blocking=True)
+            lg = step(xdev)
         labels_host.copy_(lg.argmax(1).to(torch.int32), non_blocking=True)
         ev2[i][1].record()
     barrier()
@@ -286,6 +298,7 @@ def main():
                                    f"{CLASSES} classes, {G} GWs, random-init weights", "blocks_per_gpu_per_step": B,
                        "l2": "flushed between steps (256 MiB write outside the per-step event pair); 4 rotating input batches",
                        "parallelism": f"block-sharded x{world}, no data-path collective",
+                       "launch": "eager" if graphed is None else "CUDA graph replay of the eager step (gfs3d/graph.py)",
                        "attention": "hand-written tcgen05 flash kernel (gfs_attention_fwd)"},
             "clocks": clk, "e2e": {"value": total_blocks / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                                    "ms_per_step": e2e_ms / a.steps},

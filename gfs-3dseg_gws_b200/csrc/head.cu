@@ -9,45 +9,38 @@ namespace gfs {
 
 constexpr int CL_MAXC = 32;
 
-// CTA = 128 consecutive points of one block.  The (D x 128) feature tile is staged with cp.async (every load of the tile in
-// flight at once: the kernel is bandwidth- instead of latency-bound), prototypes (already L2-normalised) are broadcast from
-// shared memory; one thread per point.
+// one thread per point; prototypes (already L2-normalised) broadcast from shared memory
 __global__ void __launch_bounds__(128)
 cos_logits_kernel(const float* __restrict__ feat, int64_t bstride, int D, int N, const float* __restrict__ proto, int PB, int CLS,
                   const float* __restrict__ coding, int G, const int32_t* __restrict__ assignment, float th,
                   float* __restrict__ logits) {
-    extern __shared__ __align__(16) float sp[];   // [CLS][D] prototypes, then [D][128] feature tile
-    float* F = sp + ((CLS * D + 3) & ~3);
-    const int b = blockIdx.y, n0 = blockIdx.x * 128, tid = threadIdx.x;
-    const float* fb = feat + (int64_t)b * bstride;
-    const bool vec = ((N & 3) == 0) && ((bstride & 3) == 0) && ((reinterpret_cast<uintptr_t>(feat) & 15) == 0);
-    if (vec) {
-        for (int i = tid; i < D * 32; i += 128) {
-            const int d = i >> 5, q = i & 31;
-            const int col = n0 + q * 4;
-            int bytes = (N - col) * 4;
-            bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
-            cp_async16(F + d * 128 + q * 4, fb + (int64_t)d * N + (bytes > 0 ? col : 0), bytes);
-        }
-        cp_async_commit();
-    } else {
-        for (int i = tid; i < D * 128; i += 128) {
-            const int d = i >> 7, j = i & 127;
-            F[i] = n0 + j < N ? fb[(int64_t)d * N + n0 + j] : 0.0f;
-        }
-    }
+    extern __shared__ float sp[];   // [CLS][D]
+    const int b = blockIdx.y;
     const float* pb = proto + (PB > 1 ? (int64_t)b * CLS * D : 0);
-    for (int i = tid; i < CLS * D; i += 128) sp[i] = pb[i];
-    cp_async_wait<0>();
+    for (int i = threadIdx.x; i < CLS * D; i += blockDim.x) sp[i] = pb[i];
     __syncthreads();
-    const int n = n0 + tid;
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
+    const float* f = feat + (int64_t)b * bstride + n;
     float acc[CL_MAXC];
 #pragma unroll
     for (int c = 0; c < CL_MAXC; ++c) acc[c] = 0.0f;
     float nrm = 0.0f;
-    for (int d = 0; d < D; ++d) {
-        const float v = F[d * 128 + tid];
+    int d = 0;
+    for (; d + 8 <= D; d += 8) {          // 8 independent, coalesced loads in flight per thread
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldg(f + (int64_t)(d + u) * N);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            nrm = fmaf(v[u], v[u], nrm);
+#pragma unroll
+            for (int c = 0; c < CL_MAXC; ++c)
+                if (c < CLS) acc[c] = fmaf(v[u], sp[c * D + d + u], acc[c]);
+        }
+    }
+    for (; d < D; ++d) {
+        const float v = f[(int64_t)d * N];
         nrm = fmaf(v, v, nrm);
 #pragma unroll
         for (int c = 0; c < CL_MAXC; ++c)
@@ -164,9 +157,8 @@ extern "C" int gfs_cos_logits(const float* feat, int64_t feat_bstride, int B, in
     GFS_REQUIRE(CLS <= CL_MAXC, GFS_ERR_UNSUPPORTED, "gfs_cos_logits: CLS=%d > %d is not built", CLS, CL_MAXC);
     GFS_REQUIRE(PB == 1 || PB == B, GFS_ERR_BAD_ARG, "gfs_cos_logits: PB=%d must be 1 or B=%d", PB, B);
     GFS_REQUIRE(!coding || (assignment && G > 0), GFS_ERR_BAD_ARG, "gfs_cos_logits: coding needs assignment and G");
-    GFS_REQUIRE(D <= 256, GFS_ERR_UNSUPPORTED, "gfs_cos_logits: D=%d > 256 is not built", D);
-    const size_t smem = ((size_t)((CLS * D + 3) & ~3) + (size_t)D * 128) * sizeof(float);
-    GFS_CUDA_OK(allow_smem(reinterpret_cast<const void*>(cos_logits_kernel), (32 * 256 + 256 * 128) * sizeof(float)));
+    const size_t smem = (size_t)CLS * D * sizeof(float);
+    GFS_REQUIRE(smem <= 48 * 1024, GFS_ERR_UNSUPPORTED, "gfs_cos_logits: CLS*D too large");
     cos_logits_kernel<<<dim3((N + 127) / 128, B), 128, smem, static_cast<cudaStream_t>(stream)>>>(
         feat, feat_bstride, D, N, proto_l2, PB, CLS, coding, G, assignment, th, logits);
     GFS_LAUNCH_OK("cos_logits_kernel");
