@@ -1,0 +1,90 @@
+"""GPU suite at BASELINE.json's full sizes, through size-independent properties (the oracle only sees bounded samples)."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gfs_oracle as O
+from parity import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(golden_sd, gp):
+    from model.capl import mpti_net_Point_GeoAsWeight_v2
+    args = SimpleNamespace(edgeconv_widths=[[64, 64]] * 3, dgcnn_mlp_widths=[512, 256], pc_in_dim=9, dgcnn_k=20,
+                           base_widths=[128, 64], output_dim=64, eval_weight=1.2)
+    m = mpti_net_Point_GeoAsWeight_v2(classes=13, criterion=torch.nn.CrossEntropyLoss(ignore_index=255), args=args, base_num=7,
+                                      gp=gp.cuda(), energy=0.9)
+    m.load_state_dict(golden_sd("gfs_s3dis_weights"))
+    return m.cuda().eval()
+
+
+def test_config2_full_batch_properties(golden_sd):
+    """configs[1]: B = 32 blocks x 2048 points.  (a) kNN structure on every row, bit-exact vs the oracle on two blocks;
+    (b) blocks are independent: a block's logits do not depend on what else is in the batch (bit-identical);
+    (c) label agreement vs the oracle on a sample of blocks."""
+    from gfs3d import ops
+    from gfs3d.synthetic import synthetic_blocks
+    B, N, k = 32, 2048, 20
+    x = synthetic_blocks(B, N, seed=4242)
+    xc = x.cuda()
+    idx, dist = ops.knn(xc, k, return_dist=True)
+    ii, dd = idx.cpu().numpy(), dist.cpu().numpy()
+    assert ii.min() >= 0 and ii.max() < N
+    assert (dd[..., :-1] >= dd[..., 1:]).all(), "neighbours must be sorted nearest first"
+    assert (ii == np.arange(N)[None, :, None]).any(-1).all(), "every point is its own neighbour (distance 0)"
+    assert (np.sort(ii, -1)[..., 1:] != np.sort(ii, -1)[..., :-1]).all(), "no index may appear twice in a row"
+    for b in (0, 31):
+        ref_i, ref_d = O.knn_exact(x[b:b + 1], k, return_dist=True)
+        assert np.array_equal(ii[b], ref_i[0].numpy()) and np.array_equal(dd[b], ref_d[0].numpy())
+
+    g = torch.Generator().manual_seed(11)
+    gp = torch.randn(150, 192, generator=torch.Generator().manual_seed(7))
+    gened = torch.nn.functional.normalize(torch.randn(13, 128, generator=g), dim=1)
+    coding = (torch.rand(13, 150, generator=g) < 0.3).float()
+    m = _model(golden_sd, gp)
+    kw = dict(y=None, eval_model=True, gened_proto=gened.cuda(), base_class_coding=coding[:7].cuda(), novel_class_coding=coding[7:].cuda())
+    with torch.no_grad():
+        full, _, _ = m(x=xc, **kw)
+        solo, _, _ = m(x=xc[5:6].contiguous(), **kw)
+        pair, _, _ = m(x=xc[4:6].contiguous(), **kw)
+    assert full.shape == (B, 13, N)
+    assert torch.equal(full[5], solo[0]) and torch.equal(full[5], pair[1]), "a block's result must not depend on its batch"
+    sd = golden_sd("gfs_s3dis_weights")
+    sample = [0, 17, 31]
+    with torch.no_grad():
+        ref, f = O.forward_eval(sd, gp, x[sample], gened, coding[:7], coding[7:], 7, 1.2)
+    got = full[sample].cpu()
+    agree = float((got.argmax(1) == ref.argmax(1)).float().mean())
+    same_gw = float((m._features(xc[sample].contiguous())[1].cpu().long() == f["assignment"]).float().mean())
+    print(f"full-size label agreement on {len(sample)} x {N} points: {agree:.5f}; GW assignment agreement {same_gw:.5f}")
+    assert agree >= 0.999 and same_gw >= 0.99
+
+
+def test_config4_kmeans_shard_properties():
+    """configs[3] per-GPU shard (4 M / 8 = 500 k points, 150 centroids): checksums and sampled fp64 verification"""
+    from gfs3d import ops
+    n, D, K = 500000, 192, 150
+    g = torch.Generator(device="cuda").manual_seed(1)
+    cent = torch.randn(K, D, device="cuda", generator=g)
+    X = cent[torch.randint(0, K, (n,), device="cuda", generator=g)] + 0.35 * torch.randn(n, D, device="cuda", generator=g)
+    C = X[torch.randperm(n, device="cuda", generator=g)[:K]].clone()
+    ct = torch.zeros(D, 152, device="cuda")
+    ct[:, :K] = C.t()
+    labels = ops.kmeans_assign(X.t().contiguous(), ct, K)
+    sums, counts = ops.kmeans_accumulate(X, labels, K)
+    assert int(counts.sum()) == n and int(labels.min()) >= 0 and int(labels.max()) < K
+    assert torch.equal(counts, torch.bincount(labels.long(), minlength=K))
+    # checksum of checksums: the centroid sums add up to the sum of all points
+    assert rel_err(sums.sum(0).cpu(), X.double().sum(0).cpu()) <= 1e-5
+    # sampled points: the chosen centroid is the nearest one (fp64), up to fp32 rounding of the score
+    s = torch.randperm(n, device="cuda", generator=g)[:4096]
+    d = ((X[s].double()[:, None, :] - C.double()[None]) ** 2).sum(-1)
+    best = d.min(1).values
+    chosen = d[torch.arange(len(s), device="cuda"), labels[s].long()]
+    assert bool((chosen <= best + 1e-4 * best.abs() + 1e-4).all())
+    # bit-exact against the pinned-order oracle on a slice
+    ref = O.kmeans_assign_exact(X[:20000].cpu().numpy(), C.cpu().numpy())
+    assert np.array_equal(labels[:20000].cpu().numpy(), ref)
