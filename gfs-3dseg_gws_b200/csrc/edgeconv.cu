@@ -7,12 +7,12 @@
 // scale is folded into W2 the remaining "+shift, LeakyReLU" is monotone and is applied once after the max.
 //
 // Warp roles (persistent CTA, one per SM):
-//   warps 0-3  producers : cp.async gather of P'[idx] (256 B contiguous per edge) into a shared-memory ring, two slots
+//   warps 0-7  producers : cp.async gather of P'[idx] (256 B contiguous per edge) into a shared-memory ring, two slots
 //                          ahead; + Q' (registers) -> LReLU -> bf16 -> SWIZZLE_128B A tile in shared memory ->
 //                          fence.proxy.async -> arrive full[stage]
-//   warp  8    MMA       : one thread issues 4 x tcgen05.mma (128x64x16) per A tile into TMEM stage acc;
+//   warp  12   MMA       : one thread issues 4 x tcgen05.mma (128x64x16) per A tile into TMEM stage acc;
 //                          tcgen05.commit -> empty[stage], accf[acc].  W2 (8 KB image) arrives once by TMA bulk copy.
-//   warps 4-7  epilogue  : tcgen05.ld 32x32b, running max in registers, arrive acce[acc]; after slot k-1:
+//   warps 8-11 epilogue  : tcgen05.ld 32x32b, running max in registers, arrive acce[acc]; after slot k-1:
 //                          +shift, LeakyReLU, store fp32 channel-major and bf16 "act" tiles.
 #include "common.cuh"
 
@@ -21,10 +21,11 @@ namespace gfs {
 constexpr int EC_TM = 128;
 constexpr int EC_NST = 4;
 constexpr int EC_NACC = 4;
-constexpr int EC_THREADS = 288;
+constexpr int EC_PROD = 256;        // producer threads (warps 0-7)
+constexpr int EC_THREADS = EC_PROD + 128 + 32;   // + 4 epilogue warps (8-11) + 1 MMA warp (12)
 constexpr uint32_t EC_TMEM_COLS = 256;
 
-constexpr int EC_NG = 3;           // gather ring depth (slots of 128 rows x 256 B of fp32 P')
+constexpr int EC_NG = 4;           // gather ring depth (slots of 128 rows x 256 B of fp32 P'); EC_NG - 1 slots are in flight
 
 struct EcSmem {
     uint8_t A[EC_NST][16384];
@@ -36,7 +37,7 @@ struct EcSmem {
 };
 
 template <bool ARGMAX>
-__global__ void __launch_bounds__(EC_THREADS, 1)
+__global__ void __launch_bounds__(512, 1)   // 416 threads are launched; 512 caps registers at 128 (13 warps -> 4 on one SMSP)
 edgeconv_kernel(const float* __restrict__ pq, const int32_t* __restrict__ idx, const uint8_t* __restrict__ w2p,
                 const float* __restrict__ shift2, int N, int k, int64_t M, int ntiles, float* __restrict__ y_cm,
                 int64_t y_bstride, uint8_t* __restrict__ y_act, int act_kblocks, int act_kb, uint8_t* __restrict__ y_act2,
@@ -47,10 +48,10 @@ edgeconv_kernel(const float* __restrict__ pq, const int32_t* __restrict__ idx, c
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid < 64) s.shift[tid] = shift2[tid];
-    if (warp == 8) {
+    if (warp == 12) {
         if (lane == 0) {
             for (int i = 0; i < EC_NST; ++i) {
-                mbar_init(&s.full[i], 128);
+                mbar_init(&s.full[i], EC_PROD);
                 mbar_init(&s.empty[i], 1);
             }
             for (int i = 0; i < EC_NACC; ++i) {
@@ -70,27 +71,27 @@ edgeconv_kernel(const float* __restrict__ pq, const int32_t* __restrict__ idx, c
     tc_fence_after();
     const uint32_t tmem = s.tmem_base;
 
-    if (warp < 4) {
+    if (warp < 8) {
         // =============================== producers ===============================
         // Gathers are cp.async (LDGSTS) copies into a 3-deep shared-memory ring, two neighbour slots ahead of the slot
         // being converted, so ~64 KB of P' rows are in flight per SM without holding them in registers.  Each thread
         // converts exactly the 32-byte pieces it copied itself, so cp.async.wait_group is the only synchronisation.
-        const int q = tid & 7, rsub = tid >> 3;
+        const int q = tid & 7, rsub = tid >> 3;   // rsub 0..31: rows rsub, rsub+32, rsub+64, rsub+96
         int* idxs = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(&s) + sizeof(EcSmem));   // [128][k]
         int stage = 0, phase = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int64_t m0 = (int64_t)tile * EC_TM;
-            named_bar_sync(2, 128);                              // previous tile's idx no longer needed
+            named_bar_sync(2, EC_PROD);                          // previous tile's idx no longer needed
             {
                 const int64_t lim = (M - m0) * k;                // valid ints of this tile
                 const int32_t* src = idx + m0 * k;
-                for (int i = tid; i < EC_TM * k; i += 128) idxs[i] = i < lim ? __ldg(src + i) : 0;
+                for (int i = tid; i < EC_TM * k; i += EC_PROD) idxs[i] = i < lim ? __ldg(src + i) : 0;
             }
-            float4 Q[8][2];
-            int64_t base[8];   // b*N of the row's block, or -1 for rows past M
+            float4 Q[4][2];
+            int64_t base[4];   // b*N of the row's block, or -1 for rows past M
 #pragma unroll
-            for (int p = 0; p < 8; ++p) {
-                const int64_t m = m0 + p * 16 + rsub;
+            for (int p = 0; p < 4; ++p) {
+                const int64_t m = m0 + p * 32 + rsub;
                 if (m < M) {
                     base[p] = (m / N) * N;
                     const float4* src = reinterpret_cast<const float4*>(pq + m * 128 + 64 + q * 8);
@@ -101,15 +102,15 @@ edgeconv_kernel(const float* __restrict__ pq, const int32_t* __restrict__ idx, c
                     Q[p][0] = Q[p][1] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
-            named_bar_sync(2, 128);                              // idx tile visible to all producer threads
+            named_bar_sync(2, EC_PROD);                          // idx tile visible to all producer threads
 
             auto issue = [&](int kk) {
                 if (kk < k) {
                     unsigned char* G = s.G[kk % EC_NG];
 #pragma unroll
-                    for (int p = 0; p < 8; ++p) {
+                    for (int p = 0; p < 4; ++p) {
                         if (base[p] >= 0) {
-                            const int r = p * 16 + rsub;
+                            const int r = p * 32 + rsub;
                             const int j = idxs[r * k + kk];
                             const float* src = pq + (base[p] + j) * 128 + q * 8;
                             unsigned char* dst = G + r * 256;
@@ -122,15 +123,16 @@ edgeconv_kernel(const float* __restrict__ pq, const int32_t* __restrict__ idx, c
             };
             issue(0);
             issue(1);
+            issue(2);
             for (int kk = 0; kk < k; ++kk) {
-                issue(kk + 2);
-                cp_async_wait<2>();                              // this thread's copies of slot kk have landed
+                issue(kk + 3);
+                cp_async_wait<3>();                              // this thread's copies of slot kk have landed
                 mbar_wait(&s.empty[stage], phase ^ 1);
                 uint8_t* A = s.A[stage];
                 const unsigned char* G = s.G[kk % EC_NG];
 #pragma unroll
-                for (int p = 0; p < 8; ++p) {
-                    const int r = p * 16 + rsub;
+                for (int p = 0; p < 4; ++p) {
+                    const int r = p * 32 + rsub;
                     uint4 o;
                     if (base[p] >= 0) {
                         const float4 v0 = *reinterpret_cast<const float4*>(G + r * 256 + (((2 * q) ^ (r & 3)) << 4));
@@ -153,7 +155,7 @@ edgeconv_kernel(const float* __restrict__ pq, const int32_t* __restrict__ idx, c
             }
             cp_async_wait<0>();
         }
-    } else if (warp == 8) {
+    } else if (warp == 12) {
         // =============================== MMA issuer ===============================
         if (lane == 0) {
             mbar_wait(&s.wbar, 0);
@@ -185,7 +187,7 @@ edgeconv_kernel(const float* __restrict__ pq, const int32_t* __restrict__ idx, c
         __syncwarp();
     } else {
         // =============================== epilogue ===============================
-        const int quarter = warp - 4;            // == warp % 4: the TMEM lane quarter this warp may read
+        const int quarter = warp - 8;            // == warp % 4: the TMEM lane quarter this warp may read
         const int row = quarter * 32 + lane;
         const uint32_t tlane = (uint32_t)(quarter * 32) << 16;
         int acc = 0, aphase = 0;
@@ -266,7 +268,7 @@ edgeconv_kernel(const float* __restrict__ pq, const int32_t* __restrict__ idx, c
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == 12) {
         tc_fence_after();
         tmem_dealloc(tmem, EC_TMEM_COLS);
     }
@@ -292,15 +294,17 @@ extern "C" int gfs_edgeconv_fwd(const float* pq, const int32_t* idx, const void*
     GFS_REQUIRE(sms > 0, GFS_ERR_CUDA, "gfs_edgeconv_fwd: cannot query the device");
     const int grid = ntiles < sms ? ntiles : sms;
     const size_t smem = sizeof(EcSmem) + 1024 + (size_t)EC_TM * k * sizeof(int);
+    constexpr size_t EC_MAX_SMEM = 227 * 1024;
+    GFS_REQUIRE(smem <= EC_MAX_SMEM, GFS_ERR_UNSUPPORTED, "gfs_edgeconv_fwd: k=%d needs %zu bytes of shared memory (> 227 KB)", k, smem);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (argmax) {
-        GFS_CUDA_OK(allow_smem(reinterpret_cast<const void*>(edgeconv_kernel<true>), sizeof(EcSmem) + 1024 + EC_TM * 64 * sizeof(int)));
+        GFS_CUDA_OK(allow_smem(reinterpret_cast<const void*>(edgeconv_kernel<true>), EC_MAX_SMEM));
         edgeconv_kernel<true><<<grid, EC_THREADS, smem, st>>>(
             pq, idx, static_cast<const uint8_t*>(w2_packed), shift2, N, k, M, ntiles, y_cm, y_bstride,
             static_cast<uint8_t*>(y_act), y_act_kblocks, y_act_kb, static_cast<uint8_t*>(y_act2), y_act2_kblocks, y_act2_kb,
             argmax);
     } else {
-        GFS_CUDA_OK(allow_smem(reinterpret_cast<const void*>(edgeconv_kernel<false>), sizeof(EcSmem) + 1024 + EC_TM * 64 * sizeof(int)));
+        GFS_CUDA_OK(allow_smem(reinterpret_cast<const void*>(edgeconv_kernel<false>), EC_MAX_SMEM));
         edgeconv_kernel<false><<<grid, EC_THREADS, smem, st>>>(
             pq, idx, static_cast<const uint8_t*>(w2_packed), shift2, N, k, M, ntiles, y_cm, y_bstride,
             static_cast<uint8_t*>(y_act), y_act_kblocks, y_act_kb, static_cast<uint8_t*>(y_act2), y_act2_kblocks, y_act2_kb,
