@@ -221,6 +221,39 @@ knn_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int k, co
                 const float dv[4] = {dv4.x, dv4.y, dv4.z, dv4.w};
                 float tau = s.tau[q];
                 const int jb = j0 + lane * 4;
+                if (LR == 1 && t == 0) {
+                    // First tile: every candidate is a survivor (tau = -inf).  Instead of four overflow merges, sort the four
+                    // 32-candidate column groups as four interleaved bitonic networks (ILP 4) and merge them pairwise:
+                    // the row's list starts as the exact top 32 of its first 128 candidates.
+                    u64 key[4];
+#pragma unroll
+                    for (int v = 0; v < 4; ++v)
+                        key[v] = (jb + v < N) ? (((u64)ord_key(dv[v]) << 32) | (u64)(~(uint32_t)(jb + v))) : 0ull;
+#pragma unroll
+                    for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+#pragma unroll
+                        for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+                            const bool keep_max = ((lane & j2) == 0) == ((lane & k2) == 0);
+#pragma unroll
+                            for (int v = 0; v < 4; ++v) key[v] = cmpex(key[v], j2, keep_max);
+                        }
+                    }
+                    u64 r1 = __shfl_sync(0xffffffffu, key[1], 31 - lane), r3 = __shfl_sync(0xffffffffu, key[3], 31 - lane);
+                    u64 t0 = key[0] > r1 ? key[0] : r1, t1 = key[2] > r3 ? key[2] : r3;
+#pragma unroll
+                    for (int j2 = 16; j2 > 0; j2 >>= 1) {
+                        t0 = cmpex(t0, j2, (lane & j2) == 0);
+                        t1 = cmpex(t1, j2, (lane & j2) == 0);
+                    }
+                    const u64 rr1 = __shfl_sync(0xffffffffu, t1, 31 - lane);
+                    u64 f = t0 > rr1 ? t0 : rr1;
+#pragma unroll
+                    for (int j2 = 16; j2 > 0; j2 >>= 1) f = cmpex(f, j2, (lane & j2) == 0);
+                    s.list[q * 64 + lane] = make_uint2((uint32_t)(f >> 32), (uint32_t)f);
+                    const uint32_t kth = __shfl_sync(0xffffffffu, (uint32_t)(f >> 32), k - 1);
+                    if (lane == 0) s.tau[q] = kth ? ord_val(kth) : -INFINITY;
+                    continue;
+                }
                 bool p[4];
                 unsigned m[4];
 #pragma unroll
