@@ -11,10 +11,11 @@ ACT_NONE, ACT_LRELU02, ACT_RELU = 0, 1, 2
 
 # ---- launch accounting / optional per-call CUDA-event timing (bench.py's roofline leg) ----
 LAUNCHES = 0            # kernels launched through the C ABI since import (each entry point launches a fixed number)
+PROFILE_SHAPES = False  # add the GEMM shape to the profile key
 PROFILE = None          # set to {} to record (name, start_event, end_event) per call on the current stream
 
 
-def _call(name: str, n_kernels: int, *args):
+def _call(name: str, n_kernels: int, *args, tag: str = ""):
     global LAUNCHES
     fn = getattr(lib(), name)
     if PROFILE is None:
@@ -24,7 +25,7 @@ def _call(name: str, n_kernels: int, *args):
         e0.record()
         rc = fn(*args)
         e1.record()
-        PROFILE.setdefault(name, []).append((e0, e1))
+        PROFILE.setdefault(name + tag, []).append((e0, e1))
     LAUNCHES += n_kernels
     check(rc, name)
 
@@ -231,7 +232,8 @@ def gemm_f32(A, lda, a_trans, B, ldb, b_trans, R, Ncols, K, C, ldc, c_trans=Fals
     _need_cuda(A, B, C, bias)
     ws = torch.empty(splitk * R * Ncols, dtype=torch.float32, device=C.device) if splitk > 1 else None
     _call("gfs_gemm_f32", 2 if splitk > 1 else 1, _ptr(A), lda, int(a_trans), a_bs, _ptr(B), ldb, int(b_trans), b_bs, _ptr(C), ldc,
-          int(c_trans), c_bs, _ptr(bias), R, Ncols, K, batch, splitk, _ptr(ws), int(accumulate), _stream())
+          int(c_trans), c_bs, _ptr(bias), R, Ncols, K, batch, splitk, _ptr(ws), int(accumulate), _stream(),
+          tag=(f"[{R}x{Ncols}x{K} b{batch} t{int(a_trans)}{int(b_trans)}{int(c_trans)} sk{splitk}]" if PROFILE_SHAPES else ""))
     return C
 
 

@@ -77,6 +77,7 @@ if dist:
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / a.steps
 ops.PROFILE = {}
+ops.PROFILE_SHAPES = True
 step(0)
 torch.cuda.synchronize()
 prof = {k: round(sum(s_.elapsed_time(e_) for s_, e_ in v), 3) for k, v in ops.PROFILE.items()}

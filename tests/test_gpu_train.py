@@ -200,3 +200,40 @@ def test_adam_steps_reduce_the_loss(golden, golden_sd):
         losses.append(float(loss.detach()))
     print("losses:", " ".join(f"{v:.4f}" for v in losses))
     assert losses[-1] < losses[0] - 0.05
+
+
+def test_eval_after_training_uses_the_updated_weights(golden, golden_sd):
+    """train a few steps, switch to eval: the folded / packed inference weights must be rebuilt from the updated parameters and
+    BatchNorm running statistics (checked against the oracle evaluated on the model's own state_dict)"""
+    import random
+    m, g = _train_model(golden, golden_sd)
+    x, y = torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["y"]).long().cuda()
+    gp = torch.from_numpy(g["gp"])
+    gen = torch.Generator().manual_seed(5)
+    gened = torch.nn.functional.normalize(torch.randn(13, 128, generator=gen), dim=1)
+    coding = (torch.rand(13, 150, generator=gen) < 0.3).float()
+    kw = dict(y=None, eval_model=True, gened_proto=gened.cuda(), base_class_coding=coding[:7].cuda(), novel_class_coding=coding[7:].cuda())
+    m.eval()
+    with torch.no_grad():
+        before, _, _ = m(x=x, **kw)
+    m.train()
+    opt = torch.optim.Adam(m.parameters(), lr=5e-3)
+    for _ in range(3):
+        random.seed(7)
+        opt.zero_grad()
+        _, loss = m(x=x, y=y)
+        loss.backward()
+        opt.step()
+    m.eval()
+    with torch.no_grad():
+        after, _, _ = m(x=x, **kw)
+    assert not torch.allclose(before, after), "eval output must change after training steps"
+    sd = {k: v.detach().float().cpu() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        ref, f = O.forward_eval(sd, gp, x.cpu(), gened, coding[:7], coding[7:], 7, 1.2)
+    same = (m._features(x)[1].cpu().long() == f["assignment"])
+    mask = same.unsqueeze(1).expand_as(ref)
+    err = float((after.cpu() - ref)[mask].abs().max() / ref.abs().max())
+    agree = float((after.argmax(1).cpu() == ref.argmax(1)).float().mean())
+    print(f"eval after training: logits rel err {err:.3e}, label agreement {agree:.4f}, GW assignment agreement {float(same.float().mean()):.4f}")
+    assert err <= 2e-2 and agree >= 0.99
