@@ -253,7 +253,7 @@ def main():
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
 
     # dominant kernel: the fused kNN (3 launches per step; the two C=64 layers dominate)
-    knn_ms = prof.get("gfs_knn_f32", 0.0)
+    knn_ms = prof.get("gfs_knn_tc_f32", 0.0) + prof.get("gfs_knn_f32", 0.0)
     knn_bytes = sum(B * NPTS * (c * 4 + KNN * 4) for c in (9, 64, 64))                  # read x once + write idx, per step
     knn_flops = sum(2.0 * c * NPTS * NPTS * B for c in (9, 64, 64))
     ec_ms = prof.get("gfs_edgeconv_fwd", 0.0)
@@ -266,11 +266,11 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["knn_kernel_bytes_per_step_b32"] * B / 32.0
     except Exception:
         pass
-    roof = {"kernel": "knn_kernel (gfs_knn_f32, 3 launches/step)", "bound": "hbm", "achieved": gbs(knn_bytes, knn_ms), "peak": hbm_peak,
+    roof = {"kernel": "kNN graph: knn_prep + knn_tc (tcgen05 filter) + knn_finish (gfs_knn_tc_f32, 3 calls/step)", "bound": "hbm", "achieved": gbs(knn_bytes, knn_ms), "peak": hbm_peak,
             "unit": "GB/s", "frac": (gbs(knn_bytes, knn_ms) or 0) / hbm_peak, "traffic": traffic, "peak_source": peak_src,
             "ms_per_step": knn_ms, "share_of_step": knn_ms / (sum(prof.values()) or 1),
-            "binding_roof": "fp32 FFMA + top-k selection (not HBM): see fp32_tflops", "fp32_tflops": knn_flops / 1e12 / (knn_ms / 1e3) if knn_ms else None,
-            "fp32_peak_tflops_nominal": 74.4,
+            "binding_roof": "per-row top-k selection out of TMEM (dependent-issue latency), not HBM or the tensor pipe",
+            "distance_tflops_algorithmic": knn_flops / 1e12 / (knn_ms / 1e3) if knn_ms else None,
             "timing": "CUDA events around every C-ABI call on the launch stream, instrumented replay of the same K steps"}
     extra = {
         "edgeconv_given_graph": {"bound": "hbm", "achieved": gbs(ec_bytes, ec_ms), "peak": hbm_peak, "unit": "GB/s",

@@ -2,6 +2,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <mutex>
+#include <map>
 #include <set>
 #include <utility>
 
@@ -33,14 +34,15 @@ int sm_count() {
 
 cudaError_t allow_smem(const void* func, size_t bytes) {
     static std::mutex mu;
-    static std::set<std::pair<int, const void*>> done;
+    static std::map<std::pair<int, const void*>, size_t> done;   // largest size granted so far
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     std::lock_guard<std::mutex> lk(mu);
-    if (done.count({dev, func})) return cudaSuccess;
+    auto it = done.find({dev, func});
+    if (it != done.end() && it->second >= bytes) return cudaSuccess;
     e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (e == cudaSuccess) done.insert({dev, func});
+    if (e == cudaSuccess) done[{dev, func}] = bytes;
     return e;
 }
 

@@ -180,7 +180,7 @@ attention_kernel(const uint8_t* __restrict__ qkv, int kblocks, int kb_q, int til
                 for (int c0 = 0; c0 < 128; c0 += 32) {
                     uint32_t r[32];
                     tmem_ld32(tmem + tlane + TM_S + sb * 128 + c0, r);
-                    tmem_ld_wait();
+                    tmem_ld_wait32(r);
 #pragma unroll
                     for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(r[c]));
                 }
@@ -193,7 +193,7 @@ attention_kernel(const uint8_t* __restrict__ qkv, int kblocks, int kb_q, int til
                 for (int c0 = 0; c0 < 128; c0 += 32) {
                     uint32_t r[32];
                     tmem_ld32(tmem + tlane + TM_S + sb * 128 + c0, r);
-                    tmem_ld_wait();
+                    tmem_ld_wait32(r);
                     uint8_t* Pt = s.P[sb] + (c0 >> 6) * 16384;
 #pragma unroll
                     for (int qq = 0; qq < 4; ++qq) {
@@ -224,7 +224,7 @@ attention_kernel(const uint8_t* __restrict__ qkv, int kblocks, int kb_q, int til
                     for (int h = 0; h < 2; ++h) {
                         uint32_t r[32];
                         tmem_ld32(tmem + tlane + TM_O + ob * 64 + h * 32, r);
-                        tmem_ld_wait();
+                        tmem_ld_wait32(r);
 #pragma unroll
                         for (int c = 0; c < 32; ++c) o[h * 32 + c] = (o[h * 32 + c] + __uint_as_float(r[c])) * alpha;
                     }
@@ -244,7 +244,7 @@ attention_kernel(const uint8_t* __restrict__ qkv, int kblocks, int kb_q, int til
                 for (int h = 0; h < 2; ++h) {
                     uint32_t r[32];
                     tmem_ld32(tmem + tlane + TM_O + ob * 64 + h * 32, r);
-                    tmem_ld_wait();
+                    tmem_ld_wait32(r);
 #pragma unroll
                     for (int c = 0; c < 32; ++c) o[h * 32 + c] = (o[h * 32 + c] + __uint_as_float(r[c])) * inv;
                 }

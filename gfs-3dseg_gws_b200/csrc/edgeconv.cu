@@ -207,7 +207,7 @@ edgeconv_kernel(const float* __restrict__ pq, const int32_t* __restrict__ idx, c
                 for (int h = 0; h < 2; ++h) {
                     uint32_t r[32];
                     tmem_ld32(tmem + tlane + acc * 64 + h * 32, r);
-                    tmem_ld_wait();
+                    tmem_ld_wait32(r);
 #pragma unroll
                     for (int c = 0; c < 32; ++c) {
                         const float vv = __uint_as_float(r[c]);

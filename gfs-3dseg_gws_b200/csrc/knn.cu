@@ -103,7 +103,9 @@ __device__ __noinline__ float knn_flush(KnnSmem& s, int q, int lane, int fill, i
 template <int LR>
 __global__ void __launch_bounds__(KNN_THREADS, 1)
 knn_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int k, const float* __restrict__ sqnorm,
-           int32_t* __restrict__ idx_out, float* __restrict__ dist_out) {
+           int32_t* __restrict__ idx_out, float* __restrict__ dist_out, const int* __restrict__ tile_flags) {
+    // repair pass of knn_tc.cu: only the flagged 64-row tiles are redone
+    if (tile_flags && tile_flags[blockIdx.y * gridDim.x + blockIdx.x] == 0) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     KnnSmem& s = *reinterpret_cast<KnnSmem*>(smem_raw);
     float* As = reinterpret_cast<float*>(smem_raw + sizeof(KnnSmem));
@@ -320,6 +322,26 @@ knn_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int k, co
     }
 }
 
+static int knn_exact_launch(const float* x, int64_t x_bstride, int B, int C, int N, int k, const float* sqnorm, const int* flags,
+                            int32_t* idx_out, float* dist_out, cudaStream_t st) {
+    const size_t smem = sizeof(KnnSmem) + (size_t)C * T_ROWS * sizeof(float);
+    const dim3 grid((N + T_ROWS - 1) / T_ROWS, B);
+    if (k <= 32) {
+        GFS_CUDA_OK(allow_smem(reinterpret_cast<const void*>(knn_kernel<1>), sizeof(KnnSmem) + 64 * T_ROWS * sizeof(float)));
+        knn_kernel<1><<<grid, KNN_THREADS, smem, st>>>(x, x_bstride, C, N, k, sqnorm, idx_out, dist_out, flags);
+    } else {
+        GFS_CUDA_OK(allow_smem(reinterpret_cast<const void*>(knn_kernel<2>), sizeof(KnnSmem) + 64 * T_ROWS * sizeof(float)));
+        knn_kernel<2><<<grid, KNN_THREADS, smem, st>>>(x, x_bstride, C, N, k, sqnorm, idx_out, dist_out, flags);
+    }
+    GFS_LAUNCH_OK("knn_kernel");
+    return GFS_OK;
+}
+
+int knn_exact_flagged(const float* x, int64_t x_bstride, int B, int C, int N, int k, const float* sqnorm, const int* flags,
+                      int32_t* idx_out, float* dist_out, cudaStream_t st) {
+    return knn_exact_launch(x, x_bstride, B, C, N, k, sqnorm, flags, idx_out, dist_out, st);
+}
+
 }  // namespace gfs
 
 extern "C" int gfs_knn_f32(const float* x, int64_t x_bstride, int B, int C, int N, int k, float* sqnorm, int32_t* idx_out,
@@ -335,15 +357,5 @@ extern "C" int gfs_knn_f32(const float* x, int64_t x_bstride, int B, int C, int 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     sqnorm_kernel<<<dim3((N + 255) / 256, B), 256, 0, st>>>(x, x_bstride, C, N, sqnorm);
     GFS_LAUNCH_OK("sqnorm_kernel");
-    const size_t smem = sizeof(KnnSmem) + (size_t)C * T_ROWS * sizeof(float);
-    const dim3 grid((N + T_ROWS - 1) / T_ROWS, B);
-    if (k <= 32) {
-        GFS_CUDA_OK(allow_smem(reinterpret_cast<const void*>(knn_kernel<1>), sizeof(KnnSmem) + 64 * T_ROWS * sizeof(float)));
-        knn_kernel<1><<<grid, KNN_THREADS, smem, st>>>(x, x_bstride, C, N, k, sqnorm, idx_out, dist_out);
-    } else {
-        GFS_CUDA_OK(allow_smem(reinterpret_cast<const void*>(knn_kernel<2>), sizeof(KnnSmem) + 64 * T_ROWS * sizeof(float)));
-        knn_kernel<2><<<grid, KNN_THREADS, smem, st>>>(x, x_bstride, C, N, k, sqnorm, idx_out, dist_out);
-    }
-    GFS_LAUNCH_OK("knn_kernel");
-    return GFS_OK;
+    return knn_exact_launch(x, x_bstride, B, C, N, k, sqnorm, nullptr, idx_out, dist_out, st);
 }

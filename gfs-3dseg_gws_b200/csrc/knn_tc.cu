@@ -1,0 +1,622 @@
+// knn_tc.cu -- kNN graph with a tensor-core candidate filter and an exact fp32 finish (model/dgcnn.py:17-23).
+//
+// The pinned result (oracle/gfs_oracle.c: d = fmaf(2, dot, -xx_i) - xx_j with dot one fp32 fma chain, the k largest per row,
+// ties -> ascending index) cannot be formed on tensor cores, but the tensor cores can tell cheaply which few candidates
+// can possibly be among the k best:
+//
+//   1. knn_center_kernel / knn_prep_kernel: distances do not change under a translation, so the filter works on
+//      coordinates centred on the block mean (small norms = small absolute error).  Every centred coordinate is split into
+//      two bf16 terms x~ = h + l (+ r, |r| <= 2^-18 |x~|) and stored as [h | l] in the UMMA K-major SWIZZLE_128B tile
+//      layout, next to -|x~_j|^2/2 per point and a point-major fp32 copy of the ORIGINAL coordinates.
+//   2. knn_tc_kernel: one CTA owns 256 query rows of one block (two UMMA M=128 tiles, operands resident in shared
+//      memory) and streams the block's candidates in stages of 64 (TMA bulk copies, double buffered).  Per stage three
+//      tcgen05.mma chains  h_i.h_j + h_i.l_j + l_i.h_j  leave  D' ~= x~_i.x~_j  in TMEM (fp32, four stages in flight).
+//      Eight selection warps read TMEM with tcgen05.ld, ONE THREAD PER QUERY ROW (no shuffles, no cross-lane sorting):
+//      every candidate whose filter value v = D' - |x~_j|^2/2 reaches (bound - margin) is appended to the row's cell
+//      array in shared memory (predicated 8-byte stores; a few percent of the candidates).  When the cells fill up, the
+//      new ones are folded into a k-deep sorted register list (min/max chain), bound = the exact k-th best v so far,
+//      and the cells below (bound - margin) are dropped.
+//      margin = 2^-14 (|x~_i|^2 + max_j |x~_j|^2) + (C+4) 2^-24 (|x_i|^2 + max_j |x_j|^2) is twice a bound on the
+//      error of v against the pinned distance (in units of v = d/2 + const): bf16 split residual <= 3 * 2^-18 |x~_i||x~_j|,
+//      fp32 accumulation of <= 192 products in the tensor core (<= 1 ulp each), and the rounding of the pinned fp32
+//      chain itself on the original coordinates; tests/test_gpu_knn_tc.py measures the observed error against it.  Any
+//      candidate outside (k-th best v - margin) therefore cannot be among the exact top k.
+//   3. knn_finish_kernel: the survivors (k plus a handful) get their EXACT pinned distance from the point-major fp32
+//      copy, one warp per row and one lane per survivor, are sorted by (d desc, index asc) and written out:
+//      bit-identical to knn.cu.  A row with more than 64 survivors (floods of exact ties) raises a flag for its 64-row
+//      tile and knn.cu's exact kernel redoes just those tiles inside the same call.
+#include "common.cuh"
+
+namespace gfs {
+
+constexpr int KT_ROWS = 256;          // query rows per CTA
+constexpr int KT_COLS = 64;           // candidates per stage
+constexpr int KT_TST = 4;             // TMEM stages: 2 row tiles x 4 stages x 64 fp32 columns = 512 columns
+constexpr int KT_THREADS = 384;       // warp 0 TMA, warp 1 MMA, warps 2-3 idle, warps 4-11 selection
+constexpr int KT_P = 64;              // candidate cells (8 bytes) per row
+constexpr int KT_SURV = 64;           // survivors per row handed to the finish kernel (one or two per lane)
+
+typedef unsigned long long u64;
+
+__device__ __forceinline__ uint32_t kt_ord_key(float d) {
+    const uint32_t u = __float_as_uint(d);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float kt_ord_val(uint32_t u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// operand preparation
+// ---------------------------------------------------------------------------------------------------------------
+// mu[b][c] = mean over the block's points (any shift would be valid; the mean makes the centred norms small)
+__global__ void __launch_bounds__(256)
+knn_center_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, float* __restrict__ mu) {
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int c = blockIdx.y * 8 + warp; c < C; c += 8 * gridDim.y) {
+        const float* p = x + (int64_t)b * bstride + (int64_t)c * N;
+        float acc = 0.0f;
+        for (int n = lane * 4; n < N; n += 128) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(p + n));
+            acc += (v.x + v.y) + (v.z + v.w);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) mu[b * 64 + c] = acc / (float)N;
+    }
+}
+
+// one thread per point
+__global__ void __launch_bounds__(128)
+knn_prep_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int Npad, int Cp16, int KB, int CPT,
+                const float* __restrict__ mu, uint8_t* __restrict__ ops, float* __restrict__ xp, float* __restrict__ nh,
+                float* __restrict__ sqnorm, int* __restrict__ m2) {
+    const int t = threadIdx.x, rt = blockIdx.x, b = blockIdx.y;
+    const int n = rt * 128 + t;
+    const bool valid = n < N;
+    const float* xb = x + (int64_t)b * bstride + n;
+    const float* mub = mu + b * 64;
+    uint8_t* tiles = ops + ((int64_t)b * (Npad / 128) + rt) * KB * 16384;
+    float* xrow = xp + ((int64_t)b * Npad + n) * CPT;
+    float xx = 0.0f, cc = 0.0f;
+    for (int c0 = 0; c0 < Cp16; c0 += 8) {
+        float xv[8], xc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int c = c0 + e;
+            const bool on = valid && c < C;
+            xv[e] = on ? __ldg(xb + (int64_t)c * N) : 0.0f;
+            xc[e] = on ? xv[e] - mub[c] : 0.0f;
+            xx = fmaf(xv[e], xv[e], xx);          // same chain as sqnorm_kernel (zeros past C leave it unchanged)
+            cc = fmaf(xc[e], xc[e], cc);
+        }
+        uint32_t hp[4], lp[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(xc[2 * e]), h1 = __float2bfloat16_rn(xc[2 * e + 1]);
+            const float r0 = xc[2 * e] - __bfloat162float(h0), r1 = xc[2 * e + 1] - __bfloat162float(h1);
+            __nv_bfloat162 hh;
+            hh.x = h0;
+            hh.y = h1;
+            hp[e] = *reinterpret_cast<uint32_t*>(&hh);
+            lp[e] = pack_bf16x2(r0, r1);
+        }
+        const int ch = c0, cl = Cp16 + c0;
+        *reinterpret_cast<uint4*>(tiles + (ch >> 6) * 16384 + sw128(t, (ch & 63) >> 3)) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+        *reinterpret_cast<uint4*>(tiles + (cl >> 6) * 16384 + sw128(t, (cl & 63) >> 3)) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+        *reinterpret_cast<float4*>(xrow + c0) = make_float4(xv[0], xv[1], xv[2], xv[3]);
+        *reinterpret_cast<float4*>(xrow + c0 + 4) = make_float4(xv[4], xv[5], xv[6], xv[7]);
+    }
+    for (int c0 = Cp16; c0 < CPT; c0 += 4) *reinterpret_cast<float4*>(xrow + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
+    nh[(int64_t)b * Npad + n] = valid ? -0.5f * cc : -INFINITY;
+    if (valid) sqnorm[(int64_t)b * N + n] = xx;
+    float mc = valid ? cc : 0.0f, mo = valid ? xx : 0.0f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mc = fmaxf(mc, __shfl_xor_sync(0xffffffffu, mc, o));
+        mo = fmaxf(mo, __shfl_xor_sync(0xffffffffu, mo, o));
+    }
+    if ((t & 31) == 0) {   // norms are >= 0: the int order is the float order
+        atomicMax(m2 + 2 * b, __float_as_int(mc));
+        atomicMax(m2 + 2 * b + 1, __float_as_int(mo));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// main kernel
+// ---------------------------------------------------------------------------------------------------------------
+struct KtCtl {
+    float nh[KT_TST][KT_COLS];
+    uint64_t a_full, b_full[2], b_empty[2], d_full[KT_TST], d_empty[KT_TST];
+    uint32_t tmem_base;
+};
+
+template <int KL>
+__device__ __forceinline__ void kt_insert(float (&L)[KL], float v) {
+#pragma unroll
+    for (int i = 0; i < KL; ++i) {
+        const float hi = fmaxf(L[i], v);
+        v = fminf(L[i], v);
+        L[i] = hi;
+    }
+}
+template <int KL>
+__device__ __forceinline__ float kt_kth(const float (&L)[KL], int k) {   // L[k-1] without indexing registers dynamically
+    float r = L[0];
+#pragma unroll
+    for (int i = 1; i < KL; ++i) r = (i == k - 1) ? L[i] : r;
+    return r;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t a) {
+    uint2 r;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];\n" : "=r"(r.x), "=r"(r.y) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};\n" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+
+__device__ __forceinline__ u64 lds_u64(uint32_t a) {
+    u64 r;
+    asm volatile("ld.shared.u64 %0, [%1];\n" : "=l"(r) : "r"(a));
+    return r;
+}
+
+// One selection thread's cells: cell e of row r is the 8 bytes at cells + (e * 256 + r) * 8 = {filter value bits, column}.
+struct KtCells {
+    uint32_t c0;      // address of the row's cell 0
+    uint32_t end;     // next free cell
+    uint32_t mark;    // cells [c0, mark) have already been folded into the sorted list
+};
+constexpr uint32_t KT_STEP = KT_ROWS * 8;
+
+// Bring the row's sorted list L up to date with the cells appended since the last call, take the k-th best as the new
+// bound, drop every cell below (bound - margin).  Returns the new threshold.
+template <int KL>
+__device__ __forceinline__ float kt_refresh(float (&L)[KL], KtCells& s, float margin, int k) {
+    for (uint32_t a = s.mark; a < s.end; a += 2 * KT_STEP) {
+        // two values per trip: the two dependent min/max chains interleave
+        const float v0 = __uint_as_float(lds64(a).x);
+        const float v1 = (a + KT_STEP < s.end) ? __uint_as_float(lds64(a + KT_STEP).x) : -INFINITY;
+        if (fmaxf(v0, v1) > L[KL - 1]) {
+            kt_insert<KL>(L, v0);
+            kt_insert<KL>(L, v1);
+        }
+    }
+    const float thr = fmaxf(kt_kth<KL>(L, k) - margin, -3.402823466e38f);
+    uint32_t w = s.c0;
+    for (uint32_t a = s.c0; a < s.end; a += KT_STEP) {
+        const uint2 e = lds64(a);
+        if (__uint_as_float(e.x) >= thr) {
+            sts64(w, e.x, e.y);
+            w += KT_STEP;
+        }
+    }
+    s.end = s.mark = w;
+    return thr;
+}
+
+// Filter one chunk of 32 candidates (v = filter values, columns jb..jb+31) into the row's cells.
+template <int KL>
+__device__ __forceinline__ void kt_filter32(const float (&v)[32], uint32_t jb, float (&L)[KL], KtCells& cs, float& thr, bool& ovf,
+                                            float margin, int k) {
+    const uint32_t trigger = cs.c0 + (KT_P - 8) * KT_STEP;   // end > trigger  <=>  fewer than 8 free cells
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        if (__any_sync(0xffffffffu, cs.end > trigger)) {
+            const float t = kt_refresh<KL>(L, cs, margin, k);
+            if (cs.end > trigger) {   // still no room: more than P-8 candidates inside the margin (tie flood)
+                ovf = true;
+                cs.end = cs.mark = cs.c0;
+            }
+            thr = ovf ? INFINITY : t;
+        }
+#pragma unroll
+        for (int c = g * 8; c < g * 8 + 8; ++c) {
+            if (v[c] >= thr) {
+                sts64(cs.end, __float_as_uint(v[c]), jb + c);
+                cs.end += KT_STEP;
+            }
+        }
+    }
+}
+
+template <int KL>
+__global__ void __launch_bounds__(KT_THREADS, 1)
+knn_tc_kernel(const uint8_t* __restrict__ ops, const float* __restrict__ nh, const float* __restrict__ sqnorm,
+              const int* __restrict__ m2, int* __restrict__ flags, int C, int N, int Npad, int Cp16, int KB, int k,
+              uint16_t* __restrict__ surv, int* __restrict__ surv_cnt, float* __restrict__ dbg) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    // [A: 2 row tiles x KB k-blocks x 16 KiB][B: 2 stages x KB x 8 KiB (64 candidate rows)][cells: P x 256 x 8 B][ctl]
+    unsigned char* sA = base;
+    const uint32_t a_bytes = (uint32_t)KB * 16384u;   // one row tile of the query operand
+    const uint32_t b_bytes = (uint32_t)KB * 8192u;    // one candidate stage
+    unsigned char* sB0 = sA + 2 * a_bytes;
+    unsigned char* cells = sB0 + 2 * b_bytes;
+    KtCtl& s = *reinterpret_cast<KtCtl*>(cells + KT_P * KT_ROWS * 8);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.y, q0 = blockIdx.x * KT_ROWS;
+    const int nst = Npad / KT_COLS;
+    const uint8_t* blk = ops + (int64_t)b * (Npad / 128) * a_bytes;
+
+    if (warp == 1) {
+        if (lane == 0) {
+            mbar_init(&s.a_full, 1);
+            for (int i = 0; i < 2; ++i) {
+                mbar_init(&s.b_full[i], 1);
+                mbar_init(&s.b_empty[i], 1);
+            }
+            for (int i = 0; i < KT_TST; ++i) {
+                mbar_init(&s.d_full[i], 1);
+                mbar_init(&s.d_empty[i], 8);
+            }
+            mbar_fence_init();
+        }
+        __syncwarp();
+        tmem_alloc(&s.tmem_base, 512);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s.tmem_base;
+    // the eight selection warps carry the register-resident lists and a prefetched TMEM chunk: (setmaxnreg: 4 warps x 40 + 8 warps x 224 registers per thread)
+    // (setmaxnreg at the top of each role branch below)
+
+    if (warp == 0) {
+        // =============================== TMA producer ===============================
+        reg_dealloc<40>();
+        if (lane == 0) {
+            mbar_arrive_expect_tx(&s.a_full, 2u * a_bytes);
+            tma_load_1d(sA, blk + (int64_t)(q0 / 128) * a_bytes, 2u * a_bytes, &s.a_full);
+            for (int st = 0; st < nst; ++st) {
+                const int buf = st & 1, ts = st % KT_TST;
+                mbar_wait(&s.b_empty[buf], ((st >> 1) & 1) ^ 1);
+                mbar_wait(&s.d_empty[ts], ((st / KT_TST) & 1) ^ 1);   // the -|x_j|^2/2 slot is read by the selection warps
+                mbar_arrive_expect_tx(&s.b_full[buf], b_bytes + KT_COLS * 4u);
+                // candidates [st*64, st*64+64): half of row tile st/2, every k-block
+                const uint8_t* src = blk + (int64_t)(st >> 1) * a_bytes + (st & 1) * 8192;
+                for (int kb = 0; kb < KB; ++kb)
+                    tma_load_1d(sB0 + buf * b_bytes + kb * 8192, src + (int64_t)kb * 16384, 8192u, &s.b_full[buf]);
+                tma_load_1d(s.nh[ts], nh + (int64_t)b * Npad + st * KT_COLS, KT_COLS * 4u, &s.b_full[buf]);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // =============================== MMA issuer ===============================
+        reg_dealloc<40>();
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(128, KT_COLS);
+            const int ksteps = Cp16 >> 4;
+            mbar_wait(&s.a_full, 0);
+            for (int st = 0; st < nst; ++st) {
+                const int buf = st & 1, ts = st % KT_TST;
+                mbar_wait(&s.d_empty[ts], ((st / KT_TST) & 1) ^ 1);
+                mbar_wait(&s.b_full[buf], (st >> 1) & 1);
+                tc_fence_after();
+                const uint32_t bB = smem_u32(sB0 + buf * b_bytes);
+#pragma unroll 1
+                for (int mt = 0; mt < 2; ++mt) {
+                    const uint32_t aB = smem_u32(sA + mt * a_bytes);
+                    const uint32_t d = tmem + mt * 256 + ts * KT_COLS;
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        const int ch = ks * 16, cl = Cp16 + ks * 16;
+                        const uint32_t ih = (uint32_t)(ch & 63) * 2u, il = (uint32_t)(cl & 63) * 2u;
+                        const uint64_t ah = umma_desc_sw128(aB + (uint32_t)(ch >> 6) * 16384u + ih);
+                        const uint64_t al = umma_desc_sw128(aB + (uint32_t)(cl >> 6) * 16384u + il);
+                        const uint64_t bh = umma_desc_sw128(bB + (uint32_t)(ch >> 6) * 8192u + ih);
+                        const uint64_t bl = umma_desc_sw128(bB + (uint32_t)(cl >> 6) * 8192u + il);
+                        umma_bf16(d, ah, bh, idesc, ks ? 1u : 0u);
+                        umma_bf16(d, ah, bl, idesc, 1u);
+                        umma_bf16(d, al, bh, idesc, 1u);
+                    }
+                }
+                umma_commit(&s.b_empty[buf]);
+                umma_commit(&s.d_full[ts]);
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // =============================== selection: one thread per query row ===============================
+        reg_alloc<224>();
+        const int mt = (warp - 4) >> 2, quarter = warp & 3;
+        const int row = mt * 128 + quarter * 32 + lane;
+        const int n = q0 + row;
+        const bool valid = n < N;
+        const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16) + mt * 256;
+        KtCells cs;
+        cs.c0 = smem_u32(cells) + row * 8;
+        cs.end = cs.mark = cs.c0;
+        const float xxi = valid ? sqnorm[(int64_t)b * N + n] : 0.0f;
+        const float cci = valid ? -2.0f * nh[(int64_t)b * Npad + n] : 0.0f;     // centred squared norm
+        const float margin = 0x1p-14f * (cci + __int_as_float(m2[2 * b])) +
+                             (float)(C + 4) * 0x1p-24f * (xxi + __int_as_float(m2[2 * b + 1]));
+        bool ovf = !valid;          // "this row takes no more candidates": padding rows, and rows that overflowed
+        float L[KL];
+#pragma unroll
+        for (int i = 0; i < KL; ++i) L[i] = -INFINITY;
+        // -FLT_MAX, not -inf: padded candidates carry -inf and must never pass, not even while the bound is unknown
+        float thr = valid ? -3.402823466e38f : INFINITY;
+
+        // stages of 64 candidates = two chunks of 32; the TMEM load of the next chunk is in flight while one is filtered
+        uint32_t r[32];
+        float v[32];
+        mbar_wait(&s.d_full[0], 0);
+        tc_fence_after();
+        tmem_ld32(tbase, r);
+        for (int st = 0; st < nst; ++st) {
+            const int ts = st % KT_TST;
+            const float* nhs = s.nh[ts];
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                tmem_ld_wait32(r);
+#pragma unroll
+                for (int c = 0; c < 32; c += 4) {
+                    const float4 h4 = *reinterpret_cast<const float4*>(nhs + half * 32 + c);
+                    v[c] = __uint_as_float(r[c]) + h4.x;
+                    v[c + 1] = __uint_as_float(r[c + 1]) + h4.y;
+                    v[c + 2] = __uint_as_float(r[c + 2]) + h4.z;
+                    v[c + 3] = __uint_as_float(r[c + 3]) + h4.w;
+                }
+                if (half == 0) {
+                    tmem_ld32(tbase + ts * KT_COLS + 32, r);
+                } else if (st + 1 < nst) {
+                    const int ts1 = (st + 1) % KT_TST;
+                    mbar_wait(&s.d_full[ts1], ((st + 1) / KT_TST) & 1);
+                    tc_fence_after();
+                    tmem_ld32(tbase + ts1 * KT_COLS, r);
+                }
+                const uint32_t jb = (uint32_t)(st * KT_COLS + half * 32);
+                if (dbg && valid) {   // diagnostic entry only: dump the filter value v = D' - |x~_j|^2/2
+                    float* o = dbg + ((int64_t)b * N + n) * Npad + jb;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) o[c] = v[c];
+                }
+                kt_filter32<KL>(v, jb, L, cs, thr, ovf, margin, k);
+            }
+            // hand the TMEM stage (and its -|x~_j|^2/2 slot) back.  Deliberately at the END of the stage: with four stages in
+            // flight nothing waits for it, and the values of the second half are certainly in registers by now
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s.d_empty[ts]);
+        }
+
+        // ---- hand-off: the cells that survive the exact k-th best filter value go to knn_finish_kernel ----
+        kt_refresh<KL>(L, cs, margin, k);   // cells = {v >= k-th best - margin}
+        if (valid) {
+            const int ns = (int)((cs.end - cs.c0) / KT_STEP);
+            const int64_t g = (int64_t)b * N + n;
+            if (ovf) {
+                surv_cnt[g] = 0;
+                flags[(int64_t)b * ((N + 63) / 64) + n / 64] = 1;
+            } else {
+                surv_cnt[g] = ns;
+                uint16_t* o = surv + g * KT_SURV;
+                for (int e = 0; e < ns; ++e) o[e] = (uint16_t)lds64(cs.c0 + e * KT_STEP).y;
+            }
+        }
+    } else {
+        reg_dealloc<40>();   // warps 2-3 only complete the first warpgroup
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// finish: exact pinned distances of the survivors, sorted, written out.  One warp per query row, one lane per survivor.
+// The survivors' fp32 rows are gathered with coalesced loads (2 or 8 rows per instruction) into a padded staging tile,
+// each lane then runs the pinned fma chain over its own row; a warp-wide bitonic sort of 64-bit keys
+// (orderable d << 32 | ~j) puts the k best first: nearest first, ties -> ascending index.
+// ---------------------------------------------------------------------------------------------------------------
+template <int CPT, int KF_WARPS>
+__global__ void __launch_bounds__(KF_WARPS * 32)
+knn_finish_kernel(const float* __restrict__ xp, const float* __restrict__ sqnorm, const uint16_t* __restrict__ surv,
+                  const int* __restrict__ surv_cnt, int N, int Npad, int k, int64_t rows, int32_t* __restrict__ idx_out,
+                  float* __restrict__ dist_out) {
+    constexpr int RS = CPT + 4;            // padded staging row: conflict-free LDS.128 across lanes
+    constexpr int LPR = CPT / 4;           // lanes that fetch one row
+    constexpr int RPI = 32 / LPR;          // rows per load instruction
+    __shared__ __align__(16) float stg_all[KF_WARPS][32 * RS];
+    __shared__ __align__(16) unsigned long long kbuf[KF_WARPS][64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* stg = stg_all[warp];
+    const int sub = lane % LPR, grp = lane / LPR;
+    // software pipeline over the warp's rows: the next row's survivor list is in flight while this row is finished
+    const int64_t gstep = (int64_t)gridDim.x * KF_WARPS;
+    int64_t g = (int64_t)blockIdx.x * KF_WARPS + warp;
+    int ns_n = 0;
+    uint32_t jl_n = 0, jh_n = 0;
+    if (g < rows) {
+        ns_n = __ldg(surv_cnt + g);
+        jl_n = __ldg(surv + g * KT_SURV + lane);
+        jh_n = __ldg(surv + g * KT_SURV + 32 + lane);
+    }
+    for (; g < rows; g += gstep) {
+        const int ns = ns_n;
+        const uint32_t jl = jl_n, jh = jh_n;
+        if (g + gstep < rows) {
+            ns_n = __ldg(surv_cnt + g + gstep);
+            jl_n = __ldg(surv + (g + gstep) * KT_SURV + lane);
+            jh_n = __ldg(surv + (g + gstep) * KT_SURV + 32 + lane);
+        }
+        if (ns == 0) continue;                       // flagged for the exact repair pass
+        const int64_t b = g / N;
+        const float* xpb = xp + b * Npad * CPT;
+        const float* xr = xpb + (g - b * N) * CPT;
+        float xi[CPT];
+#pragma unroll
+        for (int c = 0; c < CPT; c += 4) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(xr + c));
+            xi[c] = q.x;
+            xi[c + 1] = q.y;
+            xi[c + 2] = q.z;
+            xi[c + 3] = q.w;
+        }
+        const float xxi = __ldg(sqnorm + g);
+        u64* keys = reinterpret_cast<u64*>(kbuf[warp]);
+        for (int half = 0; half * 32 < ns; ++half) {   // a second round only for rows with more than 32 survivors
+            const int e = half * 32 + lane;
+            const uint32_t j = e < ns ? (half ? jh : jl) : 0u;   // entries past ns are uninitialised memory
+            float4 t[32 / RPI];
+#pragma unroll
+            for (int it = 0; it < 32 / RPI; ++it) {
+                const uint32_t jj = __shfl_sync(0xffffffffu, j, it * RPI + grp);
+                t[it] = __ldg(reinterpret_cast<const float4*>(xpb + (int64_t)jj * CPT + sub * 4));
+            }
+            const float xxj = __ldg(sqnorm + b * N + j);
+            __syncwarp();                            // the previous chains are done with the staging tile
+#pragma unroll
+            for (int it = 0; it < 32 / RPI; ++it) *reinterpret_cast<float4*>(stg + (it * RPI + grp) * RS + sub * 4) = t[it];
+            __syncwarp();
+            float dot = 0.0f;
+#pragma unroll
+            for (int c = 0; c < CPT; c += 4) {
+                const float4 q = *reinterpret_cast<const float4*>(stg + lane * RS + c);
+                dot = fmaf(xi[c], q.x, dot);
+                dot = fmaf(xi[c + 1], q.y, dot);
+                dot = fmaf(xi[c + 2], q.z, dot);
+                dot = fmaf(xi[c + 3], q.w, dot);
+            }
+            const float d = fmaf(2.0f, dot, -xxi) - xxj;
+            // 64-bit key: larger = nearer, equal distances -> smaller index first; 0 = empty slot (below every real key)
+            keys[e] = e < ns ? (((u64)kt_ord_key(d) << 32) | (u64)(~j)) : 0ull;
+        }
+        __syncwarp();
+        // rank by counting (independent broadcast reads: no dependent shuffle network), keys are all distinct
+        const int nk = ns > 32 ? 64 : 32;
+        for (int half = 0; half * 32 < ns; ++half) {
+            const u64 mine = keys[half * 32 + lane];
+            int rank = 0;
+#pragma unroll 8
+            for (int f = 0; f < nk; ++f) rank += keys[f] > mine ? 1 : 0;
+            if (mine != 0ull && rank < k) {
+                idx_out[g * k + rank] = (int32_t)(~(uint32_t)mine);
+                if (dist_out) dist_out[g * k + rank] = kt_ord_val((uint32_t)(mine >> 32));
+            }
+        }
+        __syncwarp();                                // keys are reused by the next row
+    }
+}
+
+struct KtPlan {
+    int Npad, Cp16, KB, CPT;
+    size_t off_xp, off_nh, off_surv, off_cnt, off_mu, off_m2, off_flags, total, zero_bytes;
+};
+static KtPlan kt_plan(int B, int C, int N) {
+    KtPlan p;
+    p.Npad = (N + KT_ROWS - 1) / KT_ROWS * KT_ROWS;
+    p.Cp16 = (C + 15) / 16 * 16;
+    p.CPT = C <= 16 ? 16 : 64;
+    p.KB = (2 * p.Cp16 + 63) / 64;
+    size_t o = (size_t)B * (p.Npad / 128) * p.KB * 16384;
+    p.off_xp = o;
+    o += (size_t)B * p.Npad * p.CPT * 4;
+    p.off_nh = o;
+    o += (size_t)B * p.Npad * 4;
+    p.off_surv = o;
+    o += (size_t)B * N * KT_SURV * 2;
+    p.off_cnt = o;
+    o += (size_t)B * N * 4;
+    o = (o + 15) / 16 * 16;
+    p.off_mu = o;
+    o += (size_t)B * 64 * 4;
+    p.off_m2 = o;
+    o += (size_t)B * 8;
+    p.off_flags = o;
+    o += (size_t)B * ((N + 63) / 64) * 4;
+    p.zero_bytes = o - p.off_m2;
+    p.total = (o + 255) / 256 * 256;
+    return p;
+}
+
+// knn.cu: the exact kernel restricted to the flagged 64-row tiles
+int knn_exact_flagged(const float* x, int64_t x_bstride, int B, int C, int N, int k, const float* sqnorm, const int* flags,
+                      int32_t* idx_out, float* dist_out, cudaStream_t st);
+
+static int kt_launch(const KtPlan& p, uint8_t* ws, const float* sqnorm, int B, int C, int N, int k, int32_t* idx_out, float* dist_out,
+                     float* dbg, cudaStream_t st) {
+    const size_t smem = (size_t)2 * p.KB * 16384 + (size_t)2 * p.KB * 8192 + (size_t)KT_P * KT_ROWS * 8 + sizeof(KtCtl) + 1024;
+    GFS_CUDA_OK(allow_smem(reinterpret_cast<const void*>(knn_tc_kernel<20>), smem));
+    uint16_t* surv = reinterpret_cast<uint16_t*>(ws + p.off_surv);
+    int* cnt = reinterpret_cast<int*>(ws + p.off_cnt);
+    knn_tc_kernel<20><<<dim3(p.Npad / KT_ROWS, B), KT_THREADS, smem, st>>>(
+        ws, reinterpret_cast<const float*>(ws + p.off_nh), sqnorm, reinterpret_cast<const int*>(ws + p.off_m2),
+        reinterpret_cast<int*>(ws + p.off_flags), C, N, p.Npad, p.Cp16, p.KB, k, surv, cnt, dbg);
+    GFS_LAUNCH_OK("knn_tc_kernel");
+    const int64_t rows = (int64_t)B * N;
+    const int sms = sm_count();
+    GFS_REQUIRE(sms > 0, GFS_ERR_CUDA, "gfs_knn_tc_f32: cannot query the device");
+    const float* xp = reinterpret_cast<const float*>(ws + p.off_xp);
+    if (p.CPT == 16) {
+        const int64_t want = (rows + 7) / 8;
+        const int grid = (int)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
+        knn_finish_kernel<16, 8><<<grid, 256, 0, st>>>(xp, sqnorm, surv, cnt, N, p.Npad, k, rows, idx_out, dist_out);
+    } else {
+        const int64_t want = (rows + 3) / 4;
+        const int grid = (int)(want < (int64_t)sms * 16 ? want : (int64_t)sms * 16);
+        knn_finish_kernel<64, 4><<<grid, 128, 0, st>>>(xp, sqnorm, surv, cnt, N, p.Npad, k, rows, idx_out, dist_out);
+    }
+    GFS_LAUNCH_OK("knn_finish_kernel");
+    return GFS_OK;
+}
+
+}  // namespace gfs
+
+extern "C" int64_t gfs_knn_tc_workspace_bytes(int B, int C, int N) {
+    if (B <= 0 || C <= 0 || N <= 0 || C > 64) return 0;
+    return (int64_t)gfs::kt_plan(B, C, N).total;
+}
+
+static int kt_run(const float* x, int64_t x_bstride, int B, int C, int N, int k, float* sqnorm, void* workspace,
+                  int64_t workspace_bytes, int32_t* idx_out, float* dist_out, float* dbg, void* stream) {
+    using namespace gfs;
+    GFS_REQUIRE(x && sqnorm && idx_out && workspace, GFS_ERR_BAD_ARG, "gfs_knn_tc_f32: null pointer");
+    GFS_REQUIRE(B > 0 && C > 0 && N > 0 && k > 0, GFS_ERR_BAD_ARG, "gfs_knn_tc_f32: non-positive size (B=%d C=%d N=%d k=%d)", B, C, N, k);
+    GFS_REQUIRE(k <= N, GFS_ERR_BAD_ARG, "gfs_knn_tc_f32: k=%d exceeds N=%d", k, N);
+    GFS_REQUIRE(k <= 20, GFS_ERR_UNSUPPORTED, "gfs_knn_tc_f32: k=%d > 20 is not built (use gfs_knn_f32)", k);
+    GFS_REQUIRE(C <= 64, GFS_ERR_UNSUPPORTED, "gfs_knn_tc_f32: C=%d > 64 is not built", C);
+    GFS_REQUIRE(N <= 65535, GFS_ERR_UNSUPPORTED, "gfs_knn_tc_f32: N=%d > 65535 (16-bit candidate slots)", N);
+    GFS_REQUIRE(N % 4 == 0 && x_bstride % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, GFS_ERR_UNSUPPORTED,
+                "gfs_knn_tc_f32: needs N %% 4 == 0 and 16-byte aligned rows (N=%d)", N);
+    const KtPlan p = kt_plan(B, C, N);
+    GFS_REQUIRE(workspace_bytes >= (int64_t)p.total && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, GFS_ERR_BAD_ARG,
+                "gfs_knn_tc_f32: workspace of %lld bytes (256-byte aligned) needed, got %lld", (long long)p.total,
+                (long long)workspace_bytes);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    GFS_CUDA_OK(cudaMemsetAsync(ws + p.off_m2, 0, p.zero_bytes, st));
+    knn_center_kernel<<<dim3(B, (C + 7) / 8), 256, 0, st>>>(x, x_bstride, C, N, reinterpret_cast<float*>(ws + p.off_mu));
+    GFS_LAUNCH_OK("knn_center_kernel");
+    knn_prep_kernel<<<dim3(p.Npad / 128, B), 128, 0, st>>>(x, x_bstride, C, N, p.Npad, p.Cp16, p.KB, p.CPT,
+                                                           reinterpret_cast<const float*>(ws + p.off_mu), ws,
+                                                           reinterpret_cast<float*>(ws + p.off_xp),
+                                                           reinterpret_cast<float*>(ws + p.off_nh), sqnorm,
+                                                           reinterpret_cast<int*>(ws + p.off_m2));
+    GFS_LAUNCH_OK("knn_prep_kernel");
+    const int rc = kt_launch(p, ws, sqnorm, B, C, N, k, idx_out, dist_out, dbg, st);
+    if (rc != GFS_OK) return rc;
+    return knn_exact_flagged(x, x_bstride, B, C, N, k, sqnorm, reinterpret_cast<const int*>(ws + p.off_flags), idx_out, dist_out, st);
+}
+
+extern "C" int gfs_knn_tc_f32(const float* x, int64_t x_bstride, int B, int C, int N, int k, float* sqnorm, void* workspace,
+                              int64_t workspace_bytes, int32_t* idx_out, float* dist_out, void* stream) {
+    return kt_run(x, x_bstride, B, C, N, k, sqnorm, workspace, workspace_bytes, idx_out, dist_out, nullptr, stream);
+}
+
+extern "C" int gfs_knn_tc_diag_f32(const float* x, int64_t x_bstride, int B, int C, int N, int k, float* sqnorm, void* workspace,
+                                   int64_t workspace_bytes, int32_t* idx_out, float* filter_out, int32_t* repair_flags_out,
+                                   void* stream) {
+    using namespace gfs;
+    GFS_REQUIRE(filter_out && repair_flags_out, GFS_ERR_BAD_ARG, "gfs_knn_tc_diag_f32: null output");
+    const int rc = kt_run(x, x_bstride, B, C, N, k, sqnorm, workspace, workspace_bytes, idx_out, nullptr, filter_out, stream);
+    if (rc != GFS_OK) return rc;
+    const KtPlan p = kt_plan(B, C, N);
+    GFS_CUDA_OK(cudaMemcpyAsync(repair_flags_out, static_cast<uint8_t*>(workspace) + p.off_flags, (size_t)B * ((N + 63) / 64) * 4,
+                                cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+    return GFS_OK;
+}

@@ -125,7 +125,7 @@ linear_kernel(const uint8_t* __restrict__ x_act, int x_kblocks, int x_kb0, int k
             for (int c0 = 0; c0 < NT; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld32(tmem + tlane + acc * 256 + c0, r);
-                tmem_ld_wait();
+                tmem_ld_wait32(r);
                 float v[32];
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {

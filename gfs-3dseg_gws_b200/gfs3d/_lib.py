@@ -13,6 +13,8 @@ _i, _i64, _p, _f = ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_float
 # name -> argtypes; every function returns int (gfs_status) except the three utilities
 SIGNATURES = {
     "gfs_knn_f32": [_p, _i64, _i, _i, _i, _i, _p, _p, _p, _p],
+    "gfs_knn_tc_f32": [_p, _i64, _i, _i, _i, _i, _p, _p, _i64, _p, _p, _p],
+    "gfs_knn_tc_diag_f32": [_p, _i64, _i, _i, _i, _i, _p, _p, _i64, _p, _p, _p, _p],
     "gfs_pointwise_f32": [_p, _i64, _i, _i, _i, _p, _p, _i, _p, _p],
     "gfs_edgeconv_fwd": [_p, _p, _p, _p, _i, _i, _i, _p, _i64, _p, _i, _i, _p, _i, _i, _p, _p],
     "gfs_pack_weight_bf16": [_p, _p, _i, _i, _p, _p],
@@ -37,7 +39,8 @@ SIGNATURES = {
     "gfs_softmax_rows_bwd": [_p, _p, _p, _i64, _i, _f, _p, _p],
 }
 UTILITIES = {"gfs_version": (_i, []), "gfs_last_error_string": (ctypes.c_char_p, []),
-             "gfs_device_sm_count": (_i, []), "gfs_kmeans_partials": (_i, [])}
+             "gfs_device_sm_count": (_i, []), "gfs_kmeans_partials": (_i, []),
+             "gfs_knn_tc_workspace_bytes": (_i64, [_i, _i, _i])}
 
 _lib = None
 

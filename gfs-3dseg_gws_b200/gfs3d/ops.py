@@ -1,5 +1,6 @@
 """Thin torch-facing wrappers over the C ABI: allocate outputs as torch tensors, pass raw device pointers and the
 current CUDA stream.  No arithmetic happens here."""
+import os
 from typing import Optional
 
 import torch
@@ -66,16 +67,50 @@ def act_to_dense(act: torch.Tensor, M: int) -> torch.Tensor:
     return dense.permute(0, 2, 1, 3, 4).reshape(mt * 128, kb * 64)[:M]
 
 
-def knn(x: torch.Tensor, k: int, return_dist: bool = False):
-    """x: (B, C, N) fp32 view with unit point stride and channel stride N -> idx (B, N, k) int32"""
+KNN_IMPL = os.environ.get("GFS3D_KNN", "auto")   # "auto" | "tc" | "exact": both are CUDA and return identical bits
+
+
+def knn_tc_eligible(C: int, N: int, k: int) -> bool:
+    return k <= 20 and C <= 64 and N <= 65535 and N % 4 == 0
+
+
+def knn(x: torch.Tensor, k: int, return_dist: bool = False, impl: Optional[str] = None):
+    """x: (B, C, N) fp32 view with unit point stride and channel stride N -> idx (B, N, k) int32
+
+    impl "tc": tensor-core filter + exact finish (gfs_knn_tc_f32); "exact": the all-fp32 kernel (gfs_knn_f32);
+    "auto": tc whenever the shape is eligible.  The two produce the same indices and distances bit for bit."""
     _need_cuda(x)
     B, C, N = x.shape
     assert x.dtype == torch.float32 and x.stride(2) == 1 and x.stride(1) == N, "x must be channel-major"
+    impl = impl or KNN_IMPL
     sq = torch.empty(B, N, dtype=torch.float32, device=x.device)
     idx = torch.empty(B, N, k, dtype=torch.int32, device=x.device)
     dist = torch.empty(B, N, k, dtype=torch.float32, device=x.device) if return_dist else None
-    _call("gfs_knn_f32", 2, _ptr(x), x.stride(0), B, C, N, k, _ptr(sq), _ptr(idx), _ptr(dist), _stream())
+    if impl == "tc" or (impl == "auto" and knn_tc_eligible(C, N, k)):
+        nbytes = int(lib().gfs_knn_tc_workspace_bytes(B, C, N))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        _call("gfs_knn_tc_f32", 4, _ptr(x), x.stride(0), B, C, N, k, _ptr(sq), _ptr(ws), nbytes, _ptr(idx), _ptr(dist),
+              _stream())
+    else:
+        _call("gfs_knn_f32", 2, _ptr(x), x.stride(0), B, C, N, k, _ptr(sq), _ptr(idx), _ptr(dist), _stream())
     return (idx, dist) if return_dist else idx
+
+
+def knn_tc_diag(x: torch.Tensor, k: int):
+    """(tests) tc kNN + what its filter saw: returns idx (B,N,k), filter (B,N,Npad) ~ x_i.x_j - |x_j|^2/2, flags (B, ceil(N/64))"""
+    _need_cuda(x)
+    B, C, N = x.shape
+    assert x.dtype == torch.float32 and x.stride(2) == 1 and x.stride(1) == N
+    npad = (N + 255) // 256 * 256
+    sq = torch.empty(B, N, dtype=torch.float32, device=x.device)
+    idx = torch.empty(B, N, k, dtype=torch.int32, device=x.device)
+    filt = torch.zeros(B, N, npad, dtype=torch.float32, device=x.device)
+    flags = torch.empty(B, (N + 63) // 64, dtype=torch.int32, device=x.device)
+    nbytes = int(lib().gfs_knn_tc_workspace_bytes(B, C, N))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    _call("gfs_knn_tc_diag_f32", 4, _ptr(x), x.stride(0), B, C, N, k, _ptr(sq), _ptr(ws), nbytes, _ptr(idx), _ptr(filt),
+          _ptr(flags), _stream())
+    return idx, filt, flags
 
 
 def pointwise(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:

@@ -26,10 +26,12 @@ def test_knn_bit_exact_vs_oracle(B, C, N, k, dup):
     else:
         x = torch.randn(B, C, N, generator=torch.Generator().manual_seed(N + C)) * 0.3
     idx_ref, d_ref = O.knn_exact(x, k, return_dist=True)
-    idx, d = ops.knn(x.cuda(), k, return_dist=True)
-    torch.cuda.synchronize()
-    assert torch.equal(idx.cpu(), idx_ref), "neighbour indices differ from the pinned-order oracle"
-    assert torch.equal(d.cpu(), d_ref), "distances are not bit-identical"
+    impls = ["exact", "tc"] if ops.knn_tc_eligible(C, N, k) else ["exact"]
+    for impl in impls:
+        idx, d = ops.knn(x.cuda(), k, return_dist=True, impl=impl)
+        torch.cuda.synchronize()
+        assert torch.equal(idx.cpu(), idx_ref), f"{impl}: neighbour indices differ from the pinned-order oracle"
+        assert torch.equal(d.cpu(), d_ref), f"{impl}: distances are not bit-identical"
 
 
 def test_knn_on_strided_slice_of_concat_buffer():
@@ -125,5 +127,6 @@ def test_knn_tie_floods_take_the_exact_fallback(N, k, frac):
     nd = int(N * frac)
     x[:, :, torch.randperm(N, generator=g)[:nd]] = x[:, :, :1]          # nd copies of point 0
     idx_ref, d_ref = O.knn_exact(x, k, return_dist=True)
-    idx, d = ops.knn(x.cuda(), k, return_dist=True)
-    assert torch.equal(idx.cpu(), idx_ref) and torch.equal(d.cpu(), d_ref)
+    for impl in (("exact", "tc") if ops.knn_tc_eligible(9, N, k) else ("exact",)):
+        idx, d = ops.knn(x.cuda(), k, return_dist=True, impl=impl)
+        assert torch.equal(idx.cpu(), idx_ref) and torch.equal(d.cpu(), d_ref), impl

@@ -1,0 +1,109 @@
+"""GPU suite: the tensor-core filtered kNN (gfs_knn_tc_f32) must return the bits of the all-fp32 kernel and of the
+pinned-order oracle, and its filter's error must stay inside the margin the proof of exactness assumes."""
+import pytest
+import torch
+
+from oracle import gfs_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from gfs3d import ops
+    return ops
+
+
+def _both(x, k):
+    ops = _ops()
+    a = ops.knn(x, k, return_dist=True, impl="exact")
+    b = ops.knn(x, k, return_dist=True, impl="tc")
+    torch.cuda.synchronize()
+    return a, b
+
+
+@pytest.mark.parametrize("B,C,N,k", [(4, 64, 2048, 20), (4, 9, 2048, 20), (2, 64, 1000, 20), (3, 6, 300, 16),
+                                     (2, 48, 516, 20), (1, 17, 260, 1), (2, 64, 4096, 20), (1, 12, 8192, 20)])
+def test_tc_equals_exact_kernel_bit_for_bit(B, C, N, k):
+    g = torch.Generator().manual_seed(B * 1000 + C * 10 + N)
+    x = torch.randn(B, C, N, generator=g).cuda() * 0.7
+    (ia, da), (ib, db) = _both(x, k)
+    assert torch.equal(ia, ib), "indices differ between the tensor-core filtered and the all-fp32 kernel"
+    assert torch.equal(da, db), "distances differ"
+
+
+def test_tc_on_edgeconv_like_features_full_batch():
+    """post-LeakyReLU, correlated 64-channel features (what the second and third kNN of the backbone see)"""
+    g = torch.Generator().manual_seed(5)
+    B, N = 8, 2048
+    pos = torch.rand(B, 3, N, generator=g)
+    w = torch.randn(64, 3, generator=g)
+    f = torch.nn.functional.leaky_relu(torch.einsum("oc,bcn->bon", w, pos) + 0.1 * torch.randn(B, 64, N, generator=g), 0.2)
+    (ia, da), (ib, db) = _both(f.cuda().contiguous(), 20)
+    assert torch.equal(ia, ib) and torch.equal(da, db)
+    ref = O.knn_exact(f[:1], 20)
+    assert torch.equal(ib[:1].cpu(), ref)
+
+
+@pytest.mark.parametrize("case", ["zeros", "offset", "huge", "tiny", "one_hot"])
+def test_tc_adversarial_inputs(case):
+    g = torch.Generator().manual_seed(11)
+    B, C, N, k = 2, 9, 512, 20
+    x = torch.rand(B, C, N, generator=g)
+    if case == "zeros":
+        x.zero_()                                   # every distance ties: all rows go to the exact repair pass
+    elif case == "offset":
+        x += 1000.0                                 # |x|^2 >> neighbour spacing: the margin swallows many candidates
+    elif case == "huge":
+        x *= 1e15
+    elif case == "tiny":
+        x *= 1e-18
+    elif case == "one_hot":
+        x.zero_()
+        x[:, 0, ::2] = 1.0                          # two clusters of identical points
+    idx_ref, d_ref = O.knn_exact(x, k, return_dist=True)
+    (ia, da), (ib, db) = _both(x.cuda(), k)
+    assert torch.equal(ib.cpu(), idx_ref), "tc differs from the oracle"
+    assert torch.equal(ia, ib) and torch.equal(da, db)
+    assert torch.equal(db.cpu(), d_ref)
+
+
+@pytest.mark.parametrize("C,N,scale,offset", [(9, 2048, 1.0, 0.0), (64, 2048, 1.0, 0.0), (64, 1024, 37.0, 0.0),
+                                              (33, 512, 1e-3, 0.0), (64, 2048, 1.0, 5.0), (9, 1024, 0.05, 3.0)])
+def test_filter_error_is_inside_the_margin(C, N, scale, offset):
+    """The proof of exactness in knn_tc.cu needs |v(i,j) - D(i,j)| <= margin / 2 for the filter value v, i.e. (in units of
+    d = 2 D + const_i)  |2 v(i,j) - d(i,j) - const_i| <= margin_i.  Measure it: it must stay below HALF of that."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(C + N)
+    x = (torch.randn(1, C, N, generator=g) * scale + offset).cuda()
+    idx, filt, flags = ops.knn_tc_diag(x, 20)
+    torch.cuda.synchronize()
+    xd = x[0].double()
+    xx = (xd * xd).sum(0)
+    d_true = 2.0 * (xd.t() @ xd) - xx[:, None] - xx[None, :]            # real-arithmetic d(i, j)
+    resid = 2.0 * filt[0, :, :N].double() - d_true                       # = |x~_i|^2 + error
+    err = (resid - resid.median(dim=1, keepdim=True).values).abs()
+    xc = xd - xd.mean(dim=1, keepdim=True)
+    cc = (xc * xc).sum(0)
+    margin = 2.0 ** -14 * (cc + cc.max()) + (C + 4) * 2.0 ** -24 * (xx + xx.max())
+    ratio = float((err / margin[:, None]).max())
+    print(f"C={C} N={N} scale={scale} offset={offset}: max filter error / margin = {ratio:.4f}, "
+          f"repaired tiles {int(flags.sum())}")
+    assert ratio < 0.5, "the filter's error is too close to the margin the exactness proof assumes"
+    assert int(flags.sum()) == 0, "random data must not need the repair pass"
+    assert torch.equal(idx.cpu(), O.knn_exact(x.cpu(), 20))
+
+
+def test_tie_flood_rows_are_repaired_not_guessed():
+    ops = _ops()
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(1, 9, 1024, generator=g)
+    x[:, :, 100:400] = x[:, :, 100:101]             # 300 identical points: their rows cannot be decided by the filter
+    idx, filt, flags = ops.knn_tc_diag(x.cuda(), 20)
+    assert int(flags.sum()) > 0
+    assert torch.equal(idx.cpu(), O.knn_exact(x, 20))
+
+
+def test_tc_rejects_what_it_does_not_build():
+    ops = _ops()
+    with pytest.raises(RuntimeError, match="k=21"):
+        ops.knn(torch.randn(1, 9, 128, device="cuda"), 21, impl="tc")
