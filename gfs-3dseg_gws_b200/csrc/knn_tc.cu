@@ -66,51 +66,35 @@ knn_center_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, fl
     }
 }
 
-// one thread per point
+// One CTA per 128 points.  The (C x 128) slab is staged in shared memory with coalesced loads; thread t then owns point t
+// for the two norm chains, and the operand tiles / the point-major copy are written with (row, 16-byte chunk) work items
+// so that consecutive threads write consecutive bytes.
+constexpr int KP_LD = 129;   // padded row of the staged slab
 __global__ void __launch_bounds__(128)
 knn_prep_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int Npad, int Cp16, int KB, int CPT,
                 const float* __restrict__ mu, uint8_t* __restrict__ ops, float* __restrict__ xp, float* __restrict__ nh,
                 float* __restrict__ sqnorm, int* __restrict__ m2) {
+    __shared__ float xs[64 * KP_LD];
+    __shared__ float mus[64];
     const int t = threadIdx.x, rt = blockIdx.x, b = blockIdx.y;
-    const int n = rt * 128 + t;
+    const int n0 = rt * 128, n = n0 + t;
     const bool valid = n < N;
-    const float* xb = x + (int64_t)b * bstride + n;
-    const float* mub = mu + b * 64;
-    uint8_t* tiles = ops + ((int64_t)b * (Npad / 128) + rt) * KB * 16384;
-    float* xrow = xp + ((int64_t)b * Npad + n) * CPT;
+    const float* xb = x + (int64_t)b * bstride;
+    if (t < 64) mus[t] = t < C ? mu[b * 64 + t] : 0.0f;
+    for (int c = 0; c < Cp16; ++c) xs[c * KP_LD + t] = (valid && c < C) ? __ldg(xb + (int64_t)c * N + n) : 0.0f;
+    __syncthreads();
+
     float xx = 0.0f, cc = 0.0f;
-    for (int c0 = 0; c0 < Cp16; c0 += 8) {
-        float xv[8], xc[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int c = c0 + e;
-            const bool on = valid && c < C;
-            xv[e] = on ? __ldg(xb + (int64_t)c * N) : 0.0f;
-            xc[e] = on ? xv[e] - mub[c] : 0.0f;
-            xx = fmaf(xv[e], xv[e], xx);          // same chain as sqnorm_kernel (zeros past C leave it unchanged)
-            cc = fmaf(xc[e], xc[e], cc);
-        }
-        uint32_t hp[4], lp[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(xc[2 * e]), h1 = __float2bfloat16_rn(xc[2 * e + 1]);
-            const float r0 = xc[2 * e] - __bfloat162float(h0), r1 = xc[2 * e + 1] - __bfloat162float(h1);
-            __nv_bfloat162 hh;
-            hh.x = h0;
-            hh.y = h1;
-            hp[e] = *reinterpret_cast<uint32_t*>(&hh);
-            lp[e] = pack_bf16x2(r0, r1);
-        }
-        const int ch = c0, cl = Cp16 + c0;
-        *reinterpret_cast<uint4*>(tiles + (ch >> 6) * 16384 + sw128(t, (ch & 63) >> 3)) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-        *reinterpret_cast<uint4*>(tiles + (cl >> 6) * 16384 + sw128(t, (cl & 63) >> 3)) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
-        *reinterpret_cast<float4*>(xrow + c0) = make_float4(xv[0], xv[1], xv[2], xv[3]);
-        *reinterpret_cast<float4*>(xrow + c0 + 4) = make_float4(xv[4], xv[5], xv[6], xv[7]);
+    for (int c = 0; c < C; ++c) {
+        const float v = xs[c * KP_LD + t];
+        const float u = v - mus[c];
+        xx = fmaf(v, v, xx);                 // same chain as sqnorm_kernel
+        cc = fmaf(u, u, cc);
     }
-    for (int c0 = Cp16; c0 < CPT; c0 += 4) *reinterpret_cast<float4*>(xrow + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!valid) cc = 0.0f;                   // padding rows: all-zero operands (their v - mu would not be zero)
     nh[(int64_t)b * Npad + n] = valid ? -0.5f * cc : -INFINITY;
     if (valid) sqnorm[(int64_t)b * N + n] = xx;
-    float mc = valid ? cc : 0.0f, mo = valid ? xx : 0.0f;
+    float mc = cc, mo = valid ? xx : 0.0f;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         mc = fmaxf(mc, __shfl_xor_sync(0xffffffffu, mc, o));
@@ -119,6 +103,42 @@ knn_prep_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int 
     if ((t & 31) == 0) {   // norms are >= 0: the int order is the float order
         atomicMax(m2 + 2 * b, __float_as_int(mc));
         atomicMax(m2 + 2 * b + 1, __float_as_int(mo));
+    }
+
+    // operand tiles: columns [h: 0..Cp16) [l: Cp16..2 Cp16), 8 columns per 16-byte chunk
+    uint8_t* tiles = ops + ((int64_t)b * (Npad / 128) + rt) * KB * 16384;
+    const int cpr = Cp16 >> 3;               // chunks per row and per part
+    for (int i = t; i < 128 * cpr; i += 128) {
+        const int r = i / cpr, q = i - r * cpr;
+        const bool on = n0 + r < N;
+        uint32_t hp[4], lp[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int c = q * 8 + 2 * e;
+            const float u0 = (on && c < C) ? xs[c * KP_LD + r] - mus[c] : 0.0f;
+            const float u1 = (on && c + 1 < C) ? xs[(c + 1) * KP_LD + r] - mus[c + 1] : 0.0f;
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(u0), h1 = __float2bfloat16_rn(u1);
+            __nv_bfloat162 hh;
+            hh.x = h0;
+            hh.y = h1;
+            hp[e] = *reinterpret_cast<uint32_t*>(&hh);
+            lp[e] = pack_bf16x2(u0 - __bfloat162float(h0), u1 - __bfloat162float(h1));
+        }
+        const int ch = q * 8, cl = Cp16 + q * 8;
+        *reinterpret_cast<uint4*>(tiles + (ch >> 6) * 16384 + sw128(r, (ch & 63) >> 3)) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+        *reinterpret_cast<uint4*>(tiles + (cl >> 6) * 16384 + sw128(r, (cl & 63) >> 3)) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+    }
+    // point-major fp32 copy of the ORIGINAL coordinates, rows of CPT floats (zero padded)
+    float* xrows = xp + ((int64_t)b * Npad + n0) * CPT;
+    const int fpr = CPT >> 2;
+    for (int i = t; i < 128 * fpr; i += 128) {
+        const int r = i / fpr, q = i - r * fpr;
+        float4 o;
+        o.x = 4 * q < Cp16 ? xs[(4 * q) * KP_LD + r] : 0.0f;
+        o.y = 4 * q + 1 < Cp16 ? xs[(4 * q + 1) * KP_LD + r] : 0.0f;
+        o.z = 4 * q + 2 < Cp16 ? xs[(4 * q + 2) * KP_LD + r] : 0.0f;
+        o.w = 4 * q + 3 < Cp16 ? xs[(4 * q + 3) * KP_LD + r] : 0.0f;
+        *reinterpret_cast<float4*>(xrows + (int64_t)r * CPT + q * 4) = o;
     }
 }
 
@@ -423,6 +443,7 @@ knn_finish_kernel(const float* __restrict__ xp, const float* __restrict__ sqnorm
     constexpr int RPI = 32 / LPR;          // rows per load instruction
     __shared__ __align__(16) float stg_all[KF_WARPS][32 * RS];
     __shared__ __align__(16) unsigned long long kbuf[KF_WARPS][64];
+    __shared__ __align__(16) float xi_all[KF_WARPS][CPT];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* stg = stg_all[warp];
     const int sub = lane % LPR, grp = lane / LPR;
@@ -447,16 +468,10 @@ knn_finish_kernel(const float* __restrict__ xp, const float* __restrict__ sqnorm
         if (ns == 0) continue;                       // flagged for the exact repair pass
         const int64_t b = g / N;
         const float* xpb = xp + b * Npad * CPT;
-        const float* xr = xpb + (g - b * N) * CPT;
-        float xi[CPT];
-#pragma unroll
-        for (int c = 0; c < CPT; c += 4) {
-            const float4 q = __ldg(reinterpret_cast<const float4*>(xr + c));
-            xi[c] = q.x;
-            xi[c + 1] = q.y;
-            xi[c + 2] = q.z;
-            xi[c + 3] = q.w;
-        }
+        // the query row itself goes to shared memory (broadcast reads in the chain): holding it in 64 registers per lane
+        // would halve the number of resident warps, and this kernel lives on latency hiding
+        float* xis = xi_all[warp];
+        if (lane < LPR) *reinterpret_cast<float4*>(xis + lane * 4) = __ldg(reinterpret_cast<const float4*>(xpb + (g - b * N) * CPT + lane * 4));
         const float xxi = __ldg(sqnorm + g);
         u64* keys = reinterpret_cast<u64*>(kbuf[warp]);
         for (int half = 0; half * 32 < ns; ++half) {   // a second round only for rows with more than 32 survivors
@@ -477,10 +492,11 @@ knn_finish_kernel(const float* __restrict__ xp, const float* __restrict__ sqnorm
 #pragma unroll
             for (int c = 0; c < CPT; c += 4) {
                 const float4 q = *reinterpret_cast<const float4*>(stg + lane * RS + c);
-                dot = fmaf(xi[c], q.x, dot);
-                dot = fmaf(xi[c + 1], q.y, dot);
-                dot = fmaf(xi[c + 2], q.z, dot);
-                dot = fmaf(xi[c + 3], q.w, dot);
+                const float4 a = *reinterpret_cast<const float4*>(xis + c);
+                dot = fmaf(a.x, q.x, dot);
+                dot = fmaf(a.y, q.y, dot);
+                dot = fmaf(a.z, q.z, dot);
+                dot = fmaf(a.w, q.w, dot);
             }
             const float d = fmaf(2.0f, dot, -xxi) - xxj;
             // 64-bit key: larger = nearer, equal distances -> smaller index first; 0 = empty slot (below every real key)
