@@ -14,10 +14,14 @@ __global__ void __launch_bounds__(128)
 cos_logits_kernel(const float* __restrict__ feat, int64_t bstride, int D, int N, const float* __restrict__ proto, int PB, int CLS,
                   const float* __restrict__ coding, int G, const int32_t* __restrict__ assignment, float th,
                   float* __restrict__ logits) {
-    extern __shared__ float sp[];   // [CLS][D]
+    extern __shared__ __align__(16) float sp[];   // [D][CP]: the CLS prototype values of one channel are CP/4 broadcast LDS.128
+    const int CP = (CLS + 3) & ~3;
     const int b = blockIdx.y;
     const float* pb = proto + (PB > 1 ? (int64_t)b * CLS * D : 0);
-    for (int i = threadIdx.x; i < CLS * D; i += blockDim.x) sp[i] = pb[i];
+    for (int i = threadIdx.x; i < CP * D; i += blockDim.x) {
+        const int d = i / CP, c = i - d * CP;
+        sp[i] = c < CLS ? pb[c * D + d] : 0.0f;
+    }
     __syncthreads();
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
@@ -34,9 +38,17 @@ cos_logits_kernel(const float* __restrict__ feat, int64_t bstride, int D, int N,
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             nrm = fmaf(v[u], v[u], nrm);
+            const float* row = sp + (d + u) * CP;
 #pragma unroll
-            for (int c = 0; c < CL_MAXC; ++c)
-                if (c < CLS) acc[c] = fmaf(v[u], sp[c * D + d + u], acc[c]);
+            for (int c = 0; c < CL_MAXC; c += 4) {
+                if (c < CP) {
+                    const float4 w = *reinterpret_cast<const float4*>(row + c);
+                    acc[c] = fmaf(v[u], w.x, acc[c]);
+                    acc[c + 1] = fmaf(v[u], w.y, acc[c + 1]);
+                    acc[c + 2] = fmaf(v[u], w.z, acc[c + 2]);
+                    acc[c + 3] = fmaf(v[u], w.w, acc[c + 3]);
+                }
+            }
         }
     }
     for (; d < D; ++d) {
@@ -44,7 +56,7 @@ cos_logits_kernel(const float* __restrict__ feat, int64_t bstride, int D, int N,
         nrm = fmaf(v, v, nrm);
 #pragma unroll
         for (int c = 0; c < CL_MAXC; ++c)
-            if (c < CLS) acc[c] = fmaf(v, sp[c * D + d], acc[c]);
+            if (c < CLS) acc[c] = fmaf(v, sp[d * CP + c], acc[c]);
     }
     const float inv = 10.0f / fmaxf(sqrtf(nrm), 1e-12f);
     int a = 0;
@@ -94,19 +106,20 @@ constexpr int SP_CH = 128;
 __global__ void __launch_bounds__(128)
 softmax_pool_kernel(const float* __restrict__ logits, const float* __restrict__ stats, const float* __restrict__ feat,
                     int64_t bstride, int CLS, int D, int N, int nchunks, float* __restrict__ partial) {
-    extern __shared__ float sm[];
-    float* P = sm;                       // [CLS][SP_CH]
-    float* F = sm + CLS * SP_CH;         // [D][SP_CH + 1]
+    extern __shared__ __align__(16) float sm[];
+    const int CP = (CLS + 3) & ~3;
+    float* P = sm;                       // [SP_CH][CP]: the CLS probabilities of one point are CP/4 broadcast LDS.128
+    float* F = sm + CP * SP_CH;          // [D][SP_CH + 1]
     const int b = blockIdx.y, ch = blockIdx.x, n0 = ch * SP_CH, tid = threadIdx.x;
-    for (int i = tid; i < CLS * SP_CH; i += 128) {
+    for (int i = tid; i < CP * SP_CH; i += 128) {
         const int c = i / SP_CH, j = i - c * SP_CH;
         const int n = n0 + j;
         float v = 0.0f;
-        if (n < N) {
+        if (n < N && c < CLS) {
             const float* st = stats + ((int64_t)b * CLS + c) * 2;
             v = expf(logits[((int64_t)b * CLS + c) * N + n] - st[0]) / st[1];
         }
-        P[i] = v;
+        P[j * CP + c] = v;
     }
     for (int i = tid; i < D * SP_CH; i += 128) {       // 4-byte cp.async: the whole tile is in flight at once
         const int d = i / SP_CH, j = i - d * SP_CH;
@@ -126,9 +139,17 @@ softmax_pool_kernel(const float* __restrict__ logits, const float* __restrict__ 
         const float* fr = F + d * (SP_CH + 1);
         for (int j = 0; j < SP_CH; ++j) {
             const float v = fr[j];
+            const float* pr = P + j * CP;
 #pragma unroll
-            for (int c = 0; c < CL_MAXC; ++c)
-                if (c < CLS) acc[c] = fmaf(P[c * SP_CH + j], v, acc[c]);
+            for (int c = 0; c < CL_MAXC; c += 4) {
+                if (c < CP) {
+                    const float4 w = *reinterpret_cast<const float4*>(pr + c);
+                    acc[c] = fmaf(w.x, v, acc[c]);
+                    acc[c + 1] = fmaf(w.y, v, acc[c + 1]);
+                    acc[c + 2] = fmaf(w.z, v, acc[c + 2]);
+                    acc[c + 3] = fmaf(w.w, v, acc[c + 3]);
+                }
+            }
         }
 #pragma unroll
         for (int c = 0; c < CL_MAXC; ++c)
@@ -157,7 +178,7 @@ extern "C" int gfs_cos_logits(const float* feat, int64_t feat_bstride, int B, in
     GFS_REQUIRE(CLS <= CL_MAXC, GFS_ERR_UNSUPPORTED, "gfs_cos_logits: CLS=%d > %d is not built", CLS, CL_MAXC);
     GFS_REQUIRE(PB == 1 || PB == B, GFS_ERR_BAD_ARG, "gfs_cos_logits: PB=%d must be 1 or B=%d", PB, B);
     GFS_REQUIRE(!coding || (assignment && G > 0), GFS_ERR_BAD_ARG, "gfs_cos_logits: coding needs assignment and G");
-    const size_t smem = (size_t)CLS * D * sizeof(float);
+    const size_t smem = (size_t)((CLS + 3) & ~3) * D * sizeof(float);
     GFS_REQUIRE(smem <= 48 * 1024, GFS_ERR_UNSUPPORTED, "gfs_cos_logits: CLS*D too large");
     cos_logits_kernel<<<dim3((N + 127) / 128, B), 128, smem, static_cast<cudaStream_t>(stream)>>>(
         feat, feat_bstride, D, N, proto_l2, PB, CLS, coding, G, assignment, th, logits);
@@ -171,7 +192,7 @@ extern "C" int gfs_softmax_pool(const float* logits, const float* feat, int64_t 
     GFS_REQUIRE(logits && feat && stats && partial && pred_proto, GFS_ERR_BAD_ARG, "gfs_softmax_pool: null pointer");
     GFS_REQUIRE(B > 0 && D > 0 && N > 0 && CLS > 0, GFS_ERR_BAD_ARG, "gfs_softmax_pool: non-positive size");
     GFS_REQUIRE(CLS <= CL_MAXC, GFS_ERR_UNSUPPORTED, "gfs_softmax_pool: CLS=%d > %d is not built", CLS, CL_MAXC);
-    const size_t smem = ((size_t)CLS * SP_CH + (size_t)D * (SP_CH + 1)) * sizeof(float);
+    const size_t smem = ((size_t)((CLS + 3) & ~3) * SP_CH + (size_t)D * (SP_CH + 1)) * sizeof(float);
     GFS_REQUIRE(smem <= 200 * 1024, GFS_ERR_UNSUPPORTED, "gfs_softmax_pool: D=%d too large", D);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int nchunks = (N + SP_CH - 1) / SP_CH;

@@ -16,11 +16,14 @@
 //      array in shared memory (predicated 8-byte stores; a few percent of the candidates).  When the cells fill up, the
 //      new ones are folded into a k-deep sorted register list (min/max chain), bound = the exact k-th best v so far,
 //      and the cells below (bound - margin) are dropped.
-//      margin = 2^-14 (|x~_i|^2 + max_j |x~_j|^2) + (C+4) 2^-24 (|x_i|^2 + max_j |x_j|^2) is twice a bound on the
-//      error of v against the pinned distance (in units of v = d/2 + const): bf16 split residual <= 3 * 2^-18 |x~_i||x~_j|,
-//      fp32 accumulation of <= 192 products in the tensor core (<= 1 ulp each), and the rounding of the pinned fp32
-//      chain itself on the original coordinates; tests/test_gpu_knn_tc.py measures the observed error against it.  Any
-//      candidate outside (k-th best v - margin) therefore cannot be among the exact top k.
+//      Error bound (per PAIR, so that one far-away point does not loosen the filter for every row):
+//        |v(i,j) - D(i,j)| <= a_i + a_j,   a = 2^-15 |x~|^2 + (C+4) 2^-25 |x|^2   per point
+//      (bf16 split residual <= 3 * 2^-18 |x~_i||x~_j|, <= 192 fp32 accumulations in the tensor core at <= 1 ulp each,
+//      |x~_i||x~_j| <= (|x~_i|^2+|x~_j|^2)/2, plus the rounding of the pinned fp32 chain on the original coordinates;
+//      tests/test_gpu_knn_tc.py measures the observed error against it).  The filter value carries +a_j, i.e. it is an
+//      UPPER bound u of D up to the row constant a_i; each cell also carries 2 a_j (bf16, rounded up) next to the column
+//      index, so the sorted list ranks the LOWER bounds w = u - 2 a_j.  The k-th largest lower bound minus 2 a_i cannot
+//      exceed the exact k-th best D, hence a candidate with u below it cannot be among the exact top k.
 //   3. knn_finish_kernel: the survivors (k plus a handful) get their EXACT pinned distance from the point-major fp32
 //      copy, one warp per row and one lane per survivor, are sorted by (d desc, index asc) and written out:
 //      bit-identical to knn.cu.  A row with more than 64 survivors (floods of exact ties) raises a flag for its 64-row
@@ -33,7 +36,7 @@ constexpr int KT_ROWS = 256;          // query rows per CTA
 constexpr int KT_COLS = 64;           // candidates per stage
 constexpr int KT_TST = 4;             // TMEM stages: 2 row tiles x 4 stages x 64 fp32 columns = 512 columns
 constexpr int KT_THREADS = 384;       // warp 0 TMA, warp 1 MMA, warps 2-3 idle, warps 4-11 selection
-constexpr int KT_P = 64;              // candidate cells (8 bytes) per row
+constexpr int KT_P = 63;              // candidate cells (8 bytes) per row (63: the control block has to fit next to them)
 constexpr int KT_SURV = 64;           // survivors per row handed to the finish kernel (one or two per lane)
 
 typedef unsigned long long u64;
@@ -73,7 +76,7 @@ constexpr int KP_LD = 129;   // padded row of the staged slab
 __global__ void __launch_bounds__(128)
 knn_prep_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int Npad, int Cp16, int KB, int CPT,
                 const float* __restrict__ mu, uint8_t* __restrict__ ops, float* __restrict__ xp, float* __restrict__ nh,
-                float* __restrict__ sqnorm, int* __restrict__ m2) {
+                uint32_t* __restrict__ tag, float* __restrict__ sqnorm) {
     __shared__ float xs[64 * KP_LD];
     __shared__ float mus[64];
     const int t = threadIdx.x, rt = blockIdx.x, b = blockIdx.y;
@@ -92,18 +95,15 @@ knn_prep_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int 
         cc = fmaf(u, u, cc);
     }
     if (!valid) cc = 0.0f;                   // padding rows: all-zero operands (their v - mu would not be zero)
-    nh[(int64_t)b * Npad + n] = valid ? -0.5f * cc : -INFINITY;
+    // a = the point's share of the pair error bound  |v(i,j) - D(i,j)| <= a_i + a_j  (see the header):
+    //   2^-15 |x~|^2  covers the bf16 split residual and the tensor core's fp32 accumulation (with |x~_i||x~_j| <= (|x~_i|^2+|x~_j|^2)/2),
+    //   (C+4) 2^-25 |x|^2  the rounding of the pinned fp32 chain on the original coordinates.
+    // The filter value carries +a_j (an upper bound of D), the tag carries 2 a_j rounded UP to bf16 (to get the lower bound back).
+    const float a = 0x1p-15f * cc + (float)(C + 4) * 0x1p-25f * xx;
+    const __nv_bfloat16 dl = __float2bfloat16_ru(2.0f * a);
+    nh[(int64_t)b * Npad + n] = valid ? -0.5f * cc + a : -INFINITY;
+    tag[(int64_t)b * Npad + n] = ((uint32_t)n << 16) | (uint32_t)__bfloat16_as_ushort(dl);
     if (valid) sqnorm[(int64_t)b * N + n] = xx;
-    float mc = cc, mo = valid ? xx : 0.0f;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        mc = fmaxf(mc, __shfl_xor_sync(0xffffffffu, mc, o));
-        mo = fmaxf(mo, __shfl_xor_sync(0xffffffffu, mo, o));
-    }
-    if ((t & 31) == 0) {   // norms are >= 0: the int order is the float order
-        atomicMax(m2 + 2 * b, __float_as_int(mc));
-        atomicMax(m2 + 2 * b + 1, __float_as_int(mo));
-    }
 
     // operand tiles: columns [h: 0..Cp16) [l: Cp16..2 Cp16), 8 columns per 16-byte chunk
     uint8_t* tiles = ops + ((int64_t)b * (Npad / 128) + rt) * KB * 16384;
@@ -146,7 +146,8 @@ knn_prep_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int 
 // main kernel
 // ---------------------------------------------------------------------------------------------------------------
 struct KtCtl {
-    float nh[KT_TST][KT_COLS];
+    float nh[KT_TST][KT_COLS];        // -|x~_j|^2/2 + a_j of the stage's candidates
+    uint32_t tag[KT_TST][KT_COLS];    // (j << 16) | bf16(2 a_j)
     uint64_t a_full, b_full[2], b_empty[2], d_full[KT_TST], d_empty[KT_TST];
     uint32_t tmem_base;
 };
@@ -196,8 +197,14 @@ template <int KL>
 __device__ __forceinline__ float kt_refresh(float (&L)[KL], KtCells& s, float margin, int k) {
     for (uint32_t a = s.mark; a < s.end; a += 2 * KT_STEP) {
         // two values per trip: the two dependent min/max chains interleave
-        const float v0 = __uint_as_float(lds64(a).x);
-        const float v1 = (a + KT_STEP < s.end) ? __uint_as_float(lds64(a + KT_STEP).x) : -INFINITY;
+        // cell = {u = upper bound of D(i,j) up to a row constant, (j << 16) | bf16(2 a_j)}; the list ranks the LOWER bounds
+        const uint2 e0 = lds64(a);
+        const float v0 = __uint_as_float(e0.x) - __uint_as_float(e0.y << 16);
+        float v1 = -INFINITY;
+        if (a + KT_STEP < s.end) {
+            const uint2 e1 = lds64(a + KT_STEP);
+            v1 = __uint_as_float(e1.x) - __uint_as_float(e1.y << 16);
+        }
         if (fmaxf(v0, v1) > L[KL - 1]) {
             kt_insert<KL>(L, v0);
             kt_insert<KL>(L, v1);
@@ -218,8 +225,8 @@ __device__ __forceinline__ float kt_refresh(float (&L)[KL], KtCells& s, float ma
 
 // Filter one chunk of 32 candidates (v = filter values, columns jb..jb+31) into the row's cells.
 template <int KL>
-__device__ __forceinline__ void kt_filter32(const float (&v)[32], uint32_t jb, float (&L)[KL], KtCells& cs, float& thr, bool& ovf,
-                                            float margin, int k) {
+__device__ __forceinline__ void kt_filter32(const float (&v)[32], const uint32_t* __restrict__ tags, float (&L)[KL], KtCells& cs,
+                                            float& thr, bool& ovf, float margin, int k) {
     const uint32_t trigger = cs.c0 + (KT_P - 8) * KT_STEP;   // end > trigger  <=>  fewer than 8 free cells
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -231,10 +238,12 @@ __device__ __forceinline__ void kt_filter32(const float (&v)[32], uint32_t jb, f
             }
             thr = ovf ? INFINITY : t;
         }
+        const uint4 t0 = *reinterpret_cast<const uint4*>(tags + g * 8), t1 = *reinterpret_cast<const uint4*>(tags + g * 8 + 4);
+        const uint32_t tg[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
 #pragma unroll
-        for (int c = g * 8; c < g * 8 + 8; ++c) {
-            if (v[c] >= thr) {
-                sts64(cs.end, __float_as_uint(v[c]), jb + c);
+        for (int c = 0; c < 8; ++c) {
+            if (v[g * 8 + c] >= thr) {
+                sts64(cs.end, __float_as_uint(v[g * 8 + c]), tg[c]);
                 cs.end += KT_STEP;
             }
         }
@@ -243,8 +252,8 @@ __device__ __forceinline__ void kt_filter32(const float (&v)[32], uint32_t jb, f
 
 template <int KL>
 __global__ void __launch_bounds__(KT_THREADS, 1)
-knn_tc_kernel(const uint8_t* __restrict__ ops, const float* __restrict__ nh, const float* __restrict__ sqnorm,
-              const int* __restrict__ m2, int* __restrict__ flags, int C, int N, int Npad, int Cp16, int KB, int k,
+knn_tc_kernel(const uint8_t* __restrict__ ops, const float* __restrict__ nh, const uint32_t* __restrict__ tag,
+              int* __restrict__ flags, int N, int Npad, int Cp16, int KB, int k,
               uint16_t* __restrict__ surv, int* __restrict__ surv_cnt, float* __restrict__ dbg) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -294,12 +303,13 @@ knn_tc_kernel(const uint8_t* __restrict__ ops, const float* __restrict__ nh, con
                 const int buf = st & 1, ts = st % KT_TST;
                 mbar_wait(&s.b_empty[buf], ((st >> 1) & 1) ^ 1);
                 mbar_wait(&s.d_empty[ts], ((st / KT_TST) & 1) ^ 1);   // the -|x_j|^2/2 slot is read by the selection warps
-                mbar_arrive_expect_tx(&s.b_full[buf], b_bytes + KT_COLS * 4u);
+                mbar_arrive_expect_tx(&s.b_full[buf], b_bytes + KT_COLS * 8u);
                 // candidates [st*64, st*64+64): half of row tile st/2, every k-block
                 const uint8_t* src = blk + (int64_t)(st >> 1) * a_bytes + (st & 1) * 8192;
                 for (int kb = 0; kb < KB; ++kb)
                     tma_load_1d(sB0 + buf * b_bytes + kb * 8192, src + (int64_t)kb * 16384, 8192u, &s.b_full[buf]);
                 tma_load_1d(s.nh[ts], nh + (int64_t)b * Npad + st * KT_COLS, KT_COLS * 4u, &s.b_full[buf]);
+                tma_load_1d(s.tag[ts], tag + (int64_t)b * Npad + st * KT_COLS, KT_COLS * 4u, &s.b_full[buf]);
             }
         }
         __syncwarp();
@@ -348,10 +358,8 @@ knn_tc_kernel(const uint8_t* __restrict__ ops, const float* __restrict__ nh, con
         KtCells cs;
         cs.c0 = smem_u32(cells) + row * 8;
         cs.end = cs.mark = cs.c0;
-        const float xxi = valid ? sqnorm[(int64_t)b * N + n] : 0.0f;
-        const float cci = valid ? -2.0f * nh[(int64_t)b * Npad + n] : 0.0f;     // centred squared norm
-        const float margin = 0x1p-14f * (cci + __int_as_float(m2[2 * b])) +
-                             (float)(C + 4) * 0x1p-24f * (xxi + __int_as_float(m2[2 * b + 1]));
+        // margin = 2 a_i (the row's own share of the pair error bound, taken from its tag: rounded up)
+        const float margin = valid ? __uint_as_float(tag[(int64_t)b * Npad + n] << 16) : 0.0f;
         bool ovf = !valid;          // "this row takes no more candidates": padding rows, and rows that overflowed
         float L[KL];
 #pragma unroll
@@ -393,7 +401,7 @@ knn_tc_kernel(const uint8_t* __restrict__ ops, const float* __restrict__ nh, con
 #pragma unroll
                     for (int c = 0; c < 32; ++c) o[c] = v[c];
                 }
-                kt_filter32<KL>(v, jb, L, cs, thr, ovf, margin, k);
+                kt_filter32<KL>(v, s.tag[ts] + half * 32, L, cs, thr, ovf, margin, k);
             }
             // hand the TMEM stage (and its -|x~_j|^2/2 slot) back.  Deliberately at the END of the stage: with four stages in
             // flight nothing waits for it, and the values of the second half are certainly in registers by now
@@ -413,7 +421,7 @@ knn_tc_kernel(const uint8_t* __restrict__ ops, const float* __restrict__ nh, con
             } else {
                 surv_cnt[g] = ns;
                 uint16_t* o = surv + g * KT_SURV;
-                for (int e = 0; e < ns; ++e) o[e] = (uint16_t)lds64(cs.c0 + e * KT_STEP).y;
+                for (int e = 0; e < ns; ++e) o[e] = (uint16_t)(lds64(cs.c0 + e * KT_STEP).y >> 16);
             }
         }
     } else {
@@ -521,7 +529,7 @@ knn_finish_kernel(const float* __restrict__ xp, const float* __restrict__ sqnorm
 
 struct KtPlan {
     int Npad, Cp16, KB, CPT;
-    size_t off_xp, off_nh, off_surv, off_cnt, off_mu, off_m2, off_flags, total, zero_bytes;
+    size_t off_xp, off_nh, off_tag, off_surv, off_cnt, off_mu, off_flags, total, zero_bytes;
 };
 static KtPlan kt_plan(int B, int C, int N) {
     KtPlan p;
@@ -534,6 +542,8 @@ static KtPlan kt_plan(int B, int C, int N) {
     o += (size_t)B * p.Npad * p.CPT * 4;
     p.off_nh = o;
     o += (size_t)B * p.Npad * 4;
+    p.off_tag = o;
+    o += (size_t)B * p.Npad * 4;
     p.off_surv = o;
     o += (size_t)B * N * KT_SURV * 2;
     p.off_cnt = o;
@@ -541,11 +551,9 @@ static KtPlan kt_plan(int B, int C, int N) {
     o = (o + 15) / 16 * 16;
     p.off_mu = o;
     o += (size_t)B * 64 * 4;
-    p.off_m2 = o;
-    o += (size_t)B * 8;
     p.off_flags = o;
     o += (size_t)B * ((N + 63) / 64) * 4;
-    p.zero_bytes = o - p.off_m2;
+    p.zero_bytes = o - p.off_flags;
     p.total = (o + 255) / 256 * 256;
     return p;
 }
@@ -561,8 +569,8 @@ static int kt_launch(const KtPlan& p, uint8_t* ws, const float* sqnorm, int B, i
     uint16_t* surv = reinterpret_cast<uint16_t*>(ws + p.off_surv);
     int* cnt = reinterpret_cast<int*>(ws + p.off_cnt);
     knn_tc_kernel<20><<<dim3(p.Npad / KT_ROWS, B), KT_THREADS, smem, st>>>(
-        ws, reinterpret_cast<const float*>(ws + p.off_nh), sqnorm, reinterpret_cast<const int*>(ws + p.off_m2),
-        reinterpret_cast<int*>(ws + p.off_flags), C, N, p.Npad, p.Cp16, p.KB, k, surv, cnt, dbg);
+        ws, reinterpret_cast<const float*>(ws + p.off_nh), reinterpret_cast<const uint32_t*>(ws + p.off_tag),
+        reinterpret_cast<int*>(ws + p.off_flags), N, p.Npad, p.Cp16, p.KB, k, surv, cnt, dbg);
     GFS_LAUNCH_OK("knn_tc_kernel");
     const int64_t rows = (int64_t)B * N;
     const int sms = sm_count();
@@ -605,14 +613,14 @@ static int kt_run(const float* x, int64_t x_bstride, int B, int C, int N, int k,
                 (long long)workspace_bytes);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     uint8_t* ws = static_cast<uint8_t*>(workspace);
-    GFS_CUDA_OK(cudaMemsetAsync(ws + p.off_m2, 0, p.zero_bytes, st));
+    GFS_CUDA_OK(cudaMemsetAsync(ws + p.off_flags, 0, p.zero_bytes, st));
     knn_center_kernel<<<dim3(B, (C + 7) / 8), 256, 0, st>>>(x, x_bstride, C, N, reinterpret_cast<float*>(ws + p.off_mu));
     GFS_LAUNCH_OK("knn_center_kernel");
     knn_prep_kernel<<<dim3(p.Npad / 128, B), 128, 0, st>>>(x, x_bstride, C, N, p.Npad, p.Cp16, p.KB, p.CPT,
                                                            reinterpret_cast<const float*>(ws + p.off_mu), ws,
                                                            reinterpret_cast<float*>(ws + p.off_xp),
-                                                           reinterpret_cast<float*>(ws + p.off_nh), sqnorm,
-                                                           reinterpret_cast<int*>(ws + p.off_m2));
+                                                           reinterpret_cast<float*>(ws + p.off_nh),
+                                                           reinterpret_cast<uint32_t*>(ws + p.off_tag), sqnorm);
     GFS_LAUNCH_OK("knn_prep_kernel");
     const int rc = kt_launch(p, ws, sqnorm, B, C, N, k, idx_out, dist_out, dbg, st);
     if (rc != GFS_OK) return rc;
