@@ -37,7 +37,7 @@ constexpr int KT_COLS = 64;           // candidates per stage
 constexpr int KT_TST = 4;             // TMEM stages: 2 row tiles x 4 stages x 64 fp32 columns = 512 columns
 constexpr int KT_THREADS = 384;       // warp 0 TMA, warp 1 MMA, warps 2-3 idle, warps 4-11 selection
 constexpr int KT_P = 63;              // candidate cells (8 bytes) per row (63: the control block has to fit next to them)
-constexpr int KT_SURV = 64;           // survivors per row handed to the finish kernel (one or two per lane)
+constexpr int KT_SURV = 256;          // survivors per row the finish kernel can take (32 per round, one per lane)
 
 typedef unsigned long long u64;
 
@@ -188,6 +188,8 @@ struct KtCells {
     uint32_t c0;      // address of the row's cell 0
     uint32_t end;     // next free cell
     uint32_t mark;    // cells [c0, mark) have already been folded into the sorted list
+    uint16_t* spill;  // the row's survivor list in global memory: cells that had to make room go there (column only)
+    int nspill;
 };
 constexpr uint32_t KT_STEP = KT_ROWS * 8;
 
@@ -232,8 +234,18 @@ __device__ __forceinline__ void kt_filter32(const float (&v)[32], const uint32_t
     for (int g = 0; g < 4; ++g) {
         if (__any_sync(0xffffffffu, cs.end > trigger)) {
             const float t = kt_refresh<KL>(L, cs, margin, k);
-            if (cs.end > trigger) {   // still no room: more than P-8 candidates inside the margin (tie flood)
-                ovf = true;
+            if (cs.end > trigger) {
+                // Still no room: more than P-8 candidates inside the error bound.  They are survivors whatever comes next
+                // (the bound only rises, but their filter values are not kept): move their columns to the row's list in
+                // global memory and go on with empty cells; the sorted list keeps their lower bounds.  A row that collects
+                // more than KT_SURV this way (a flood of exact ties) is left to the exact repair pass.
+                const int nc = (int)((cs.end - cs.c0) / KT_STEP);
+                if (!ovf && cs.nspill + nc + KT_P <= KT_SURV) {
+                    for (int e = 0; e < nc; ++e) cs.spill[cs.nspill + e] = (uint16_t)(lds64(cs.c0 + e * KT_STEP).y >> 16);
+                    cs.nspill += nc;
+                } else {
+                    ovf = true;
+                }
                 cs.end = cs.mark = cs.c0;
             }
             thr = ovf ? INFINITY : t;
@@ -358,6 +370,8 @@ knn_tc_kernel(const uint8_t* __restrict__ ops, const float* __restrict__ nh, con
         KtCells cs;
         cs.c0 = smem_u32(cells) + row * 8;
         cs.end = cs.mark = cs.c0;
+        cs.spill = surv + ((int64_t)b * N + (valid ? n : 0)) * KT_SURV;
+        cs.nspill = 0;
         // margin = 2 a_i (the row's own share of the pair error bound, taken from its tag: rounded up)
         const float margin = valid ? __uint_as_float(tag[(int64_t)b * Npad + n] << 16) : 0.0f;
         bool ovf = !valid;          // "this row takes no more candidates": padding rows, and rows that overflowed
@@ -419,8 +433,8 @@ knn_tc_kernel(const uint8_t* __restrict__ ops, const float* __restrict__ nh, con
                 surv_cnt[g] = 0;
                 flags[(int64_t)b * ((N + 63) / 64) + n / 64] = 1;
             } else {
-                surv_cnt[g] = ns;
-                uint16_t* o = surv + g * KT_SURV;
+                surv_cnt[g] = cs.nspill + ns;     // <= KT_SURV: a spill is only taken while nspill + cells + P fits
+                uint16_t* o = cs.spill + cs.nspill;
                 for (int e = 0; e < ns; ++e) o[e] = (uint16_t)(lds64(cs.c0 + e * KT_STEP).y >> 16);
             }
         }
@@ -450,7 +464,7 @@ knn_finish_kernel(const float* __restrict__ xp, const float* __restrict__ sqnorm
     constexpr int LPR = CPT / 4;           // lanes that fetch one row
     constexpr int RPI = 32 / LPR;          // rows per load instruction
     __shared__ __align__(16) float stg_all[KF_WARPS][32 * RS];
-    __shared__ __align__(16) unsigned long long kbuf[KF_WARPS][64];
+    __shared__ __align__(16) unsigned long long kbuf[KF_WARPS][KT_SURV];
     __shared__ __align__(16) float xi_all[KF_WARPS][CPT];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* stg = stg_all[warp];
@@ -482,9 +496,10 @@ knn_finish_kernel(const float* __restrict__ xp, const float* __restrict__ sqnorm
         if (lane < LPR) *reinterpret_cast<float4*>(xis + lane * 4) = __ldg(reinterpret_cast<const float4*>(xpb + (g - b * N) * CPT + lane * 4));
         const float xxi = __ldg(sqnorm + g);
         u64* keys = reinterpret_cast<u64*>(kbuf[warp]);
-        for (int half = 0; half * 32 < ns; ++half) {   // a second round only for rows with more than 32 survivors
+        for (int half = 0; half * 32 < ns; ++half) {   // further rounds only for rows with more than 32 survivors
             const int e = half * 32 + lane;
-            const uint32_t j = e < ns ? (half ? jh : jl) : 0u;   // entries past ns are uninitialised memory
+            uint32_t j = 0u;                             // entries past ns are uninitialised memory
+            if (e < ns) j = half == 0 ? jl : half == 1 ? jh : (uint32_t)__ldg(surv + g * KT_SURV + e);
             float4 t[32 / RPI];
 #pragma unroll
             for (int it = 0; it < 32 / RPI; ++it) {
@@ -512,7 +527,7 @@ knn_finish_kernel(const float* __restrict__ xp, const float* __restrict__ sqnorm
         }
         __syncwarp();
         // rank by counting (independent broadcast reads: no dependent shuffle network), keys are all distinct
-        const int nk = ns > 32 ? 64 : 32;
+        const int nk = (ns + 31) & ~31;
         for (int half = 0; half * 32 < ns; ++half) {
             const u64 mine = keys[half * 32 + lane];
             int rank = 0;

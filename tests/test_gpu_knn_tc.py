@@ -104,6 +104,20 @@ def test_tie_flood_rows_are_repaired_not_guessed():
     assert torch.equal(idx.cpu(), O.knn_exact(x, 20))
 
 
+def test_moderate_tie_floods_stay_on_the_fast_path():
+    """100 identical points: their rows keep ~100 survivors (spilled to the row's list in global memory, ranked in four
+    rounds by the finish kernel) - no repair pass, and still the oracle's answer (ties -> ascending index)"""
+    ops = _ops()
+    g = torch.Generator().manual_seed(4)
+    x = torch.rand(2, 64, 1024, generator=g)
+    x[:, :, 300:400] = x[:, :, 300:301]
+    idx, filt, flags = ops.knn_tc_diag(x.cuda(), 20)
+    assert int(flags.sum()) == 0
+    assert torch.equal(idx.cpu(), O.knn_exact(x, 20))
+    (ia, da), (ib, db) = _both(x.cuda(), 20)
+    assert torch.equal(ia, ib) and torch.equal(da, db)
+
+
 def test_tc_rejects_what_it_does_not_build():
     ops = _ops()
     with pytest.raises(RuntimeError, match="k=21"):
