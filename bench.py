@@ -261,9 +261,9 @@ def main():
     ec123_ms = knn_ms + ec_ms + prof.get("gfs_pointwise_f32", 0.0)
     ec123_bytes = 1316 * NPTS * B                                                        # compulsory bytes
     gbs = lambda byt, ms: (byt / 1e9) / (ms / 1e3) if ms > 0 else None
-    traffic = None          # dram__bytes_read+write of the three knn_kernel launches of a step, from the committed ncu capture
+    traffic = None          # dram__bytes_read+write of the kNN kernels of a step (3 x prep, filter, finish), from the committed ncu captures
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["knn_kernel_bytes_per_step_b32"] * B / 32.0
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["knn_bytes_per_step_b32"] * B / 32.0
     except Exception:
         pass
     roof = {"kernel": "kNN graph: knn_prep + knn_tc (tcgen05 filter) + knn_finish (gfs_knn_tc_f32, 3 calls/step)", "bound": "hbm", "achieved": gbs(knn_bytes, knn_ms), "peak": hbm_peak,
