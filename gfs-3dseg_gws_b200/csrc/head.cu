@@ -167,6 +167,51 @@ __global__ void softmax_pool_reduce_kernel(const float* __restrict__ partial, in
     out[i] = acc;
 }
 
+// model/capl.py:267-288 (post_refine_proto_v2, eqn. 6) + :117-120 (base classes keep the refined prototype plus the
+// generated one, novel classes take the generated one) + the L2 normalisation get_pred applies next, in ONE launch instead
+// of ~25 elementwise/reduction kernels on (B, CLS, D) tensors.  One warp per (block, class) row.
+//   w = max(<pp/|pp|, q/|q|>, 0);  r = w pp + (1 - w) q;  r = c < base ? r + g : r * 0 + g;  out = r / max(|r|, 1e-12)
+__global__ void __launch_bounds__(128)
+refine_proto_kernel(const float* __restrict__ pred_proto, const float* __restrict__ proto, const float* __restrict__ gened,
+                    int rows, int CLS, int D, int base_num, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int c = row % CLS;
+    const float* pp = pred_proto + (int64_t)row * D;
+    const float* q = proto + (int64_t)c * D;
+    const float* g = gened + (int64_t)c * D;
+    float spp = 0.f, sqq = 0.f, spq = 0.f;
+    for (int d = lane; d < D; d += 32) {
+        const float a = pp[d], b = q[d];
+        spp = fmaf(a, a, spp);
+        sqq = fmaf(b, b, sqq);
+        spq = fmaf(a, b, spq);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        spp += __shfl_xor_sync(0xffffffffu, spp, o);
+        sqq += __shfl_xor_sync(0xffffffffu, sqq, o);
+        spq += __shfl_xor_sync(0xffffffffu, spq, o);
+    }
+    float w = spq / (fmaxf(sqrtf(spp), 1e-12f) * fmaxf(sqrtf(sqq), 1e-12f));
+    w = w > 0.0f ? w : 0.0f;
+    float srr = 0.f;
+    for (int d = lane; d < D; d += 32) {
+        float r = w * pp[d] + (1.0f - w) * q[d];
+        r = c < base_num ? r + g[d] : r * 0.0f + g[d];
+        srr = fmaf(r, r, srr);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) srr += __shfl_xor_sync(0xffffffffu, srr, o);
+    const float inv = 1.0f / fmaxf(sqrtf(srr), 1e-12f);
+    for (int d = lane; d < D; d += 32) {
+        float r = w * pp[d] + (1.0f - w) * q[d];
+        r = c < base_num ? r + g[d] : r * 0.0f + g[d];
+        out[(int64_t)row * D + d] = r * inv;
+    }
+}
+
 }  // namespace gfs
 
 extern "C" int gfs_cos_logits(const float* feat, int64_t feat_bstride, int B, int D, int N, const float* proto_l2, int PB,
@@ -204,5 +249,18 @@ extern "C" int gfs_softmax_pool(const float* logits, const float* feat, int64_t 
     const int64_t total = (int64_t)B * CLS * D;
     softmax_pool_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(partial, nchunks, CLS * D, total, pred_proto);
     GFS_LAUNCH_OK("softmax_pool_reduce_kernel");
+    return GFS_OK;
+}
+
+extern "C" int gfs_refine_proto(const float* pred_proto, const float* proto, const float* gened_proto, int B, int CLS, int D,
+                                int base_num, float* refine_l2, void* stream) {
+    using namespace gfs;
+    GFS_REQUIRE(pred_proto && proto && gened_proto && refine_l2, GFS_ERR_BAD_ARG, "gfs_refine_proto: null pointer");
+    GFS_REQUIRE(B > 0 && CLS > 0 && D > 0 && base_num >= 0 && base_num <= CLS, GFS_ERR_BAD_ARG,
+                "gfs_refine_proto: bad sizes (B=%d CLS=%d D=%d base_num=%d)", B, CLS, D, base_num);
+    const int rows = B * CLS;
+    refine_proto_kernel<<<(rows + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(pred_proto, proto, gened_proto, rows, CLS, D,
+                                                                                      base_num, refine_l2);
+    GFS_LAUNCH_OK("refine_proto_kernel");
     return GFS_OK;
 }

@@ -214,6 +214,17 @@ def cos_logits(feat: torch.Tensor, proto_l2: torch.Tensor, coding: Optional[torc
     return out
 
 
+def refine_proto(pred_proto: torch.Tensor, proto: torch.Tensor, gened: torch.Tensor, base_num: int) -> torch.Tensor:
+    """(B, CLS, D) pooled prototypes, (CLS, D) main and generated prototypes -> L2-normalised refined prototypes (B, CLS, D)"""
+    _need_cuda(pred_proto, proto, gened)
+    B, CLS, D = pred_proto.shape
+    pp, q, g = pred_proto.contiguous().float(), proto.contiguous().float(), gened.contiguous().float()
+    assert q.shape == (CLS, D) and g.shape == (CLS, D)
+    out = torch.empty(B, CLS, D, dtype=torch.float32, device=pp.device)
+    _call("gfs_refine_proto", 1, _ptr(pp), _ptr(q), _ptr(g), B, CLS, D, int(base_num), _ptr(out), _stream())
+    return out
+
+
 def softmax_pool(logits: torch.Tensor, feat: torch.Tensor) -> torch.Tensor:
     """sum_n softmax_n(logits[b,c,:]) * feat[b,:,n] -> (B, CLS, D)"""
     _need_cuda(logits, feat)

@@ -200,12 +200,13 @@ class mpti_net_Point_GeoAsWeight_v2(nn.Module):
         if gened_proto.dim() == 3:
             gened_proto = gened_proto[0]
         with torch.no_grad():
-            refine_proto = self.post_refine_proto_v2(proto=self.main_proto, x=point_feat, point_feat=point_feat)
-            refine_proto[:, :base_num] = refine_proto[:, :base_num] + gened_proto[:base_num].unsqueeze(0)
-            refine_proto[:, base_num:] = refine_proto[:, base_num:] * 0 + gened_proto[base_num:].unsqueeze(0)
+            # post_refine_proto_v2 (eqn. 6), the base/novel prototype update of model/capl.py:117-120 and the normalisation
+            # of get_pred as one kernel (gfs_refine_proto) instead of ~25 small tensor ops on (B, classes, 128)
+            pred = self.get_pred(point_feat, self.main_proto)
+            pred_proto = ops.softmax_pool(pred, _cm(point_feat))
+            refine_l2 = ops.refine_proto(pred_proto, self.main_proto.detach(), gened_proto, base_num)
             gp_coding = torch.cat([base_class_coding, novel_class_coding], dim=0).float()
-            x_pre = ops.cos_logits(point_feat, F.normalize(refine_proto, p=2, dim=-1), gp_coding, assignment,
-                                   float(self.args.eval_weight))
+            x_pre = ops.cos_logits(point_feat, refine_l2, gp_coding, assignment, float(self.args.eval_weight))
             # diagnostics of model/capl.py:104-114: mean of coding[gt, assignment] over all / novel points
             if y is not None:
                 per_point = gp_coding[y.long(), assignment.long()]

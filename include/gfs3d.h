@@ -153,6 +153,12 @@ int gfs_cos_logits(const float* feat, int64_t feat_bstride, int B, int D, int N,
 int gfs_softmax_pool(const float* logits, const float* feat, int64_t feat_bstride, int B, int CLS, int D, int N,
                      float* stats, float* partial, float* pred_proto, void* stream);
 
+/* ---- query-adaptive prototype refinement, model/capl.py:267-288 (eqn. 6) + :117-120 + the normalisation of :293 -------
+ * w = max(cos(pred_proto, proto), 0);  r = w pred_proto + (1-w) proto;  base classes: r += gened; novel: r = r*0 + gened;
+ * refine_l2 = r / max(|r|, 1e-12).   pred_proto (B, CLS, D), proto and gened_proto (CLS, D), refine_l2 (B, CLS, D), fp32 */
+int gfs_refine_proto(const float* pred_proto, const float* proto, const float* gened_proto, int B, int CLS, int D,
+                     int base_num, float* refine_l2, void* stream);
+
 /* ---- k-means E/M step: sklearn KMeans.fit as called at get_basis.py:210 (_k_means_lloyd.pyx:196-218) ------------
  * labels[i] = argmin_c (|c|^2 - 2 x_i.c), fp32 pinned order, strict '<' (lowest index wins).
  *   xt        (D, n) fp32: the shard's points TRANSPOSED (channel-major, like every other fp32 operand here); n % 4 == 0

@@ -242,3 +242,25 @@ def test_attention_rejects_ragged_n():
     att = SelfAttention(256, 64).cuda().eval()
     with pytest.raises(RuntimeError, match="multiple of 128"):
         att(torch.randn(1, 256, 320, device="cuda"))
+
+
+def test_refine_proto_kernel_matches_the_reference_formula():
+    """gfs_refine_proto == post_refine_proto_v2's mix + the base/novel update of model/capl.py:117-120 + F.normalize"""
+    import torch.nn.functional as F
+    from gfs3d import ops
+    g = torch.Generator().manual_seed(17)
+    B, CLS, D, base = 5, 13, 128, 7
+    pp = torch.randn(B, CLS, D, generator=g)
+    pp[0, 3] = -pp[0, 3].abs()                      # a row with negative cosine: w clamps to 0
+    q = torch.randn(CLS, D, generator=g)
+    q[3] = q[3].abs()
+    gen = F.normalize(torch.randn(CLS, D, generator=g), dim=1)
+    w = (F.normalize(pp, 2, -1) * F.normalize(q, 2, -1).unsqueeze(0)).sum(-1, keepdim=True)
+    w = w * (w > 0).float()
+    r = w * pp + (1 - w) * q.unsqueeze(0)
+    r[:, :base] = r[:, :base] + gen[:base].unsqueeze(0)
+    r[:, base:] = r[:, base:] * 0 + gen[base:].unsqueeze(0)
+    ref = F.normalize(r, p=2, dim=-1)
+    got = ops.refine_proto(pp.cuda(), q.cuda(), gen.cuda(), base).cpu()
+    assert float((got - ref).abs().max()) <= 2e-6
+    assert float(w[0, 3]) == 0.0
