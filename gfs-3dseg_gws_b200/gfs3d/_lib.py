@@ -25,6 +25,7 @@ SIGNATURES = {
     "gfs_cos_logits": [_p, _i64, _i, _i, _i, _p, _i, _i, _p, _i, _p, _f, _p, _p],
     "gfs_softmax_pool": [_p, _p, _i64, _i, _i, _i, _i, _p, _p, _p, _p],
     "gfs_refine_proto": [_p, _p, _p, _i, _i, _i, _i, _p, _p],
+    "gfs_joint_histogram_i32": [_p, _p, _i64, _i, _i, _p, _p],
     "gfs_kmeans_assign": [_p, _i64, _i, _p, _i, _i, _p, _p, _p, _p],
     "gfs_kmeans_accumulate": [_p, _i64, _i, _p, _i, _p, _p, _p, _p, _p],
     # training path

@@ -225,6 +225,22 @@ def refine_proto(pred_proto: torch.Tensor, proto: torch.Tensor, gened: torch.Ten
     return out
 
 
+def joint_histogram(a: torch.Tensor, b: torch.Tensor, na: int, nb: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """counts[x, y] (+)= #{i: a[i] == x and b[i] == y} as int64 (na, nb); labels outside the ranges are skipped.
+    a, b: integer CUDA tensors of equal numel (converted to int32 if needed); `out` accumulates across calls."""
+    _need_cuda(a, b, out)
+    assert a.numel() == b.numel(), "label streams differ in length"
+    a32 = a.reshape(-1).to(torch.int32).contiguous()
+    b32 = b.reshape(-1).to(torch.int32).contiguous()
+    if out is None:
+        out = torch.zeros(na, nb, dtype=torch.int64, device=a.device)
+    assert out.dtype == torch.int64 and out.shape == (na, nb) and out.is_contiguous()
+    if a32.numel() == 0:
+        return out
+    _call("gfs_joint_histogram_i32", 1, _ptr(a32), _ptr(b32), a32.numel(), na, nb, _ptr(out), _stream())
+    return out
+
+
 def softmax_pool(logits: torch.Tensor, feat: torch.Tensor) -> torch.Tensor:
     """sum_n softmax_n(logits[b,c,:]) * feat[b,:,n] -> (B, CLS, D)"""
     _need_cuda(logits, feat)

@@ -159,6 +159,13 @@ int gfs_softmax_pool(const float* logits, const float* feat, int64_t feat_bstrid
 int gfs_refine_proto(const float* pred_proto, const float* proto, const float* gened_proto, int B, int CLS, int D,
                      int base_num, float* refine_l2, void* stream);
 
+/* ---- joint histogram of two label streams: the reduction behind runs/eval.py:31-48 (evaluate_metric_GFS: confusion
+ * matrix of gt x pred) and train.py:156-218 (collect_base_class_gp_coding_sum: label x geometric-word counts) ----------
+ * counts[x*NB + y] += #{i : a[i] == x, b[i] == y}; points outside [0,NA) x [0,NB) are skipped (255 = ignore).
+ * a, b: n int32 each, 16-byte aligned; counts: NA*NB uint64, ACCUMULATED into (the caller zeroes it); NA*NB <= 12288 */
+int gfs_joint_histogram_i32(const int32_t* a, const int32_t* b, int64_t n, int NA, int NB, unsigned long long* counts,
+                            void* stream);
+
 /* ---- k-means E/M step: sklearn KMeans.fit as called at get_basis.py:210 (_k_means_lloyd.pyx:196-218) ------------
  * labels[i] = argmin_c (|c|^2 - 2 x_i.c), fp32 pinned order, strict '<' (lowest index wins).
  *   xt        (D, n) fp32: the shard's points TRANSPOSED (channel-major, like every other fp32 operand here); n % 4 == 0

@@ -436,3 +436,96 @@ def randomize_bn_(sd: SD, seed: int = 5) -> SD:
             sd[p + "running_mean"] = 0.2 * torch.randn(n, generator=g)
             sd[p + "running_var"] = 0.5 + 1.5 * torch.rand(n, generator=g)
     return sd
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# N4 / N2 callers of the hot path: the mIoU metric and the geometric-word class codings
+# ---------------------------------------------------------------------------------------------------------------
+def evaluate_metric(pred_labels_list, gt_labels_list, test_classes, novel_classes, all_learning_order, scannet=False):
+    """runs/eval.py:10-108 (evaluate_metric_GFS) without the logger: the per-point Python loop of :31-48 restated with
+    numpy bincounts (integer counts, any order), the IoU arithmetic of :50-106 kept operation for operation.
+    -> (mean_iou, base_iou, novel_iou, hm, iou array)"""
+    num_class = len(test_classes)
+    order = np.asarray(all_learning_order, dtype=np.int64)
+    gt_classes = np.zeros(num_class, dtype=np.int64)
+    positive = np.zeros(num_class, dtype=np.int64)
+    true_pos = np.zeros(num_class, dtype=np.int64)
+    for pred, gt in zip(pred_labels_list, gt_labels_list):
+        p = np.asarray(pred).reshape(-1).astype(np.int64)
+        g = np.asarray(gt).reshape(-1).astype(np.int64)
+        gt_classes += np.bincount(order[g], minlength=num_class)                 # :40-41
+        positive += np.bincount(order[p], minlength=num_class)                   # :44-45
+        true_pos += np.bincount(order[g][g == p], minlength=num_class)           # :47
+    iou_list, base, novel = [], [], []
+    for c in range(num_class):
+        iou = int(true_pos[c]) / float(int(gt_classes[c]) + int(positive[c]) - int(true_pos[c]))
+        iou_list.append(iou)
+        if scannet and c == 0:
+            continue
+        (novel if c in novel_classes else base).append(iou)
+    if scannet:
+        mean_iou = np.array(iou_list[1:]).mean()
+        iou_list = iou_list[1:]
+    else:
+        mean_iou = np.array(iou_list).mean()
+    base_iou, novel_iou = np.array(base).mean(), np.array(novel).mean()
+    hm = 2 * base_iou * novel_iou / (base_iou + novel_iou)
+    return mean_iou, base_iou, novel_iou, hm, np.array(iou_list)
+
+
+def hard_coding(coding, energy):
+    """train.py:136-152 (post_processing_hard_coding): multi-hot of the most frequent words holding > energy of the mass.
+    Sequential fp32 running sum; equal frequencies lowest index first (torch.argsort leaves that open)."""
+    c = np.asarray(coding, dtype=np.float32).copy()
+    total = torch.sum(torch.from_numpy(c))
+    thr = float((energy * total).item())
+    acc = np.float32(0)
+    mask = np.zeros(c.shape, dtype=bool)
+    for i in np.argsort(-c, kind="stable"):
+        acc = np.float32(acc + c[i])
+        mask[i] = True
+        if float(acc) > thr:
+            break
+    return mask.astype(np.float32)
+
+
+def class_gw_codings(assignments, labels, train_class, G, energy):
+    """train.py:156-218 (collect_base_class_gp_coding_sum) given the per-block GW assignments instead of the model:
+    assignments / labels: lists of (n,) integer arrays, one per block (label 0 = background, cls + 1 = base class cls).
+    -> (base_class_gp_coding (num_base, G) float32 multi-hot, bg_class_coding (G,) float32, freq (num_base, G) float32 = the
+    word frequencies the multi-hot was cut from); at most 2000 blocks: no sampling"""
+    sums = {cls: np.zeros(G, dtype=np.float32) for cls in train_class}
+    counts = {cls: 0 for cls in train_class}
+    bg = []
+    for a, t in zip(assignments, labels):
+        a = np.asarray(a).astype(np.int64)
+        t = np.asarray(t).astype(np.int64)
+        for cls in np.unique(t):
+            m = t == cls
+            h = np.bincount(a[m], minlength=G).astype(np.float32)
+            if cls == 0:
+                bg.append(h / np.float32(m.sum()))                              # :187-190  mean of the one-hot columns
+            elif cls - 1 in sums:
+                sums[cls - 1] += h                                              # :196-199
+                counts[cls - 1] += int(m.sum())
+    freq = np.stack([sums[cls] / np.float32(counts[cls]) for cls in train_class], axis=0)
+    coding = np.stack([hard_coding(f, energy) for f in freq], axis=0)
+    assert len(bg) <= 2000, "the reference samples 2000 blocks at random beyond that (train.py:213-214)"
+    bg_coding = torch.mean(torch.from_numpy(np.stack(bg, axis=0)), dim=0).numpy()
+    return coding, bg_coding, freq
+
+
+def codings_equal_modulo_ties(freq, a, b):
+    """two multi-hot codings cut from the same frequencies agree if they keep the same NUMBER of words, every word more
+    frequent than the least frequent kept one, and none less frequent: `torch.argsort` orders equal frequencies arbitrarily
+    (train.py:143), so which of several equally frequent words crosses the energy threshold is not defined by the reference"""
+    freq, a, b = np.asarray(freq), np.asarray(a) > 0.5, np.asarray(b) > 0.5
+    if a.shape != b.shape or a.shape != freq.shape:
+        return False
+    for f, x, y in zip(freq.reshape(-1, freq.shape[-1]), a.reshape(-1, a.shape[-1]), b.reshape(-1, b.shape[-1])):
+        if x.sum() != y.sum():
+            return False
+        cut = f[x].min()
+        if not (np.array_equal(x[f > cut], y[f > cut]) and x[f > cut].all() and not x[f < cut].any() and not y[f < cut].any()):
+            return False
+    return True

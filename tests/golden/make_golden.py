@@ -189,11 +189,95 @@ def make_kmeans(name, n, D, K, seed):
          x_checksum=np.float64(X.astype(np.float64).sum()))
 
 
+def make_metric(name, seed, scannet):
+    """runs/eval.py of the reference (pure numpy/Python, importable as is) on random labels"""
+    from runs.eval import evaluate_metric_GFS  # noqa: E402  (reference)
+    rng = np.random.default_rng(seed)
+    ncls = 21 if scannet else 13
+    novel = [ncls - 3, ncls - 2, ncls - 1] if not scannet else [4, 9, 12, 16, 19, 20]
+    order = list(rng.permutation(ncls))                       # learning order -> class name index
+    gt = [rng.integers(0, ncls, size=(3, 96)) for _ in range(4)]
+    pred = [np.where(rng.random(g.shape) < 0.6, g, rng.integers(0, ncls, size=g.shape)) for g in gt]
+    log = SimpleNamespace(cprint=lambda *_: None)
+    mean_iou, base_iou, novel_iou, hm, ious = evaluate_metric_GFS(log, pred, gt, list(range(ncls)), novel, order, scannet=scannet)
+    got = O.evaluate_metric(pred, gt, list(range(ncls)), novel, order, scannet=scannet)
+    assert got[:4] == (mean_iou, base_iou, novel_iou, hm) and np.array_equal(got[4], ious), "oracle differs from runs/eval.py"
+    print(f"{name}: oracle == reference (mean {mean_iou:.6f} base {base_iou:.6f} novel {novel_iou:.6f} hm {hm:.6f})")
+    save(name, gt=np.stack(gt).astype(np.int16), pred=np.stack(pred).astype(np.int16), order=np.array(order, dtype=np.int16),
+         novel=np.array(novel, dtype=np.int16), scannet=np.int8(scannet), mean_iou=np.float64(mean_iou),
+         base_iou=np.float64(base_iou), novel_iou=np.float64(novel_iou), hm=np.float64(hm), ious=np.asarray(ious, dtype=np.float64))
+
+
+def _reference_train_functions(names):
+    """train.py cannot be imported here (h5py / transforms3d are missing): lift the named functions out of its source"""
+    import ast
+    import random
+    import torch.nn.functional as F
+    src = open(os.path.join(REF, "train.py")).read()
+    tree = ast.parse(src)
+    ns = {"torch": torch, "random": random, "F": F, "np": np}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in names:
+            exec(compile(ast.Module(body=[node], type_ignores=[]), "train.py", "exec"), ns)
+    return ns
+
+
+def make_coding(name, seed, G=150, num_base=7, blocks=12, n=256, energy=0.9):
+    """train.py:136-241: class codings from the one-hot GW features of a stub model (the model itself is pinned elsewhere)"""
+    ns = _reference_train_functions(["post_processing_hard_coding", "collect_base_class_gp_coding_sum",
+                                     "collect_new_clsss_gp_coding_sum"])
+    rng = np.random.default_rng(seed)
+    # geometric words correlate with the class, as in real data (a few dominant words per class + noise)
+    labels = [rng.integers(0, num_base + 1, size=n) for _ in range(blocks)]
+    assign = [np.where(rng.random(n) < 0.7, (t * 17 + rng.integers(0, 6, size=n)) % G, rng.integers(0, G, size=n)) for t in labels]
+    state = {"i": 0}
+
+    class Stub:
+        def eval(self):
+            return self
+
+        def getFeatures(self, inp):
+            a = torch.from_numpy(assign[state["i"]])
+            state["i"] += 1
+            return None, None, torch.nn.functional.one_hot(a, num_classes=G).transpose(1, 0).float().unsqueeze(0)
+
+    loader = [(torch.zeros(1, 9, n), torch.from_numpy(t).unsqueeze(0), None) for t in labels]
+    orig_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self            # the reference calls .cuda(): no driver in this container
+    try:
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()):
+            coding, bg = ns["collect_base_class_gp_coding_sum"](Stub(), loader, list(range(num_base)), energy)
+            novel_feats = {7: [torch.nn.functional.one_hot(torch.from_numpy(rng.integers(0, 40, size=64)), G).float()],
+                           9: [torch.nn.functional.one_hot(torch.from_numpy(rng.integers(30, 90, size=50)), G).float(),
+                               torch.nn.functional.one_hot(torch.from_numpy(rng.integers(30, 60, size=20)), G).float()]}
+            novel_in = {k: [t.clone() for t in v] for k, v in novel_feats.items()}
+            novel_coding = ns["collect_new_clsss_gp_coding_sum"](novel_feats, energy)
+    finally:
+        torch.Tensor.cuda = orig_cuda
+    oc, ob, freq = O.class_gw_codings(assign, labels, list(range(num_base)), G, energy)
+    assert O.codings_equal_modulo_ties(freq, oc, coding.numpy()), "oracle base-class coding differs from train.py"
+    print(f"{name}: oracle coding == reference modulo equal-frequency ties ({int((oc != coding.numpy()).sum())} tied words differ); "
+          f"bg coding max diff {float(np.abs(ob - bg.numpy()).max()):.2e}; "
+          f"words kept per class {coding.sum(1).int().tolist()}")
+    assert float(np.abs(ob - bg.numpy()).max()) <= 1e-7
+    save(name, assign=np.stack(assign).astype(np.int16), labels=np.stack(labels).astype(np.int16), G=np.int32(G),
+         num_base=np.int32(num_base), energy=np.float64(energy), coding=coding.numpy().astype(np.float32), freq=freq,
+         bg_coding=bg.numpy().astype(np.float32), novel_coding=novel_coding.numpy().astype(np.float32),
+         novel7=novel_in[7][0].argmax(1).numpy().astype(np.int16), novel9a=novel_in[9][0].argmax(1).numpy().astype(np.int16),
+         novel9b=novel_in[9][1].argmax(1).numpy().astype(np.int16))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="")
     a = ap.parse_args()
-    todo = a.only.split(",") if a.only else ["dgcnn", "gfs", "kmeans", "train"]
+    todo = a.only.split(",") if a.only else ["dgcnn", "gfs", "kmeans", "train", "callers"]
+    if "callers" in todo:
+        make_metric("metric_s3dis", seed=5, scannet=False)
+        make_metric("metric_scannet", seed=6, scannet=True)
+        make_coding("coding_s3dis", seed=7)
     if "dgcnn" in todo:
         sd = make_dgcnn("dgcnn_b2_n256", 2, 256, 20, seed=1234)
         save("dgcnn_weights", **np_sd(sd))

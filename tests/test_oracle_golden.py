@@ -101,3 +101,34 @@ def test_kmeans_assign_ties_lowest_index():
     X = np.zeros((4, 8), np.float32)
     C = np.zeros((5, 8), np.float32)      # all centroids identical -> label 0 (strict <, _k_means_lloyd.pyx:208)
     assert (O.kmeans_assign_exact(X, C) == 0).all()
+
+
+@pytest.mark.parametrize("name", ["metric_s3dis", "metric_scannet"])
+def test_metric_oracle_matches_reference_eval(golden, name):
+    """oracle.evaluate_metric == the reference's runs/eval.py (evaluate_metric_GFS) on the committed labels, float for float"""
+    g = golden(name)
+    ncls = len(g["order"])
+    got = O.evaluate_metric(list(g["pred"]), list(g["gt"]), list(range(ncls)), g["novel"].tolist(), g["order"].tolist(),
+                            scannet=bool(g["scannet"]))
+    assert got[0] == float(g["mean_iou"]) and got[1] == float(g["base_iou"])
+    assert got[2] == float(g["novel_iou"]) and got[3] == float(g["hm"])
+    assert np.array_equal(got[4], g["ious"])
+
+
+def test_class_coding_oracle_matches_reference_train_functions(golden):
+    """oracle.class_gw_codings == train.py:156-218 run on a stub model's one-hot GW features (modulo the order torch.argsort
+    gives to equally frequent words); the background coding is a plain mean and must agree to the last bit"""
+    g = golden("coding_s3dis")
+    nb, G = int(g["num_base"]), int(g["G"])
+    coding, bg, freq = O.class_gw_codings(list(g["assign"]), list(g["labels"]), list(range(nb)), G, float(g["energy"]))
+    assert np.array_equal(freq, g["freq"])
+    assert O.codings_equal_modulo_ties(freq, coding, g["coding"])
+    assert np.array_equal(bg, g["bg_coding"])
+    assert coding.sum(1).tolist() == g["coding"].sum(1).tolist()
+
+
+def test_hard_coding_keeps_the_smallest_prefix_above_the_energy():
+    c = np.array([0.05, 0.4, 0.05, 0.3, 0.2], dtype=np.float32)
+    assert O.hard_coding(c, 0.85).tolist() == [0, 1, 0, 1, 1]          # 0.4 + 0.3 = 0.7 <= 0.85 < 0.9
+    assert O.hard_coding(c, 0.95).tolist() == [1, 1, 0, 1, 1]          # equal frequencies: lowest index first
+    assert O.hard_coding(c, 1.0).tolist() == [1, 1, 1, 1, 1]           # never strictly above the total: keep everything
