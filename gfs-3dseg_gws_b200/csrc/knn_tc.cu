@@ -527,12 +527,19 @@ knn_finish_kernel(const float* __restrict__ xp, const float* __restrict__ sqnorm
         }
         __syncwarp();
         // rank by counting (independent broadcast reads: no dependent shuffle network), keys are all distinct
-        const int nk = (ns + 31) & ~31;
+        const int nk = (ns + 3) & ~3;                  // slots up to the next multiple of 32 hold 0 = never greater
         for (int half = 0; half * 32 < ns; ++half) {
             const u64 mine = keys[half * 32 + lane];
             int rank = 0;
-#pragma unroll 8
-            for (int f = 0; f < nk; ++f) rank += keys[f] > mine ? 1 : 0;
+#pragma unroll 2
+            for (int f = 0; f < nk; f += 4) {            // two 16-byte broadcast loads = four keys
+                const ulonglong2 q0 = *reinterpret_cast<const ulonglong2*>(keys + f);
+                const ulonglong2 q1 = *reinterpret_cast<const ulonglong2*>(keys + f + 2);
+                if (q0.x > mine) ++rank;
+                if (q0.y > mine) ++rank;
+                if (q1.x > mine) ++rank;
+                if (q1.y > mine) ++rank;
+            }
             if (mine != 0ull && rank < k) {
                 idx_out[g * k + rank] = (int32_t)(~(uint32_t)mine);
                 if (dist_out) dist_out[g * k + rank] = kt_ord_val((uint32_t)(mine >> 32));
