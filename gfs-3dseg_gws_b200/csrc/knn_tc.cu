@@ -4,8 +4,8 @@
 // ties -> ascending index) cannot be formed on tensor cores, but the tensor cores can tell cheaply which few candidates
 // can possibly be among the k best:
 //
-//   1. knn_center_kernel / knn_prep_kernel: distances do not change under a translation, so the filter works on
-//      coordinates centred on the block mean (small norms = small absolute error).  Every centred coordinate is split into
+//   1. knn_prep_kernel: distances do not change under a translation, so the filter works on coordinates shifted by a
+//      point inside the block's cloud (the mean of four spread-out points; small norms = small absolute error).  Every centred coordinate is split into
 //      two bf16 terms x~ = h + l (+ r, |r| <= 2^-18 |x~|) and stored as [h | l] in the UMMA K-major SWIZZLE_128B tile
 //      layout, next to -|x~_j|^2/2 per point and a point-major fp32 copy of the ORIGINAL coordinates.
 //   2. knn_tc_kernel: one CTA owns 256 query rows of one block (two UMMA M=128 tiles, operands resident in shared
@@ -52,38 +52,26 @@ __device__ __forceinline__ float kt_ord_val(uint32_t u) {
 // ---------------------------------------------------------------------------------------------------------------
 // operand preparation
 // ---------------------------------------------------------------------------------------------------------------
-// mu[b][c] = mean over the block's points (any shift would be valid; the mean makes the centred norms small)
-__global__ void __launch_bounds__(256)
-knn_center_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, float* __restrict__ mu) {
-    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int c = blockIdx.y * 8 + warp; c < C; c += 8 * gridDim.y) {
-        const float* p = x + (int64_t)b * bstride + (int64_t)c * N;
-        float acc = 0.0f;
-        for (int n = lane * 4; n < N; n += 128) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(p + n));
-            acc += (v.x + v.y) + (v.z + v.w);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) mu[b * 64 + c] = acc / (float)N;
-    }
-}
-
 // One CTA per 128 points.  The (C x 128) slab is staged in shared memory with coalesced loads; thread t then owns point t
 // for the two norm chains, and the operand tiles / the point-major copy are written with (row, 16-byte chunk) work items
 // so that consecutive threads write consecutive bytes.
 constexpr int KP_LD = 129;   // padded row of the staged slab
 __global__ void __launch_bounds__(128)
 knn_prep_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int Npad, int Cp16, int KB, int CPT,
-                const float* __restrict__ mu, uint8_t* __restrict__ ops, float* __restrict__ xp, float* __restrict__ nh,
-                uint32_t* __restrict__ tag, float* __restrict__ sqnorm) {
+                uint8_t* __restrict__ ops, float* __restrict__ xp, float* __restrict__ nh, uint32_t* __restrict__ tag,
+                float* __restrict__ sqnorm) {
     __shared__ float xs[64 * KP_LD];
     __shared__ float mus[64];
     const int t = threadIdx.x, rt = blockIdx.x, b = blockIdx.y;
     const int n0 = rt * 128, n = n0 + t;
     const bool valid = n < N;
     const float* xb = x + (int64_t)b * bstride;
-    if (t < 64) mus[t] = t < C ? mu[b * 64 + t] : 0.0f;
+    // the shift: any vector is valid (distances are translation invariant), it only has to be the SAME for every point of
+    // the block and close to the data.  The mean of four spread-out points costs four loads and no extra kernel.
+    if (t < 64) {
+        const float* p = xb + (int64_t)t * N;
+        mus[t] = t < C ? 0.25f * ((__ldg(p) + __ldg(p + N / 4)) + (__ldg(p + N / 2) + __ldg(p + 3 * (N / 4)))) : 0.0f;
+    }
     for (int c = 0; c < Cp16; ++c) xs[c * KP_LD + t] = (valid && c < C) ? __ldg(xb + (int64_t)c * N + n) : 0.0f;
     __syncthreads();
 
@@ -551,7 +539,7 @@ knn_finish_kernel(const float* __restrict__ xp, const float* __restrict__ sqnorm
 
 struct KtPlan {
     int Npad, Cp16, KB, CPT;
-    size_t off_xp, off_nh, off_tag, off_surv, off_cnt, off_mu, off_flags, total, zero_bytes;
+    size_t off_xp, off_nh, off_tag, off_surv, off_cnt, off_flags, total, zero_bytes;
 };
 static KtPlan kt_plan(int B, int C, int N) {
     KtPlan p;
@@ -571,8 +559,6 @@ static KtPlan kt_plan(int B, int C, int N) {
     p.off_cnt = o;
     o += (size_t)B * N * 4;
     o = (o + 15) / 16 * 16;
-    p.off_mu = o;
-    o += (size_t)B * 64 * 4;
     p.off_flags = o;
     o += (size_t)B * ((N + 63) / 64) * 4;
     p.zero_bytes = o - p.off_flags;
@@ -636,10 +622,7 @@ static int kt_run(const float* x, int64_t x_bstride, int B, int C, int N, int k,
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     uint8_t* ws = static_cast<uint8_t*>(workspace);
     GFS_CUDA_OK(cudaMemsetAsync(ws + p.off_flags, 0, p.zero_bytes, st));
-    knn_center_kernel<<<dim3(B, (C + 7) / 8), 256, 0, st>>>(x, x_bstride, C, N, reinterpret_cast<float*>(ws + p.off_mu));
-    GFS_LAUNCH_OK("knn_center_kernel");
-    knn_prep_kernel<<<dim3(p.Npad / 128, B), 128, 0, st>>>(x, x_bstride, C, N, p.Npad, p.Cp16, p.KB, p.CPT,
-                                                           reinterpret_cast<const float*>(ws + p.off_mu), ws,
+    knn_prep_kernel<<<dim3(p.Npad / 128, B), 128, 0, st>>>(x, x_bstride, C, N, p.Npad, p.Cp16, p.KB, p.CPT, ws,
                                                            reinterpret_cast<float*>(ws + p.off_xp),
                                                            reinterpret_cast<float*>(ws + p.off_nh),
                                                            reinterpret_cast<uint32_t*>(ws + p.off_tag), sqnorm);

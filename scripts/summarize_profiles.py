@@ -33,7 +33,7 @@ if os.path.exists(fn):
     hdr, data = rows[0], rows[1:]
     iN, iV = hdr.index("Kernel Name"), hdr.index("Metric Value")
     seq = [(r[iN], float(r[iV]) / 1000.0) for r in data]
-    starts = [i for i, (n, _) in enumerate(seq) if "sqnorm_kernel" in n or "knn_center_kernel" in n]
+    starts = [i for i, (n, _) in enumerate(seq) if "sqnorm_kernel" in n or "knn_prep_kernel" in n]
     if len(starts) >= 4:
         step = seq[starts[0]:starts[3]]
         tot = sum(t for _, t in step)

@@ -81,7 +81,9 @@ def test_filter_error_is_inside_the_margin(C, N, scale, offset):
     xd = x[0].double()
     xx = (xd * xd).sum(0)
     d_true = 2.0 * (xd.t() @ xd) - xx[:, None] - xx[None, :]            # real-arithmetic d(i, j)
-    xc = xd - xd.mean(dim=1, keepdim=True)
+    x32 = x[0]
+    mu = 0.25 * ((x32[:, 0] + x32[:, N // 4]) + (x32[:, N // 2] + x32[:, 3 * (N // 4)]))       # the kernel's shift
+    xc = xd - mu.double()[:, None]
     cc = (xc * xc).sum(0)
     a = 2.0 ** -15 * cc + (C + 4) * 2.0 ** -25 * xx
     resid = 2.0 * (filt[0, :, :N].double() - a[None, :]) - d_true        # = |x~_i|^2 + error
