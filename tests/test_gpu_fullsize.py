@@ -88,3 +88,28 @@ def test_config4_kmeans_shard_properties():
     # bit-exact against the pinned-order oracle on a slice
     ref = O.kmeans_assign_exact(X[:20000].cpu().numpy(), C.cpu().numpy())
     assert np.array_equal(labels[:20000].cpu().numpy(), ref)
+
+
+def test_both_knn_kernels_give_the_same_model_output_bit_for_bit(golden_sd):
+    """End to end at B = 16 x 2048: the tensor-core filtered kNN and the all-fp32 kNN produce the same three graphs on the
+    model's own (dynamic) feature spaces, hence bit-identical logits -- including the collapsed layer-3 features of an
+    untrained network, where many candidates sit inside the filter's error bound."""
+    from gfs3d import ops
+    from gfs3d.synthetic import synthetic_blocks
+    x = synthetic_blocks(16, 2048, seed=777).cuda()
+    g = torch.Generator().manual_seed(12)
+    gp = torch.randn(150, 192, generator=torch.Generator().manual_seed(7))
+    gened = torch.nn.functional.normalize(torch.randn(13, 128, generator=g), dim=1)
+    coding = (torch.rand(13, 150, generator=g) < 0.3).float()
+    m = _model(golden_sd, gp)
+    kw = dict(y=None, eval_model=True, gened_proto=gened.cuda(), base_class_coding=coding[:7].cuda(), novel_class_coding=coding[7:].cuda())
+    outs = {}
+    saved = ops.KNN_IMPL
+    try:
+        for impl in ("exact", "tc"):
+            ops.KNN_IMPL = impl
+            with torch.no_grad():
+                outs[impl] = m(x=x, **kw)[0].clone()
+    finally:
+        ops.KNN_IMPL = saved
+    assert torch.equal(outs["exact"], outs["tc"])
