@@ -143,6 +143,8 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="blocks per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--e2e-serial", action="store_true",
+                    help="end-to-end leg without prefetch: H2D, forward and D2H of a step strictly one after the other")
     a = ap.parse_args()
     if a.impl == "reference":
         return run_reference(a)
@@ -208,18 +210,43 @@ def main():
     dev_ms = sum(s.elapsed_time(e) for s, e in ev)
 
     # ---- timed region 2: end to end through the public module API with HOST buffers (H2D + forward + D2H labels) ----
-    xdev = torch.empty(B, 9, NPTS, device=dev)
+    # Default: the next batch's pinned host -> device copy is issued (on a copy stream, into a second device buffer) at the
+    # START of a step's timed interval, so it runs under that step's kernels; every interval contains exactly one H2D, one
+    # forward and one D2H of the labels.  --e2e-serial keeps the three strictly one after the other.
+    xdev = [torch.empty(B, 9, NPTS, device=dev) for _ in range(2)]
     ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream()
+    ready = [torch.cuda.Event(), torch.cuda.Event()]     # H2D into xdev[j] finished
+    freed = [torch.cuda.Event(), torch.cuda.Event()]     # the forward that read xdev[j] finished
     barrier()
+    if not a.e2e_serial:
+        with torch.cuda.stream(copy_stream):             # prologue: the first batch (its copy is the one step K-1 would prefetch)
+            xdev[0].copy_(host[0], non_blocking=True)
+            ready[0].record(copy_stream)
+        freed[1].record(main_stream)
     for i in range(a.steps):
         flush.zero_()
         ev2[i][0].record()
-        if graphed is not None:
-            lg = graphed(host[i % NROT])                     # pinned host -> static device input, then one graph launch
+        if a.e2e_serial:
+            if graphed is not None:
+                lg = graphed(host[i % NROT])                 # pinned host -> static device input, then one graph launch
+            else:
+                xdev[0].copy_(host[i % NROT], non_blocking=True)
+                lg = step(xdev[0])
         else:
-            xdev.copy_(host[i % NROT], non_blocking=True)
-            lg = step(xdev)
+            cur, nxt = i & 1, (i + 1) & 1
+            copy_stream.wait_event(ev2[i][0])                # the prefetch belongs to this interval
+            copy_stream.wait_event(freed[nxt])
+            with torch.cuda.stream(copy_stream):
+                xdev[nxt].copy_(host[(i + 1) % NROT], non_blocking=True)
+                ready[nxt].record(copy_stream)
+            main_stream.wait_event(ready[cur])
+            lg = graphed(xdev[cur]) if graphed is not None else step(xdev[cur])
+            freed[cur].record(main_stream)
         labels_host.copy_(lg.argmax(1).to(torch.int32), non_blocking=True)
+        if not a.e2e_serial:
+            main_stream.wait_event(ready[(i + 1) & 1])       # the interval ends after ITS host -> device copy as well
         ev2[i][1].record()
     barrier()
     e2e_ms = sum(s.elapsed_time(e) for s, e in ev2)
@@ -301,7 +328,10 @@ def main():
                        "launch": "eager" if graphed is None else "CUDA graph replay of the eager step (gfs3d/graph.py)",
                        "attention": "hand-written tcgen05 flash kernel (gfs_attention_fwd)"},
             "clocks": clk, "e2e": {"value": total_blocks / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                                   "ms_per_step": e2e_ms / a.steps},
+                                   "ms_per_step": e2e_ms / a.steps,
+                                   "mode": "serial: H2D, forward, D2H one after the other" if a.e2e_serial else
+                                           "prefetch: each step's timed interval holds one pinned H2D (the next batch, on a copy "
+                                           "stream, into a second device buffer), one forward and one D2H of the labels"},
             "gpu_launches": launches, "roofline": roof, "roofline_detail": extra, "cpu_baseline": cpu, "wall_s_timed_region": wall}
     print(json.dumps(line))
     if dist is not None:
