@@ -5,17 +5,18 @@
 // can possibly be among the k best:
 //
 //   1. knn_prep_kernel: distances do not change under a translation, so the filter works on coordinates shifted by a
-//      point inside the block's cloud (the mean of four spread-out points; small norms = small absolute error).  Every centred coordinate is split into
-//      two bf16 terms x~ = h + l (+ r, |r| <= 2^-18 |x~|) and stored as [h | l] in the UMMA K-major SWIZZLE_128B tile
-//      layout, next to -|x~_j|^2/2 per point and a point-major fp32 copy of the ORIGINAL coordinates.
+//      point inside the block's cloud (the mean of four spread-out points; small norms = small absolute error).  Every
+//      shifted coordinate is split into two bf16 terms x~ = h + l (+ r, |r| <= 2^-18 |x~|) and stored as [h | l] in the
+//      UMMA K-major SWIZZLE_128B tile layout, next to -|x~_j|^2/2 + a_j and a tag (j << 16 | bf16(2 a_j)) per point and
+//      a point-major fp32 copy of the ORIGINAL coordinates.
 //   2. knn_tc_kernel: one CTA owns 256 query rows of one block (two UMMA M=128 tiles, operands resident in shared
 //      memory) and streams the block's candidates in stages of 64 (TMA bulk copies, double buffered).  Per stage three
 //      tcgen05.mma chains  h_i.h_j + h_i.l_j + l_i.h_j  leave  D' ~= x~_i.x~_j  in TMEM (fp32, four stages in flight).
 //      Eight selection warps read TMEM with tcgen05.ld, ONE THREAD PER QUERY ROW (no shuffles, no cross-lane sorting):
-//      every candidate whose filter value v = D' - |x~_j|^2/2 reaches (bound - margin) is appended to the row's cell
-//      array in shared memory (predicated 8-byte stores; a few percent of the candidates).  When the cells fill up, the
-//      new ones are folded into a k-deep sorted register list (min/max chain), bound = the exact k-th best v so far,
-//      and the cells below (bound - margin) are dropped.
+//      every candidate whose filter value u = D' - |x~_j|^2/2 + a_j reaches the row's threshold is appended to the row's
+//      cell array in shared memory (predicated 8-byte stores of {u, tag}; a few percent of the candidates).  When the
+//      cells fill up, the new ones are folded into a k-deep sorted register list (min/max chains), the threshold becomes
+//      (k-th best lower bound so far) - 2 a_i, and the cells below it are dropped.
 //      Error bound (per PAIR, so that one far-away point does not loosen the filter for every row):
 //        |v(i,j) - D(i,j)| <= a_i + a_j,   a = 2^-15 |x~|^2 + (C+4) 2^-25 |x|^2   per point
 //      (bf16 split residual <= 3 * 2^-18 |x~_i||x~_j|, <= 192 fp32 accumulations in the tensor core at <= 1 ulp each,
@@ -25,9 +26,12 @@
 //      index, so the sorted list ranks the LOWER bounds w = u - 2 a_j.  The k-th largest lower bound minus 2 a_i cannot
 //      exceed the exact k-th best D, hence a candidate with u below it cannot be among the exact top k.
 //   3. knn_finish_kernel: the survivors (k plus a handful) get their EXACT pinned distance from the point-major fp32
-//      copy, one warp per row and one lane per survivor, are sorted by (d desc, index asc) and written out:
-//      bit-identical to knn.cu.  A row with more than 64 survivors (floods of exact ties) raises a flag for its 64-row
-//      tile and knn.cu's exact kernel redoes just those tiles inside the same call.
+//      copy, one warp per row and one lane per survivor (32 per round), are ranked by (d desc, index asc) and written out:
+//      bit-identical to knn.cu.
+//   Rows with more than P-8 candidates inside the bound (duplicated points; feature spaces so collapsed that the pinned
+//   chain's own rounding is of the order of the neighbour spacing) move their cells' columns to the row's survivor list in
+//   global memory and carry on; only a row that collects more than 256 survivors (a flood of exact ties) raises a flag
+//   for its 64-row tile, and knn.cu's exact kernel redoes just those tiles inside the same call.
 #include "common.cuh"
 
 namespace gfs {
