@@ -49,26 +49,34 @@ class KMeans:
             return rs
         return np.random.RandomState(rs)
 
-    def _seed_plusplus(self, Xc, rng):
-        """k-means++ (sklearn _kmeans.py:_kmeans_plusplus) with device-side distance / cumsum / searchsorted and the host
-        RNG consumed in sklearn's order.  (not a hand-written kernel yet.)"""
+    def _seed_plusplus(self, Xc, xt, rng):
+        """k-means++ (sklearn _kmeans.py:_kmeans_plusplus): per centre, 2 + ln K candidates drawn with probability
+        proportional to the current squared distance (host RNG consumed in sklearn's order, cumulative sum and search on the
+        device), all candidates scored in ONE pass over the resident channel-major copy (gfs_kmeans_pp_trial), the best kept."""
         n, D = Xc.shape
         K = self.n_clusters
         trials = 2 + int(np.log(K))
-        xsq = (Xc * Xc).sum(1)
-        centers = torch.empty(K, D, dtype=torch.float32, device=Xc.device)
+        if trials > 8:
+            raise NotImplementedError(f"k-means++ with {trials} local trials (n_clusters={K}) is not built")
+        dev = Xc.device
+        npad = xt.shape[1]
+        xsq = torch.zeros(npad, dtype=torch.float32, device=dev)
+        xsq[:n] = (Xc * Xc).sum(1)
+        centers = torch.empty(K, D, dtype=torch.float32, device=dev)
+        m = [torch.empty(8, npad, dtype=torch.float32, device=dev) for _ in range(2)]      # double buffer: closest lives in one
+        pots = torch.zeros(8, dtype=torch.float64, device=dev)
         first = int(rng.choice(n))
         centers[0] = Xc[first]
-        closest = (xsq - 2.0 * (Xc @ centers[0]) + xsq[first]).clamp_min_(0)
-        pot = closest.double().sum()
+        ops.kmeans_pp_trial(xt, n, xsq, centers[0:1].contiguous(), None, m[0], pots)
+        closest, pot, cur = m[0][0], pots[0].clone(), 0
         for c in range(1, K):
-            rv = torch.from_numpy(rng.uniform(size=trials)).to(Xc.device) * pot
-            cand = torch.searchsorted(torch.cumsum(closest.double(), 0), rv).clamp_max_(n - 1)
-            d = (xsq[None, :] - 2.0 * (Xc[cand] @ Xc.t()) + xsq[cand][:, None]).clamp_min_(0)
-            d = torch.minimum(d, closest[None, :])
-            pots = d.double().sum(1)
-            best = int(torch.argmin(pots))
-            pot, closest = pots[best], d[best]
+            rv = torch.from_numpy(rng.uniform(size=trials)).to(dev) * pot
+            cand = torch.searchsorted(torch.cumsum(closest[:n].double(), 0), rv).clamp_max_(n - 1)
+            pots.zero_()
+            ops.kmeans_pp_trial(xt, n, xsq, Xc[cand].contiguous(), closest, m[cur ^ 1], pots)
+            best = int(torch.argmin(pots[:trials]))
+            cur ^= 1
+            pot, closest = pots[best].clone(), m[cur][best]
             centers[c] = Xc[cand[best]]
         return centers
 
@@ -104,7 +112,7 @@ class KMeans:
             if self.shard and _dist().get_rank(self.process_group) != 0:
                 centers = torch.empty(K, D, dtype=torch.float32, device=dev)
             else:
-                centers = self._seed_plusplus(Xc, self._rng())      # multi-GPU: seeded from rank 0's shard, then broadcast
+                centers = self._seed_plusplus(Xc, xt, self._rng())  # multi-GPU: seeded from rank 0's shard, then broadcast
             if self.shard:
                 _dist().broadcast(centers, src=_dist().get_global_rank(self.process_group, 0) if self.process_group else 0,
                                   group=self.process_group)

@@ -256,6 +256,17 @@ def softmax_pool(logits: torch.Tensor, feat: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def kmeans_pp_trial(xt: torch.Tensor, n: int, xsq: torch.Tensor, cand: torch.Tensor, closest: Optional[torch.Tensor],
+                    m_out: torch.Tensor, pots: torch.Tensor):
+    """k-means++ step: xt (D, npad) channel-major, cand (T, D) -> m_out (T, npad) = min(d(x, cand_t), closest), pots (T) f64 (+)="""
+    _need_cuda(xt, xsq, cand, closest, m_out, pots)
+    D, npad = xt.shape
+    T = cand.shape[0]
+    assert xt.is_contiguous() and cand.is_contiguous() and cand.shape[1] == D and m_out.is_contiguous() and m_out.shape[1] == npad
+    assert m_out.shape[0] >= T and pots.dtype == torch.float64 and pots.numel() >= T and xsq.numel() >= n
+    _call("gfs_kmeans_pp_trial", 1, _ptr(xt), npad, n, D, _ptr(xsq), _ptr(cand), T, _ptr(closest), _ptr(m_out), _ptr(pots), _stream())
+
+
 def kmeans_assign(xt: torch.Tensor, centers_t: torch.Tensor, K: int, want_score: bool = False):
     """xt (D, n) fp32, centers_t (D, Kp) fp32 zero padded -> labels (n) int32"""
     _need_cuda(xt, centers_t)

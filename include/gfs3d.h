@@ -179,6 +179,13 @@ int gfs_kmeans_partials(void);
 int gfs_kmeans_accumulate(const float* X, int64_t n, int D, const int32_t* labels, int K,
                           float* partial, int32_t* pcount, double* sums, int64_t* counts, void* stream);
 
+/* ---- k-means++ seeding step (sklearn _kmeans.py:_kmeans_plusplus behind get_basis.py:210) ---------------
+ * For T <= 8 candidate centres:  m[t][i] = min(max(|x_i|^2 - 2 x_i.c_t + |c_t|^2, 0), closest[i]),  pots[t] += sum_i m[t][i]
+ *   xt (D, npad) channel-major fp32 (the E-step's copy), xsq (n) squared norms, cand (T, D) row-major, closest (n) or NULL
+ *   (= +inf: the first centre), m_out (T, npad) fp32, pots (T) fp64 ACCUMULATED into (the caller zeroes it)              */
+int gfs_kmeans_pp_trial(const float* xt, int64_t npad, int64_t n, int D, const float* xsq, const float* cand, int T,
+                        const float* closest, float* m_out, double* pots, void* stream);
+
 /* =====================================================================================================================
  * TRAINING path (model.train(), train.py:614-631).  fp32 end to end, activations channel-major (C, M) with M = B*N points
  * or E = B*N*k edges (e = i*k + slot).  Round-1 version: correct first -- the per-edge tensors are materialised.

@@ -529,3 +529,28 @@ def codings_equal_modulo_ties(freq, a, b):
         if not (np.array_equal(x[f > cut], y[f > cut]) and x[f > cut].all() and not x[f < cut].any() and not y[f < cut].any()):
             return False
     return True
+
+
+def kmeans_plusplus_ref(X, n_clusters, rng):
+    """sklearn _kmeans.py:_kmeans_plusplus restated in float64 numpy with the random stream consumed the way
+    gfs3d.kmeans.KMeans consumes it (choice(n) for the first centre, then uniform(size=2+ln k) per centre; sklearn >= 1.3
+    draws the first centre through choice(n, p=...) and accumulates the distances in float32, so its picks are not
+    reproducible bit for bit by any parallel implementation: the seeding is pinned to THIS restatement).
+    -> (centres (k, D) float64, indices (k,))"""
+    X = np.asarray(X, dtype=np.float64)
+    n = X.shape[0]
+    trials = 2 + int(np.log(n_clusters))
+    xsq = (X * X).sum(1)
+    idx = np.empty(n_clusters, dtype=np.int64)
+    idx[0] = int(rng.choice(n))
+    closest = np.maximum(xsq - 2.0 * (X @ X[idx[0]]) + xsq[idx[0]], 0.0)
+    pot = closest.sum()
+    for c in range(1, n_clusters):
+        rv = rng.uniform(size=trials) * pot
+        cand = np.minimum(np.searchsorted(np.cumsum(closest), rv), n - 1)
+        d = np.maximum(xsq[None, :] - 2.0 * (X[cand] @ X.T) + xsq[cand][:, None], 0.0)
+        d = np.minimum(d, closest[None, :])
+        pots = d.sum(1)
+        best = int(np.argmin(pots))
+        pot, closest, idx[c] = pots[best], d[best], cand[best]
+    return X[idx], idx

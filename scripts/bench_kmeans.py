@@ -75,6 +75,17 @@ if rank == 0:
             "assign": {"ms": am, "fp32_tflops": 2.0 * n * D * 192 / am / 1e9, "algorithmic_gbs": (n * D * 4 + n * 4) / am / 1e6},
             "accumulate": {"ms": cm, "algorithmic_gbs": (n * D * 4 + n * 4) / cm / 1e6, "hbm_peak_gbs": peaks.get("hbm_gbs")},
             "allreduce_bytes": (K * D + K) * 8 if world > 1 else 0}
+    # k-means++ seeding: one pass over the resident channel-major copy per centre (gfs_kmeans_pp_trial)
+    from gfs3d.kmeans import KMeans as GKMeans
+    seeder = GKMeans(n_clusters=K, init="k-means++", random_state=0)
+    seeder._seed_plusplus(X[:40000], xt[:, :40000].contiguous(), np.random.RandomState(0))      # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    seeder._seed_plusplus(X, xt, np.random.RandomState(0))
+    torch.cuda.synchronize()
+    seed_s = time.perf_counter() - t0
+    line["seeding"] = {"seconds": seed_s, "ms_per_centre": 1e3 * seed_s / K, "trials_per_centre": 2 + int(np.log(K)),
+                       "algorithmic_gbs": K * n * D * 4 / 1e9 / seed_s, "hbm_peak_gbs": peaks.get("hbm_gbs")}
     if a.cpu_sample:
         from sklearn.cluster import KMeans
         rs = np.random.RandomState(0)
@@ -84,6 +95,10 @@ if rank == 0:
         t0 = time.perf_counter()
         km = KMeans(n_clusters=K, init=init, n_init=1, max_iter=5, tol=0).fit(Xc)
         dt = time.perf_counter() - t0
+        from sklearn.cluster import kmeans_plusplus
+        t0 = time.perf_counter()
+        kmeans_plusplus(Xc, K, random_state=np.random.RandomState(0))
+        line["seeding"]["cpu_sklearn_seconds_scaled_to_points_per_gpu"] = (time.perf_counter() - t0) * n / a.cpu_sample
         line["cpu_sklearn"] = {"ms_per_iter": 1e3 * dt / max(1, km.n_iter_), "points": a.cpu_sample, "cores": os.cpu_count(),
                                "ms_per_iter_scaled_to_points_per_gpu": 1e3 * dt / max(1, km.n_iter_) * n / a.cpu_sample}
     print(json.dumps(line))

@@ -105,3 +105,49 @@ def test_gw_basis_pipeline_end_to_end(golden_sd):
     assert np.array_equal(kmean_to_proto(X, km.labels_, 40), O.kmean_to_proto(X, km.labels_, 40))
     assert np.abs(svd_reconstruct(O.kmean_to_proto(X, km.labels_, 40)) - O.svd_reconstruct(O.kmean_to_proto(X, km.labels_, 40))).max() < 1e-5
     assert np.linalg.matrix_rank(basis.astype(np.float64), tol=1e-4) < 40          # rank-truncated at 95 % energy
+
+
+def test_kmeans_plusplus_kernel_picks_the_reference_centres():
+    """gfs_kmeans_pp_trial under KMeans._seed_plusplus vs the float64 restatement of sklearn's k-means++ on the same random
+    stream: same centres, and a potential as good as sklearn's own seeding"""
+    from gfs3d import ops
+    from gfs3d.kmeans import KMeans
+    rs = np.random.RandomState(5)
+    K, D, n = 24, 48, 20000
+    cent = rs.randn(K, D) * 3.0
+    X = (cent[rs.randint(0, K, n)] + rs.randn(n, D)).astype(np.float32)
+    ref_c, ref_idx = O.kmeans_plusplus_ref(X, K, np.random.RandomState(11))
+    km = KMeans(n_clusters=K, init="k-means++", random_state=11)
+    Xd = torch.from_numpy(X).cuda()
+    npad = (n + 3) // 4 * 4
+    xt = torch.zeros(D, npad, device="cuda")
+    xt[:, :n] = Xd.t()
+    got = km._seed_plusplus(Xd, xt, np.random.RandomState(11)).cpu().numpy()
+    same = (np.abs(got - ref_c) < 1e-6).all(axis=1)
+    assert same.all(), f"centres differ from the reference restatement at picks {np.nonzero(~same)[0][:5]}"
+    from sklearn.cluster import kmeans_plusplus
+    sk_c, _ = kmeans_plusplus(X, K, random_state=np.random.RandomState(11))
+    pot = lambda C: float(((X[:, None, :].astype(np.float64) - C[None].astype(np.float64)) ** 2).sum(-1).min(1).sum())
+    assert pot(got) <= 1.25 * pot(sk_c)
+
+
+def test_kmeans_pp_trial_matches_a_float64_evaluation():
+    from gfs3d import ops
+    g = torch.Generator().manual_seed(2)
+    n, D, T = 5003, 192, 7
+    X = torch.randn(n, D, generator=g)
+    npad = (n + 3) // 4 * 4
+    xt = torch.zeros(D, npad)
+    xt[:, :n] = X.t()
+    cand = X[torch.randint(0, n, (T,), generator=g)].contiguous()
+    closest = torch.rand(n, generator=g) * 400
+    xsq = (X * X).sum(1)
+    m = torch.empty(8, npad, device="cuda")
+    pots = torch.zeros(8, dtype=torch.float64, device="cuda")
+    ops.kmeans_pp_trial(xt.cuda(), n, xsq.cuda(), cand.cuda(), closest.cuda(), m, pots)
+    Xd, Cd = X.double(), cand.double()
+    d = ((Xd[None] - Cd[:, None]) ** 2).sum(-1)
+    ref = torch.minimum(d, closest.double()[None])
+    assert float((m[:T, :n].cpu().double() - ref).abs().max()) <= 2e-3          # fp32 |x|^2 - 2 x.c + |c|^2 at |x|^2 ~ 200
+    assert float(((pots[:T].cpu() - ref.sum(1)).abs() / ref.sum(1)).max()) <= 1e-5
+    assert float(pots[T:].abs().sum()) == 0.0
