@@ -90,3 +90,39 @@ def collect_new_clsss_gp_coding_sum(new_cls_gp_feat_dict, energy):
         tmp_feat = tmp_feat / torch.sum(tmp_feat)
         new_class_gp_coding.append(post_processing_hard_coding(tmp_feat, energy=energy))
     return torch.stack(new_class_gp_coding, dim=0)
+
+
+def get_new_proto_Geo2SemProto(val_supp_loader, model, base_num=16, novel_num=5, novel_class_list=None, train_loader_NoAug=None,
+                               base_class_coding=None, energy=None):
+    """train.py:240-305: prototypes of the novel classes (mean foreground feature of every support sample, averaged per
+    class, eqn. 1) next to the learnt base prototypes, all L2-normalised, plus the novel classes' GW codings.
+    val_supp_loader yields (input (b, d, n), target (b, n) binary foreground mask, cls_id (b,)) with ANY batch size (the
+    reference needs bs = 1 and calls Get_Fg_Feat per sample).  Per batch: one fused forward, a masked mean of the point
+    features and one joint histogram (sample x geometric word) of the foreground points.
+    -> (gened_proto (classes, 128) L2-normalised, novel_class_coding (n_novel, G))"""
+    model.eval()
+    G = model.gp.shape[0]
+    with torch.no_grad():
+        new_cls_feat_dict = {cls: [] for cls in novel_class_list}
+        new_cls_gp_hist = {cls: [] for cls in novel_class_list}
+        for input, target, cls_id in val_supp_loader:
+            input = input.cuda()
+            target = target.cuda()
+            point_feat, assignment, _ = model._features(input)               # (b, 128, n), (b, n)
+            b, n = target.shape
+            fg = (target == 1)
+            cnt = fg.sum(dim=1)
+            feat = (point_feat * fg.unsqueeze(1)).sum(dim=2) / cnt.unsqueeze(1)      # mean over the foreground points
+            blk = torch.arange(b, device=input.device, dtype=torch.int32).unsqueeze(1).expand(b, n)
+            hist = ops.joint_histogram(torch.where(fg, blk, torch.full_like(blk, -1)), assignment, b, G)
+            for i in range(b):
+                c = int(cls_id[i])
+                new_cls_feat_dict[c].append(feat[i:i + 1])
+                new_cls_gp_hist[c].append(hist[i:i + 1].float())                     # = sum of the one-hot GW rows
+        gened_proto = torch.zeros_like(model.main_proto, requires_grad=False)
+        gened_proto[:base_num, :] = model.main_proto[:base_num, :].detach().clone()
+        for cls in novel_class_list:
+            gened_proto[cls, :] = torch.mean(torch.cat(new_cls_feat_dict[cls], dim=0), dim=0, keepdim=False)
+        gened_proto = torch.nn.functional.normalize(gened_proto, dim=1, p=2)
+        novel_class_coding = collect_new_clsss_gp_coding_sum(new_cls_gp_hist, energy=energy)
+    return gened_proto, novel_class_coding

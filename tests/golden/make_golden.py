@@ -269,6 +269,52 @@ def make_coding(name, seed, G=150, num_base=7, blocks=12, n=256, energy=0.9):
          novel9b=novel_in[9][1].argmax(1).numpy().astype(np.int16))
 
 
+
+def make_support_proto(name, seed, wname="gfs_s3dis_weights", shots=2, n=128, energy=0.9):
+    """train.py:240-305 (get_new_proto_Geo2SemProto) on the real reference model (CPU), S3DIS-shaped: 7 base + 6 novel"""
+    ns = _reference_train_functions(["post_processing_hard_coding", "collect_new_clsss_gp_coding_sum", "get_new_proto_Geo2SemProto"])
+    classes, base_num, G = 13, 7, 150
+    torch.manual_seed(321)
+    gp = torch.randn(G, 192, generator=torch.Generator().manual_seed(7))
+    m = mpti_net_Point_GeoAsWeight_v2(classes=classes, criterion=torch.nn.CrossEntropyLoss(ignore_index=255), args=ref_args(),
+                                      base_num=base_num, gp=gp, energy=energy)
+    sd = dict(np.load(os.path.join(HERE, wname + ".npz")))
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    m.eval()
+    novel = list(range(base_num, classes))
+    rng = np.random.default_rng(seed)
+    xs = O.synthetic_blocks(len(novel) * shots, n, seed=seed)
+    masks = (torch.from_numpy(rng.random((len(novel) * shots, n))) < 0.4).long()
+    cls_ids = [c for c in novel for _ in range(shots)]
+    loader = [(xs[i:i + 1], masks[i:i + 1], torch.tensor([cls_ids[i]])) for i in range(len(cls_ids))]
+    ns["args"] = SimpleNamespace(total_classes=classes)
+    ns["logger"] = SimpleNamespace(cprint=lambda *_: None)
+    orig_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()):
+            gened, coding = ns["get_new_proto_Geo2SemProto"](loader, m, base_num=base_num, novel_num=len(novel),
+                                                             novel_class_list=novel, energy=energy)
+    finally:
+        torch.Tensor.cuda = orig_cuda
+    # frequencies the codings were cut from (for the tie-aware comparison)
+    with torch.no_grad():
+        freq = []
+        for c in novel:
+            h = torch.zeros(G)
+            for i, ci in enumerate(cls_ids):
+                if ci == c:
+                    _, gpf = m.Get_Fg_Feat(x=xs[i:i + 1], y=masks[i:i + 1])
+                    h += gpf.sum(0)
+            freq.append((h / h.sum()).numpy())
+    print(f"{name}: gened_proto {tuple(gened.shape)}, novel coding keeps {coding.sum(1).int().tolist()} words")
+    save(name, x=xs.numpy(), mask=masks.numpy().astype(np.int8), cls_id=np.array(cls_ids, dtype=np.int16), gened=gened.numpy(),
+         coding=coding.numpy().astype(np.float32), freq=np.stack(freq).astype(np.float32), energy=np.float64(energy),
+         base_num=np.int32(base_num))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="")
@@ -278,6 +324,7 @@ if __name__ == "__main__":
         make_metric("metric_s3dis", seed=5, scannet=False)
         make_metric("metric_scannet", seed=6, scannet=True)
         make_coding("coding_s3dis", seed=7)
+        make_support_proto("support_proto_s3dis", seed=31)
     if "dgcnn" in todo:
         sd = make_dgcnn("dgcnn_b2_n256", 2, 256, 20, seed=1234)
         save("dgcnn_weights", **np_sd(sd))

@@ -134,3 +134,28 @@ def test_novel_class_codings_equal_the_reference(golden):
     coding = collect_new_clsss_gp_coding_sum(feats, float(g["energy"]))
     assert coding.shape == (2, G)
     assert O.codings_equal_modulo_ties(freq.astype(np.float32), coding.cpu().numpy(), g["novel_coding"])
+
+
+@pytest.mark.parametrize("batch", [1, 4])
+def test_support_prototypes_equal_the_reference(golden, golden_sd, batch):
+    """gfs3d.coding.get_new_proto_Geo2SemProto (batched) vs train.py:240-305 run on the real reference model"""
+    from gfs3d.coding import get_new_proto_Geo2SemProto
+    from model.capl import mpti_net_Point_GeoAsWeight_v2
+    g = golden("support_proto_s3dis")
+    args = SimpleNamespace(edgeconv_widths=[[64, 64]] * 3, dgcnn_mlp_widths=[512, 256], pc_in_dim=9, dgcnn_k=20,
+                           base_widths=[128, 64], output_dim=64, eval_weight=1.2)
+    gp = torch.randn(150, 192, generator=torch.Generator().manual_seed(7))
+    m = mpti_net_Point_GeoAsWeight_v2(classes=13, criterion=torch.nn.CrossEntropyLoss(ignore_index=255), args=args, base_num=7,
+                                      gp=gp.cuda(), energy=float(g["energy"]))
+    m.load_state_dict(golden_sd("gfs_s3dis_weights"))
+    m = m.cuda().eval()
+    x, mask, cls_id = torch.from_numpy(g["x"]), torch.from_numpy(g["mask"].astype(np.int64)), torch.from_numpy(g["cls_id"].astype(np.int64))
+    loader = [(x[i:i + batch], mask[i:i + batch], cls_id[i:i + batch]) for i in range(0, x.shape[0], batch)]
+    novel = sorted(set(cls_id.tolist()))
+    gened, coding = get_new_proto_Geo2SemProto(loader, m, base_num=int(g["base_num"]), novel_num=len(novel), novel_class_list=novel,
+                                               energy=float(g["energy"]))
+    assert gened.shape == (13, 128) and coding.shape == (len(novel), 150)
+    ref = torch.from_numpy(g["gened"])
+    assert float((gened.cpu() - ref).abs().max()) <= 2e-2 * float(ref.abs().max()) + 1e-3      # bf16 feature path, unit-norm rows
+    assert torch.allclose(gened.cpu()[:7], ref[:7], atol=1e-6)                                  # base prototypes: copied + normalised
+    assert O.codings_equal_modulo_ties(g["freq"], coding.cpu().numpy(), g["coding"])
