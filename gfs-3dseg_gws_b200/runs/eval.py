@@ -51,27 +51,18 @@ def evaluate_metric_GFS(logger, pred_labels_list, gt_labels_list, test_classes, 
             positive_classes[idx] += col
             true_positive_classes[idx] += int(J[lab, lab])
 
-    iou_list, base_iou_list, novel_iou_list = [], [], []
-    for c in range(NUM_CLASS):
-        iou = true_positive_classes[c] / float(gt_classes[c] + positive_classes[c] - true_positive_classes[c])
+    # IoU per class name, then the three means: the reference's arithmetic (integer counts -> Python float division ->
+    # numpy mean over a list) in the reference's order, so the floats agree to the last bit
+    iou_list = [true_positive_classes[c] / float(gt_classes[c] + positive_classes[c] - true_positive_classes[c])
+                for c in range(NUM_CLASS)]
+    for c, iou in enumerate(iou_list):
         logger.cprint('----- [class %d]  IoU: %f -----' % (c, iou))
-        iou_list.append(iou)
-        if scannet and c == 0:
-            continue
-        if c in novel_classes:
-            novel_iou_list.append(iou)
-        else:
-            base_iou_list.append(iou)
-    if scannet:
-        mean_iou = np.array(iou_list[1:]).mean()
-        iou_list = iou_list[1:]                          # skip class 0
-    else:
-        mean_iou = np.array(iou_list).mean()
-    logger.cprint('mean-iou: {}'.format(mean_iou))
-    base_iou = np.array(base_iou_list).mean()
-    logger.cprint('base-iou: {}'.format(base_iou))
-    novel_iou = np.array(novel_iou_list).mean()
-    logger.cprint('novel-iou: {}'.format(novel_iou))
+    first = 1 if scannet else 0                          # ScanNet: class name 0 is skipped everywhere
+    kept = range(first, NUM_CLASS)
+    mean_iou = np.array([iou_list[c] for c in kept]).mean()
+    base_iou = np.array([iou_list[c] for c in kept if c not in novel_classes]).mean()
+    novel_iou = np.array([iou_list[c] for c in kept if c in novel_classes]).mean()
     hm = 2 * base_iou * novel_iou / (base_iou + novel_iou)
-    logger.cprint('hm-iou: {}'.format(hm))
-    return mean_iou, base_iou, novel_iou, hm, np.array(iou_list)
+    for label, value in (('mean-iou', mean_iou), ('base-iou', base_iou), ('novel-iou', novel_iou), ('hm-iou', hm)):
+        logger.cprint('{}: {}'.format(label, value))
+    return mean_iou, base_iou, novel_iou, hm, np.array(iou_list[first:])
