@@ -31,6 +31,29 @@ def test_tc_equals_exact_kernel_bit_for_bit(B, C, N, k):
     assert torch.equal(da, db), "distances differ"
 
 
+def test_tc_equals_exact_kernel_on_random_shapes():
+    """30 seeded random (B, C, N, k) with clustered / duplicated / anisotropic data: the two kernels must agree bit for bit"""
+    rng = torch.Generator().manual_seed(2024)
+    for trial in range(30):
+        B = int(torch.randint(1, 5, (1,), generator=rng))
+        C = int(torch.randint(1, 65, (1,), generator=rng))
+        N = 4 * int(torch.randint(6, 600, (1,), generator=rng))
+        k = int(torch.randint(1, min(20, N) + 1, (1,), generator=rng))
+        x = torch.randn(B, C, N, generator=rng)
+        kind = trial % 4
+        if kind == 1:                                   # clusters: many near neighbours per point
+            cent = torch.randn(B, C, 8, generator=rng) * 5
+            x = cent[:, :, torch.randint(0, 8, (N,), generator=rng)] + 0.05 * x
+        elif kind == 2:                                 # duplicates (sampling with replacement)
+            src = torch.randint(0, N, (N // 3,), generator=rng)
+            dst = torch.randint(0, N, (N // 3,), generator=rng)
+            x[:, :, dst] = x[:, :, src]
+        elif kind == 3:                                 # far from the origin, anisotropic
+            x = x * torch.logspace(-2, 1, C).view(1, C, 1) + 30.0
+        (ia, da), (ib, db) = _both(x.cuda().contiguous(), k)
+        assert torch.equal(ia, ib) and torch.equal(da, db), f"trial {trial}: B={B} C={C} N={N} k={k} kind={kind}"
+
+
 def test_tc_on_edgeconv_like_features_full_batch():
     """post-LeakyReLU, correlated 64-channel features (what the second and third kNN of the backbone see)"""
     g = torch.Generator().manual_seed(5)
