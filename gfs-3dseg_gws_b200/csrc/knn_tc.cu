@@ -388,10 +388,13 @@ knn_tc_kernel(const uint8_t* __restrict__ ops, const float* __restrict__ nh, con
 #pragma unroll
                 for (int c = 0; c < 32; c += 4) {
                     const float4 h4 = *reinterpret_cast<const float4*>(nhs + half * 32 + c);
-                    v[c] = __uint_as_float(r[c]) + h4.x;
-                    v[c + 1] = __uint_as_float(r[c + 1]) + h4.y;
-                    v[c + 2] = __uint_as_float(r[c + 2]) + h4.z;
-                    v[c + 3] = __uint_as_float(r[c + 3]) + h4.w;
+                    // packed adds (add.f32x2): two IEEE fp32 additions per issue slot
+                    const float2 s0 = __fadd2_rn(make_float2(__uint_as_float(r[c]), __uint_as_float(r[c + 1])), make_float2(h4.x, h4.y));
+                    const float2 s1 = __fadd2_rn(make_float2(__uint_as_float(r[c + 2]), __uint_as_float(r[c + 3])), make_float2(h4.z, h4.w));
+                    v[c] = s0.x;
+                    v[c + 1] = s0.y;
+                    v[c + 2] = s1.x;
+                    v[c + 3] = s1.y;
                 }
                 if (half == 0) {
                     tmem_ld32(tbase + ts * KT_COLS + 32, r);
