@@ -7,31 +7,37 @@
 //   1. knn_prep_kernel: distances do not change under a translation, so the filter works on coordinates shifted by a
 //      point inside the block's cloud (the mean of four spread-out points; small norms = small absolute error).  Every
 //      shifted coordinate is split into two bf16 terms x~ = h + l (+ r, |r| <= 2^-18 |x~|) and stored as [h | l] in the
-//      UMMA K-major SWIZZLE_128B tile layout, next to -|x~_j|^2/2 + a_j and a tag (j << 16 | bf16(2 a_j)) per point and
-//      a point-major fp32 copy of the ORIGINAL coordinates.
+//      UMMA K-major SWIZZLE_128B tile layout, next to the per-point filter constants
+//          nh_j = -|x~_j|^2/2 + a_j (rounded up),  nl_j = -|x~_j|^2/2 - a_j (rounded down),  tag_j = (j << 16) | bf16(2 a_j)
+//      and a point-major fp32 copy of the ORIGINAL coordinates.
 //   2. knn_tc_kernel: one CTA owns 256 query rows of one block (two UMMA M=128 tiles, operands resident in shared
-//      memory) and streams the block's candidates in stages of 64 (TMA bulk copies, double buffered).  Per stage three
-//      tcgen05.mma chains  h_i.h_j + h_i.l_j + l_i.h_j  leave  D' ~= x~_i.x~_j  in TMEM (fp32, four stages in flight).
-//      Eight selection warps read TMEM with tcgen05.ld, ONE THREAD PER QUERY ROW (no shuffles, no cross-lane sorting):
-//      every candidate whose filter value u = D' - |x~_j|^2/2 + a_j reaches the row's threshold is appended to the row's
-//      cell array in shared memory (predicated 8-byte stores of {u, tag}; a few percent of the candidates).  When the
-//      cells fill up, the new ones are folded into a k-deep sorted register list (min/max chains), the threshold becomes
-//      (k-th best lower bound so far) - 2 a_i, and the cells below it are dropped.
+//      memory) and streams the block's candidates TWICE in stages of 64 (TMA bulk copies, 4 stages in flight).  Per stage
+//      three tcgen05.mma chains  h_i.h_j + h_i.l_j + l_i.h_j  leave  D' ~= x~_i.x~_j  in TMEM (fp32, four stages).
+//      Sixteen selection warps read TMEM with tcgen05.ld, TWO THREADS PER QUERY ROW (one per 32-column half of a stage),
+//      no shuffles, no sorted list, no data-dependent control flow in the scan:
+//        pass A  every thread folds the LOWER bounds  w = D' + nl_j  of its candidates into NG running group maxima
+//                (group = column position; one FADD + one FMNMX per candidate).  The k-th largest of the row's 2 NG group
+//                maxima is a valid lower bound T of the k-th largest w of the row: k different candidates reach it.
+//                (sorted in registers by a bitonic network, the two halves meet through shared memory.)
+//        pass B  the candidates whose UPPER bound  u = D' + nh_j  reaches  T - 2 a_i  are appended to the row's survivor
+//                records {u, tag} in global memory with predicated stores: about 1.2 % of the candidates at NG = 32
+//                (N = 2048, k = 20: ~25 per row), independent of the data's order.
 //      Error bound (per PAIR, so that one far-away point does not loosen the filter for every row):
-//        |v(i,j) - D(i,j)| <= a_i + a_j,   a = 2^-15 |x~|^2 + (C+4) 2^-25 |x|^2   per point
-//      (bf16 split residual <= 3 * 2^-18 |x~_i||x~_j|, <= 192 fp32 accumulations in the tensor core at <= 1 ulp each,
-//      |x~_i||x~_j| <= (|x~_i|^2+|x~_j|^2)/2, plus the rounding of the pinned fp32 chain on the original coordinates;
-//      tests/test_gpu_knn_tc.py measures the observed error against it).  The filter value carries +a_j, i.e. it is an
-//      UPPER bound u of D up to the row constant a_i; each cell also carries 2 a_j (bf16, rounded up) next to the column
-//      index, so the sorted list ranks the LOWER bounds w = u - 2 a_j.  The k-th largest lower bound minus 2 a_i cannot
-//      exceed the exact k-th best D, hence a candidate with u below it cannot be among the exact top k.
-//   3. knn_finish_kernel: the survivors (k plus a handful) get their EXACT pinned distance from the point-major fp32
-//      copy, one warp per row and one lane per survivor (32 per round), are ranked by (d desc, index asc) and written out:
-//      bit-identical to knn.cu.
-//   Rows with more than P-8 candidates inside the bound (duplicated points; feature spaces so collapsed that the pinned
-//   chain's own rounding is of the order of the neighbour spacing) move their cells' columns to the row's survivor list in
-//   global memory and carry on; only a row that collects more than 256 survivors (a flood of exact ties) raises a flag
-//   for its 64-row tile, and knn.cu's exact kernel redoes just those tiles inside the same call.
+//        |v(i,j) - D(i,j)| <= a_i + a_j,   a = 2^-15 |x~|^2 + (2C+6) 2^-25 |x|^2   per point
+//      (bf16 split residual <= 3 * 2^-18 |x~_i||x~_j|, <= 192 fp32 accumulations in the tensor core, one fp32 addition,
+//      |x~_i||x~_j| <= (|x~_i|^2+|x~_j|^2)/2, plus the rounding of the pinned fp32 chain on the original coordinates:
+//      C roundings of the dot product, C of |x_j|^2, two of the final fmaf / subtraction;
+//      tests/test_gpu_knn_tc.py measures the observed error against it).  u is an UPPER bound of D up to the row constant
+//      a_i, w a LOWER bound.  The k-th largest lower bound minus 2 a_i cannot exceed the exact k-th best D, hence a
+//      candidate with u below T - 2 a_i cannot be among the exact top k.
+//   3. knn_finish_kernel: the survivors get their EXACT pinned distance from the point-major fp32 copy, one warp per row
+//      and one lane per survivor (32 per round), are ranked by (d desc, index asc) and written out: bit-identical to knn.cu.
+//      In SET mode (what the fused EdgeConv needs: a max over the neighbours does not care about their order) the
+//      survivors are first classified by their bounds -- certainly in, certainly out, undecided band -- and only the band
+//      gets the exact arithmetic; the k indices are then written in no particular order.
+//   A row-half that collects more than KT_CAP candidates inside the bound (floods of exact ties; feature spaces so
+//   collapsed that the pinned chain's own rounding exceeds the neighbour spacing) raises a flag for its 64-row tile, and
+//   knn.cu's exact kernel redoes just those tiles inside the same call.
 #include "common.cuh"
 
 namespace gfs {
@@ -39,9 +45,11 @@ namespace gfs {
 constexpr int KT_ROWS = 256;          // query rows per CTA
 constexpr int KT_COLS = 64;           // candidates per stage
 constexpr int KT_TST = 4;             // TMEM stages: 2 row tiles x 4 stages x 64 fp32 columns = 512 columns
-constexpr int KT_THREADS = 384;       // warp 0 TMA, warp 1 MMA, warps 2-3 idle, warps 4-11 selection
-constexpr int KT_P = 63;              // candidate cells (8 bytes) per row (63: the control block has to fit next to them)
-constexpr int KT_SURV = 256;          // survivors per row the finish kernel can take (32 per round, one per lane)
+constexpr int KT_BST = 4;             // shared-memory stages of the candidate operand
+constexpr int KT_SELW = 16;           // selection warps: (row tile, lane quarter, column half)
+constexpr int KT_THREADS = 64 + 32 * KT_SELW;   // warp 0 TMA, warp 1 MMA, warps 2-17 selection
+constexpr int KT_CAP = 128;           // survivor records per (row, column half)
+constexpr int KT_SURV = 2 * KT_CAP;   // survivors per row the finish kernel can take (32 per round, one per lane)
 
 typedef unsigned long long u64;
 
@@ -62,8 +70,8 @@ __device__ __forceinline__ float kt_ord_val(uint32_t u) {
 constexpr int KP_LD = 129;   // padded row of the staged slab
 __global__ void __launch_bounds__(128)
 knn_prep_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int Npad, int Cp16, int KB, int CPT,
-                uint8_t* __restrict__ ops, float* __restrict__ xp, float* __restrict__ nh, uint32_t* __restrict__ tag,
-                float* __restrict__ sqnorm) {
+                uint8_t* __restrict__ ops, float* __restrict__ xp, float* __restrict__ nh, float* __restrict__ nl,
+                uint32_t* __restrict__ tag, float* __restrict__ sqnorm) {
     __shared__ float xs[64 * KP_LD];
     __shared__ float mus[64];
     const int t = threadIdx.x, rt = blockIdx.x, b = blockIdx.y;
@@ -88,12 +96,13 @@ knn_prep_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int 
     }
     if (!valid) cc = 0.0f;                   // padding rows: all-zero operands (their v - mu would not be zero)
     // a = the point's share of the pair error bound  |v(i,j) - D(i,j)| <= a_i + a_j  (see the header):
-    //   2^-15 |x~|^2  covers the bf16 split residual and the tensor core's fp32 accumulation (with |x~_i||x~_j| <= (|x~_i|^2+|x~_j|^2)/2),
-    //   (C+4) 2^-25 |x|^2  the rounding of the pinned fp32 chain on the original coordinates.
-    // The filter value carries +a_j (an upper bound of D), the tag carries 2 a_j rounded UP to bf16 (to get the lower bound back).
-    const float a = 0x1p-15f * cc + (float)(C + 4) * 0x1p-25f * xx;
+    //   2^-15 |x~|^2  covers the bf16 split residual, the tensor core's fp32 accumulation and the fp32 addition of the constant
+    //   (2C+6) 2^-25 |x|^2  the rounding of the pinned fp32 chain on the original coordinates.
+    // nh carries +a_j (-> an upper bound of D), nl carries -a_j (-> a lower bound), the tag 2 a_j rounded UP to bf16.
+    const float a = __fmaf_ru(0x1p-15f, cc, __fmul_ru((float)(2 * C + 6) * 0x1p-25f, xx));
     const __nv_bfloat16 dl = __float2bfloat16_ru(2.0f * a);
-    nh[(int64_t)b * Npad + n] = valid ? -0.5f * cc + a : -INFINITY;
+    nh[(int64_t)b * Npad + n] = valid ? __fmaf_ru(-0.5f, cc, a) : -INFINITY;
+    nl[(int64_t)b * Npad + n] = valid ? __fmaf_rd(-0.5f, cc, -a) : -INFINITY;
     tag[(int64_t)b * Npad + n] = ((uint32_t)n << 16) | (uint32_t)__bfloat16_as_ushort(dl);
     if (valid) sqnorm[(int64_t)b * N + n] = xx;
 
@@ -138,136 +147,48 @@ knn_prep_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int 
 // main kernel
 // ---------------------------------------------------------------------------------------------------------------
 struct KtCtl {
-    float nh[KT_TST][KT_COLS];        // -|x~_j|^2/2 + a_j of the stage's candidates
-    uint32_t tag[KT_TST][KT_COLS];    // (j << 16) | bf16(2 a_j)
-    uint64_t a_full, b_full[2], b_empty[2], d_full[KT_TST], d_empty[KT_TST];
+    float cst[KT_TST][KT_COLS];       // the stage's per-candidate constant: nl_j in pass A, nh_j in pass B
+    uint32_t tag[KT_TST][KT_COLS];    // (j << 16) | bf16(2 a_j)   (pass B only)
+    uint64_t a_full, b_full[KT_BST], b_empty[KT_BST], d_full[KT_TST], d_empty[KT_TST];
+    float* surv_base;
     uint32_t tmem_base;
 };
 
-template <int KL>
-__device__ __forceinline__ void kt_insert(float (&L)[KL], float v) {
+// bitonic sorting network on registers, descending; every index is a compile-time constant after unrolling
+template <int NG>
+__device__ __forceinline__ void kt_sort_desc(float (&a)[NG]) {
 #pragma unroll
-    for (int i = 0; i < KL; ++i) {
-        const float hi = fmaxf(L[i], v);
-        v = fminf(L[i], v);
-        L[i] = hi;
-    }
-}
-template <int KL>
-__device__ __forceinline__ float kt_kth(const float (&L)[KL], int k) {   // L[k-1] without indexing registers dynamically
-    float r = L[0];
+    for (int k = 2; k <= NG; k <<= 1) {
 #pragma unroll
-    for (int i = 1; i < KL; ++i) r = (i == k - 1) ? L[i] : r;
-    return r;
-}
-__device__ __forceinline__ uint2 lds64(uint32_t a) {
-    uint2 r;
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];\n" : "=r"(r.x), "=r"(r.y) : "r"(a));
-    return r;
-}
-__device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) {
-    asm volatile("st.shared.v2.u32 [%0], {%1, %2};\n" ::"r"(a), "r"(x), "r"(y) : "memory");
-}
-
-__device__ __forceinline__ u64 lds_u64(uint32_t a) {
-    u64 r;
-    asm volatile("ld.shared.u64 %0, [%1];\n" : "=l"(r) : "r"(a));
-    return r;
-}
-
-// One selection thread's cells: cell e of row r is the 8 bytes at cells + (e * 256 + r) * 8 = {filter value bits, column}.
-struct KtCells {
-    uint32_t c0;      // address of the row's cell 0
-    uint32_t end;     // next free cell
-    uint32_t mark;    // cells [c0, mark) have already been folded into the sorted list
-    uint16_t* spill;  // the row's survivor list in global memory: cells that had to make room go there (column only)
-    int nspill;
-};
-constexpr uint32_t KT_STEP = KT_ROWS * 8;
-
-// Bring the row's sorted list L up to date with the cells appended since the last call, take the k-th best as the new
-// bound, drop every cell below (bound - margin).  Returns the new threshold.
-template <int KL>
-__device__ __forceinline__ float kt_refresh(float (&L)[KL], KtCells& s, float margin, int k) {
-    for (uint32_t a = s.mark; a < s.end; a += 2 * KT_STEP) {
-        // two values per trip: the two dependent min/max chains interleave
-        // cell = {u = upper bound of D(i,j) up to a row constant, (j << 16) | bf16(2 a_j)}; the list ranks the LOWER bounds
-        const uint2 e0 = lds64(a);
-        const float v0 = __uint_as_float(e0.x) - __uint_as_float(e0.y << 16);
-        float v1 = -INFINITY;
-        if (a + KT_STEP < s.end) {
-            const uint2 e1 = lds64(a + KT_STEP);
-            v1 = __uint_as_float(e1.x) - __uint_as_float(e1.y << 16);
-        }
-        if (fmaxf(v0, v1) > L[KL - 1]) {
-            kt_insert<KL>(L, v0);
-            kt_insert<KL>(L, v1);
-        }
-    }
-    const float thr = fmaxf(kt_kth<KL>(L, k) - margin, -3.402823466e38f);
-    uint32_t w = s.c0;
-    for (uint32_t a = s.c0; a < s.end; a += KT_STEP) {
-        const uint2 e = lds64(a);
-        if (__uint_as_float(e.x) >= thr) {
-            sts64(w, e.x, e.y);
-            w += KT_STEP;
-        }
-    }
-    s.end = s.mark = w;
-    return thr;
-}
-
-// Filter one chunk of 32 candidates (v = filter values, columns jb..jb+31) into the row's cells.
-template <int KL>
-__device__ __forceinline__ void kt_filter32(const float (&v)[32], const uint32_t* __restrict__ tags, float (&L)[KL], KtCells& cs,
-                                            float& thr, bool& ovf, float margin, int k) {
-    const uint32_t trigger = cs.c0 + (KT_P - 8) * KT_STEP;   // end > trigger  <=>  fewer than 8 free cells
+        for (int j = k >> 1; j > 0; j >>= 1) {
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        if (__any_sync(0xffffffffu, cs.end > trigger)) {
-            const float t = kt_refresh<KL>(L, cs, margin, k);
-            if (cs.end > trigger) {
-                // Still no room: more than P-8 candidates inside the error bound.  They are survivors whatever comes next
-                // (the bound only rises, but their filter values are not kept): move their columns to the row's list in
-                // global memory and go on with empty cells; the sorted list keeps their lower bounds.  A row that collects
-                // more than KT_SURV this way (a flood of exact ties) is left to the exact repair pass.
-                const int nc = (int)((cs.end - cs.c0) / KT_STEP);
-                if (!ovf && cs.nspill + nc + KT_P <= KT_SURV) {
-                    for (int e = 0; e < nc; ++e) cs.spill[cs.nspill + e] = (uint16_t)(lds64(cs.c0 + e * KT_STEP).y >> 16);
-                    cs.nspill += nc;
-                } else {
-                    ovf = true;
+            for (int i = 0; i < NG; ++i) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const float hi = fmaxf(a[i], a[l]), lo = fminf(a[i], a[l]);
+                    const bool desc = (i & k) == 0;
+                    a[i] = desc ? hi : lo;
+                    a[l] = desc ? lo : hi;
                 }
-                cs.end = cs.mark = cs.c0;
-            }
-            thr = ovf ? INFINITY : t;
-        }
-        const uint4 t0 = *reinterpret_cast<const uint4*>(tags + g * 8), t1 = *reinterpret_cast<const uint4*>(tags + g * 8 + 4);
-        const uint32_t tg[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            if (v[g * 8 + c] >= thr) {
-                sts64(cs.end, __float_as_uint(v[g * 8 + c]), tg[c]);
-                cs.end += KT_STEP;
             }
         }
     }
 }
 
-template <int KL>
+template <int NG, int KS>
 __global__ void __launch_bounds__(KT_THREADS, 1)
-knn_tc_kernel(const uint8_t* __restrict__ ops, const float* __restrict__ nh, const uint32_t* __restrict__ tag,
-              int* __restrict__ flags, int N, int Npad, int Cp16, int KB, int k,
-              uint16_t* __restrict__ surv, int* __restrict__ surv_cnt, float* __restrict__ dbg) {
+knn_tc_kernel(const uint8_t* __restrict__ ops, const float* __restrict__ nh, const float* __restrict__ nl,
+              const uint32_t* __restrict__ tag, int* __restrict__ flags, int N, int Npad, int Cp16, int KB, int k,
+              float* __restrict__ surv, int* __restrict__ surv_cnt, float* __restrict__ dbg) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    // [A: 2 row tiles x KB k-blocks x 16 KiB][B: 2 stages x KB x 8 KiB (64 candidate rows)][cells: P x 256 x 8 B][ctl]
+    // [A: 2 row tiles x KB k-blocks x 16 KiB][B: KT_BST stages x KB x 8 KiB (64 candidate rows)][xch: 2 x NG/4 x 256 float4][ctl]
     unsigned char* sA = base;
     const uint32_t a_bytes = (uint32_t)KB * 16384u;   // one row tile of the query operand
     const uint32_t b_bytes = (uint32_t)KB * 8192u;    // one candidate stage
     unsigned char* sB0 = sA + 2 * a_bytes;
-    unsigned char* cells = sB0 + 2 * b_bytes;
-    KtCtl& s = *reinterpret_cast<KtCtl*>(cells + KT_P * KT_ROWS * 8);
+    float4* xch = reinterpret_cast<float4*>(sB0 + KT_BST * b_bytes);
+    KtCtl& s = *reinterpret_cast<KtCtl*>(reinterpret_cast<unsigned char*>(xch) + 2 * (NG / 4) * KT_ROWS * 16);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.y, q0 = blockIdx.x * KT_ROWS;
@@ -277,15 +198,16 @@ knn_tc_kernel(const uint8_t* __restrict__ ops, const float* __restrict__ nh, con
     if (warp == 1) {
         if (lane == 0) {
             mbar_init(&s.a_full, 1);
-            for (int i = 0; i < 2; ++i) {
+            for (int i = 0; i < KT_BST; ++i) {
                 mbar_init(&s.b_full[i], 1);
                 mbar_init(&s.b_empty[i], 1);
             }
             for (int i = 0; i < KT_TST; ++i) {
                 mbar_init(&s.d_full[i], 1);
-                mbar_init(&s.d_empty[i], 8);
+                mbar_init(&s.d_empty[i], KT_SELW);
             }
             mbar_fence_init();
+            s.surv_base = surv;
         }
         __syncwarp();
         tmem_alloc(&s.tmem_base, 512);
@@ -294,147 +216,193 @@ knn_tc_kernel(const uint8_t* __restrict__ ops, const float* __restrict__ nh, con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s.tmem_base;
-    // the eight selection warps carry the register-resident lists and a prefetched TMEM chunk: (setmaxnreg: 4 warps x 40 + 8 warps x 224 registers per thread)
-    // (setmaxnreg at the top of each role branch below)
 
     if (warp == 0) {
         // =============================== TMA producer ===============================
-        reg_dealloc<40>();
         if (lane == 0) {
             mbar_arrive_expect_tx(&s.a_full, 2u * a_bytes);
             tma_load_1d(sA, blk + (int64_t)(q0 / 128) * a_bytes, 2u * a_bytes, &s.a_full);
-            for (int st = 0; st < nst; ++st) {
-                const int buf = st & 1, ts = st % KT_TST;
-                mbar_wait(&s.b_empty[buf], ((st >> 1) & 1) ^ 1);
-                mbar_wait(&s.d_empty[ts], ((st / KT_TST) & 1) ^ 1);   // the -|x_j|^2/2 slot is read by the selection warps
-                mbar_arrive_expect_tx(&s.b_full[buf], b_bytes + KT_COLS * 8u);
-                // candidates [st*64, st*64+64): half of row tile st/2, every k-block
-                const uint8_t* src = blk + (int64_t)(st >> 1) * a_bytes + (st & 1) * 8192;
+            for (int st = 0; st < 2 * nst; ++st) {
+                const bool passB = st >= nst;
+                const int cs = passB ? st - nst : st;                 // candidate stage
+                const int buf = st % KT_BST, ts = st % KT_TST;
+                mbar_wait(&s.b_empty[buf], ((st / KT_BST) & 1) ^ 1);
+                mbar_wait(&s.d_empty[ts], ((st / KT_TST) & 1) ^ 1);   // the constants' slot is read by the selection warps
+                mbar_arrive_expect_tx(&s.b_full[buf], b_bytes + KT_COLS * (passB ? 8u : 4u));
+                // candidates [cs*64, cs*64+64): half of row tile cs/2, every k-block
+                const uint8_t* src = blk + (int64_t)(cs >> 1) * a_bytes + (cs & 1) * 8192;
                 for (int kb = 0; kb < KB; ++kb)
                     tma_load_1d(sB0 + buf * b_bytes + kb * 8192, src + (int64_t)kb * 16384, 8192u, &s.b_full[buf]);
-                tma_load_1d(s.nh[ts], nh + (int64_t)b * Npad + st * KT_COLS, KT_COLS * 4u, &s.b_full[buf]);
-                tma_load_1d(s.tag[ts], tag + (int64_t)b * Npad + st * KT_COLS, KT_COLS * 4u, &s.b_full[buf]);
+                tma_load_1d(s.cst[ts], (passB ? nh : nl) + (int64_t)b * Npad + cs * KT_COLS, KT_COLS * 4u, &s.b_full[buf]);
+                if (passB) tma_load_1d(s.tag[ts], tag + (int64_t)b * Npad + cs * KT_COLS, KT_COLS * 4u, &s.b_full[buf]);
             }
         }
         __syncwarp();
     } else if (warp == 1) {
         // =============================== MMA issuer ===============================
-        reg_dealloc<40>();
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(128, KT_COLS);
-            const int ksteps = Cp16 >> 4;
-            mbar_wait(&s.a_full, 0);
-            for (int st = 0; st < nst; ++st) {
-                const int buf = st & 1, ts = st % KT_TST;
-                mbar_wait(&s.d_empty[ts], ((st / KT_TST) & 1) ^ 1);
-                mbar_wait(&s.b_full[buf], (st >> 1) & 1);
-                tc_fence_after();
-                const uint32_t bB = smem_u32(sB0 + buf * b_bytes);
-#pragma unroll 1
+        // The whole warp runs the loop (uniform control flow, uniform values: the descriptors live in uniform registers) and
+        // one elected lane issues; KS (16-column k-steps of one operand part) is a template parameter so that the 6 KS
+        // tcgen05.mma of a stage are straight-line code with immediate descriptor offsets.
+        const uint32_t idesc = umma_idesc_bf16(128, KT_COLS);
+        constexpr int CP16 = KS * 16;
+        mbar_wait(&s.a_full, 0);
+        const uint64_t a0 = umma_desc_sw128(smem_u32(sA));
+        const uint64_t b0 = umma_desc_sw128(smem_u32(sB0));
+        const uint32_t a_step = a_bytes >> 4, b_step = b_bytes >> 4;     // descriptor address units (16 bytes)
+        for (int st = 0; st < 2 * nst; ++st) {
+            const int buf = st % KT_BST, ts = st % KT_TST;
+            mbar_wait(&s.d_empty[ts], ((st / KT_TST) & 1) ^ 1);
+            mbar_wait(&s.b_full[buf], (st / KT_BST) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint64_t bB = b0 + (uint64_t)(buf * b_step);
+#pragma unroll
                 for (int mt = 0; mt < 2; ++mt) {
-                    const uint32_t aB = smem_u32(sA + mt * a_bytes);
+                    const uint64_t aB = a0 + (uint64_t)(mt * a_step);
                     const uint32_t d = tmem + mt * 256 + ts * KT_COLS;
-                    for (int ks = 0; ks < ksteps; ++ks) {
-                        const int ch = ks * 16, cl = Cp16 + ks * 16;
-                        const uint32_t ih = (uint32_t)(ch & 63) * 2u, il = (uint32_t)(cl & 63) * 2u;
-                        const uint64_t ah = umma_desc_sw128(aB + (uint32_t)(ch >> 6) * 16384u + ih);
-                        const uint64_t al = umma_desc_sw128(aB + (uint32_t)(cl >> 6) * 16384u + il);
-                        const uint64_t bh = umma_desc_sw128(bB + (uint32_t)(ch >> 6) * 8192u + ih);
-                        const uint64_t bl = umma_desc_sw128(bB + (uint32_t)(cl >> 6) * 8192u + il);
-                        umma_bf16(d, ah, bh, idesc, ks ? 1u : 0u);
-                        umma_bf16(d, ah, bl, idesc, 1u);
-                        umma_bf16(d, al, bh, idesc, 1u);
+#pragma unroll
+                    for (int ks = 0; ks < KS; ++ks) {
+                        const int ch = ks * 16, cl = CP16 + ks * 16;
+                        // offset of a 16-column slice inside the operand: k-block (16 KiB / 8 KiB apart) + 32 bytes per k-step
+                        const uint32_t oah = (uint32_t)((ch >> 6) * 16384 + (ch & 63) * 2) >> 4, oal = (uint32_t)((cl >> 6) * 16384 + (cl & 63) * 2) >> 4;
+                        const uint32_t obh = (uint32_t)((ch >> 6) * 8192 + (ch & 63) * 2) >> 4, obl = (uint32_t)((cl >> 6) * 8192 + (cl & 63) * 2) >> 4;
+                        umma_bf16(d, aB + oah, bB + obh, idesc, ks ? 1u : 0u);
+                        umma_bf16(d, aB + oah, bB + obl, idesc, 1u);
+                        umma_bf16(d, aB + oal, bB + obh, idesc, 1u);
                     }
                 }
                 umma_commit(&s.b_empty[buf]);
                 umma_commit(&s.d_full[ts]);
             }
+            __syncwarp();
         }
-        __syncwarp();
-    } else if (warp >= 4) {
-        // =============================== selection: one thread per query row ===============================
-        reg_alloc<224>();
-        const int mt = (warp - 4) >> 2, quarter = warp & 3;
+    } else {
+        // =============================== selection: two threads per query row ===============================
+        // A warp may only read the TMEM lanes 32 (warp % 4) .. +31.  Among the 16 warps every residue occurs four times:
+        // they take (row tile, column half) = (0,0) (1,0) (0,1) (1,1) in warp order.
+        const int quarter = warp & 3, slot = (warp - 2) >> 2;
+        const int mt = slot & 1, half = slot >> 1;
         const int row = mt * 128 + quarter * 32 + lane;
         const int n = q0 + row;
         const bool valid = n < N;
-        const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16) + mt * 256;
-        KtCells cs;
-        cs.c0 = smem_u32(cells) + row * 8;
-        cs.end = cs.mark = cs.c0;
-        cs.spill = surv + ((int64_t)b * N + (valid ? n : 0)) * KT_SURV;
-        cs.nspill = 0;
-        // margin = 2 a_i (the row's own share of the pair error bound, taken from its tag: rounded up)
-        const float margin = valid ? __uint_as_float(tag[(int64_t)b * Npad + n] << 16) : 0.0f;
-        bool ovf = !valid;          // "this row takes no more candidates": padding rows, and rows that overflowed
-        float L[KL];
-#pragma unroll
-        for (int i = 0; i < KL; ++i) L[i] = -INFINITY;
-        // -FLT_MAX, not -inf: padded candidates carry -inf and must never pass, not even while the bound is unknown
-        float thr = valid ? -3.402823466e38f : INFINITY;
-
-        // stages of 64 candidates = two chunks of 32; the TMEM load of the next chunk is in flight while one is filtered
+        const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16) + mt * 256 + half * 32;
         uint32_t r[32];
-        float v[32];
-        mbar_wait(&s.d_full[0], 0);
-        tc_fence_after();
-        tmem_ld32(tbase, r);
+
+        // ---------------- pass A: running maxima of the lower bounds, one group per column position ----------------
+        float gm[NG];
+#pragma unroll
+        for (int i = 0; i < NG; ++i) gm[i] = -INFINITY;
         for (int st = 0; st < nst; ++st) {
             const int ts = st % KT_TST;
-            const float* nhs = s.nh[ts];
+            mbar_wait(&s.d_full[ts], (st / KT_TST) & 1);
+            tc_fence_after();
+            tmem_ld32(tbase + ts * KT_COLS, r);
+            tmem_ld_wait32(r);
+            const float* cst = s.cst[ts] + half * 32;
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                tmem_ld_wait32(r);
-#pragma unroll
-                for (int c = 0; c < 32; c += 4) {
-                    const float4 h4 = *reinterpret_cast<const float4*>(nhs + half * 32 + c);
-                    // packed adds (add.f32x2): two IEEE fp32 additions per issue slot
-                    const float2 s0 = __fadd2_rn(make_float2(__uint_as_float(r[c]), __uint_as_float(r[c + 1])), make_float2(h4.x, h4.y));
-                    const float2 s1 = __fadd2_rn(make_float2(__uint_as_float(r[c + 2]), __uint_as_float(r[c + 3])), make_float2(h4.z, h4.w));
-                    v[c] = s0.x;
-                    v[c + 1] = s0.y;
-                    v[c + 2] = s1.x;
-                    v[c + 3] = s1.y;
-                }
-                if (half == 0) {
-                    tmem_ld32(tbase + ts * KT_COLS + 32, r);
-                } else if (st + 1 < nst) {
-                    const int ts1 = (st + 1) % KT_TST;
-                    mbar_wait(&s.d_full[ts1], ((st + 1) / KT_TST) & 1);
-                    tc_fence_after();
-                    tmem_ld32(tbase + ts1 * KT_COLS, r);
-                }
-                const uint32_t jb = (uint32_t)(st * KT_COLS + half * 32);
-                if (dbg && valid) {   // diagnostic entry only: dump the filter value v = D' - |x~_j|^2/2
-                    float* o = dbg + ((int64_t)b * N + n) * Npad + jb;
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) o[c] = v[c];
-                }
-                kt_filter32<KL>(v, s.tag[ts] + half * 32, L, cs, thr, ovf, margin, k);
+            for (int c = 0; c < 32; c += 4) {
+                const float4 l4 = *reinterpret_cast<const float4*>(cst + c);
+                const float2 s0 = __fadd2_rn(make_float2(__uint_as_float(r[c]), __uint_as_float(r[c + 1])), make_float2(l4.x, l4.y));
+                const float2 s1 = __fadd2_rn(make_float2(__uint_as_float(r[c + 2]), __uint_as_float(r[c + 3])), make_float2(l4.z, l4.w));
+                gm[c % NG] = fmaxf(gm[c % NG], s0.x);
+                gm[(c + 1) % NG] = fmaxf(gm[(c + 1) % NG], s0.y);
+                gm[(c + 2) % NG] = fmaxf(gm[(c + 2) % NG], s1.x);
+                gm[(c + 3) % NG] = fmaxf(gm[(c + 3) % NG], s1.y);
             }
-            // hand the TMEM stage (and its -|x~_j|^2/2 slot) back.  Deliberately at the END of the stage: with four stages in
-            // flight nothing waits for it, and the values of the second half are certainly in registers by now
+            // hand the TMEM stage (and its constants' slot) back
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&s.d_empty[ts]);
         }
 
-        // ---- hand-off: the cells that survive the exact k-th best filter value go to knn_finish_kernel ----
-        kt_refresh<KL>(L, cs, margin, k);   // cells = {v >= k-th best - margin}
-        if (valid) {
-            const int ns = (int)((cs.end - cs.c0) / KT_STEP);
-            const int64_t g = (int64_t)b * N + n;
-            if (ovf) {
-                surv_cnt[g] = 0;
-                flags[(int64_t)b * ((N + 63) / 64) + n / 64] = 1;
-            } else {
-                surv_cnt[g] = cs.nspill + ns;     // <= KT_SURV: a spill is only taken while nspill + cells + P fits
-                uint16_t* o = cs.spill + cs.nspill;
-                for (int e = 0; e < ns; ++e) o[e] = (uint16_t)(lds64(cs.c0 + e * KT_STEP).y >> 16);
+        // ---------------- the row's threshold: k-th largest of the 2 NG group maxima ----------------
+        kt_sort_desc<NG>(gm);
+#pragma unroll
+        for (int q = 0; q < NG / 4; ++q)
+            xch[(half * (NG / 4) + q) * KT_ROWS + row] = make_float4(gm[4 * q], gm[4 * q + 1], gm[4 * q + 2], gm[4 * q + 3]);
+        named_bar_sync(1, 32 * KT_SELW);
+        float thr;
+        {
+            const float* xf = reinterpret_cast<const float*>(xch);
+            // g-th largest (0-based) of this half (mine) / of the other half
+            auto mine = [&](int g) { return xf[((half * (NG / 4) + (g >> 2)) * KT_ROWS + row) * 4 + (g & 3)]; };
+            auto other = [&](int g) { return xf[(((half ^ 1) * (NG / 4) + (g >> 2)) * KT_ROWS + row) * 4 + (g & 3)]; };
+            // take i from mine and k - i from other: the smallest i with other[k-i-1] >= mine[i]
+            int lo = k > NG ? k - NG : 0, hi = k < NG ? k : NG;
+            while (lo < hi) {
+                const int i = (lo + hi) >> 1;
+                if (other(k - i - 1) < mine(i)) lo = i + 1;
+                else hi = i;
             }
+            const float ta = lo > 0 ? mine(lo - 1) : INFINITY;
+            const float tb = k - lo > 0 ? other(k - lo - 1) : INFINITY;
+            const float T = fminf(ta, tb);
+            // margin = 2 a_i (the row's own share of the pair error bound, taken from its tag: rounded up).
+            // -FLT_MAX, not -inf: padded candidates carry -inf and must never pass, not even while the bound is unknown
+            const float margin = valid ? __uint_as_float(tag[(int64_t)b * Npad + n] << 16) : 0.0f;
+            thr = valid ? fmaxf(__fsub_rd(T, margin), -3.402823466e38f) : INFINITY;
         }
-    } else {
-        reg_dealloc<40>();   // warps 2-3 only complete the first warpgroup
+
+        // ---------------- pass B: append every candidate whose upper bound reaches the threshold ----------------
+        // 32-bit record offsets from the (uniform) base pointer: one IMAD.WIDE per predicated store instead of 64-bit pointer chains
+        const int64_t g = (int64_t)b * N + (valid ? n : 0);
+        const uint32_t off0 = (uint32_t)(g * 2 + half) * (uint32_t)(2 * KT_CAP);     // [u: KT_CAP floats][tag: KT_CAP words]
+        uint32_t off = off0;
+        const uint32_t olim = off0 + (KT_CAP - 32);
+        // the base comes from shared memory, not from the parameter bank: it then lives in a register pair instead of being
+        // re-loaded from the constant bank for every candidate
+        uint32_t* const survw = reinterpret_cast<uint32_t*>(s.surv_base);
+        bool ovf = false;
+        for (int st = nst; st < 2 * nst; ++st) {
+            const int ts = st % KT_TST;
+            mbar_wait(&s.d_full[ts], (st / KT_TST) & 1);
+            tc_fence_after();
+            tmem_ld32(tbase + ts * KT_COLS, r);
+            tmem_ld_wait32(r);
+            if (off > olim) {         // fewer than 32 free records: this row-half is left to the exact repair pass
+                ovf = true;
+                thr = INFINITY;
+            }
+            const float* cst = s.cst[ts] + half * 32;
+            const uint32_t* tgs = s.tag[ts] + half * 32;
+            float v[32];
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) {
+                const float4 h4 = *reinterpret_cast<const float4*>(cst + c);
+                const float2 s0 = __fadd2_rn(make_float2(__uint_as_float(r[c]), __uint_as_float(r[c + 1])), make_float2(h4.x, h4.y));
+                const float2 s1 = __fadd2_rn(make_float2(__uint_as_float(r[c + 2]), __uint_as_float(r[c + 3])), make_float2(h4.z, h4.w));
+                v[c] = s0.x;
+                v[c + 1] = s0.y;
+                v[c + 2] = s1.x;
+                v[c + 3] = s1.y;
+            }
+            if (dbg && valid) {   // diagnostic entry only: dump the filter value u = D' - |x~_j|^2/2 + a_j
+                float* o = dbg + ((int64_t)b * N + n) * Npad + (st - nst) * KT_COLS + half * 32;
+#pragma unroll
+                for (int c = 0; c < 32; ++c) o[c] = v[c];
+            }
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) {
+                const uint4 t4 = *reinterpret_cast<const uint4*>(tgs + c);
+                const uint32_t tg[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (v[c + e] >= thr) {
+                        uint32_t* const rec = survw + off;          // one IMAD.WIDE.U32, two stores with immediate offsets
+                        rec[0] = __float_as_uint(v[c + e]);
+                        rec[KT_CAP] = tg[e];
+                        ++off;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s.d_empty[ts]);
+        }
+        if (valid) {
+            surv_cnt[g * 2 + half] = ovf ? -1 : (int)(off - off0);
+            if (ovf) flags[(int64_t)b * ((N + 63) / 64) + n / 64] = 1;
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -445,56 +413,129 @@ knn_tc_kernel(const uint8_t* __restrict__ ops, const float* __restrict__ nh, con
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// finish: exact pinned distances of the survivors, sorted, written out.  One warp per query row, one lane per survivor.
+// finish: exact pinned distances of the survivors.  One warp per query row, one lane per survivor.
 // The survivors' fp32 rows are gathered with coalesced loads (2 or 8 rows per instruction) into a padded staging tile,
-// each lane then runs the pinned fma chain over its own row; a warp-wide bitonic sort of 64-bit keys
+// each lane then runs the pinned fma chain over its own row; ranking by counting over 64-bit keys
 // (orderable d << 32 | ~j) puts the k best first: nearest first, ties -> ascending index.
+//
+// SET mode: the caller only needs the neighbour SET (the fused EdgeConv takes a max over it).  With
+//   D_j in [w_j - a_i, u_j + a_i],  w_j = u_j - 2 a_j,  m = 2 a_i
+// a survivor is certainly among the k best if fewer than k candidates can possibly reach it (w_j > U + m, U = the (k+1)-th
+// largest u of the row), certainly not if k candidates certainly beat it (u_j + m < W, W = the k-th largest w); candidates
+// the filter dropped have u < T - m <= W - m and change neither count.  Only the band in between gets the pinned
+// arithmetic, and the best (k - #certain) of the band complete the set.  The k indices are written in no particular order.
 // ---------------------------------------------------------------------------------------------------------------
-template <int CPT, int KF_WARPS>
+template <int CPT, int KF_WARPS, bool SET>
 __global__ void __launch_bounds__(KF_WARPS * 32)
-knn_finish_kernel(const float* __restrict__ xp, const float* __restrict__ sqnorm, const uint16_t* __restrict__ surv,
-                  const int* __restrict__ surv_cnt, int N, int Npad, int k, int64_t rows, int32_t* __restrict__ idx_out,
-                  float* __restrict__ dist_out) {
+knn_finish_kernel(const float* __restrict__ xp, const float* __restrict__ sqnorm, const float* __restrict__ surv,
+                  const int* __restrict__ surv_cnt, const uint32_t* __restrict__ tag, int N, int Npad, int k, int64_t rows,
+                  int32_t* __restrict__ idx_out, float* __restrict__ dist_out) {
     constexpr int RS = CPT + 4;            // padded staging row: conflict-free LDS.128 across lanes
     constexpr int LPR = CPT / 4;           // lanes that fetch one row
     constexpr int RPI = 32 / LPR;          // rows per load instruction
     __shared__ __align__(16) float stg_all[KF_WARPS][32 * RS];
     __shared__ __align__(16) unsigned long long kbuf[KF_WARPS][KT_SURV];
     __shared__ __align__(16) float xi_all[KF_WARPS][CPT];
+    __shared__ uint16_t jbuf[KF_WARPS][KT_SURV];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* stg = stg_all[warp];
     const int sub = lane % LPR, grp = lane / LPR;
-    // software pipeline over the warp's rows: the next row's survivor list is in flight while this row is finished
     const int64_t gstep = (int64_t)gridDim.x * KF_WARPS;
-    int64_t g = (int64_t)blockIdx.x * KF_WARPS + warp;
-    int ns_n = 0;
-    uint32_t jl_n = 0, jh_n = 0;
-    if (g < rows) {
-        ns_n = __ldg(surv_cnt + g);
-        jl_n = __ldg(surv + g * KT_SURV + lane);
-        jh_n = __ldg(surv + g * KT_SURV + 32 + lane);
-    }
-    for (; g < rows; g += gstep) {
-        const int ns = ns_n;
-        const uint32_t jl = jl_n, jh = jh_n;
-        if (g + gstep < rows) {
-            ns_n = __ldg(surv_cnt + g + gstep);
-            jl_n = __ldg(surv + (g + gstep) * KT_SURV + lane);
-            jh_n = __ldg(surv + (g + gstep) * KT_SURV + 32 + lane);
-        }
-        if (ns == 0) continue;                       // flagged for the exact repair pass
+    for (int64_t g = (int64_t)blockIdx.x * KF_WARPS + warp; g < rows; g += gstep) {
+        const int c0 = __ldg(surv_cnt + 2 * g), c1 = __ldg(surv_cnt + 2 * g + 1);
+        if (c0 < 0 || c1 < 0) continue;              // flagged for the exact repair pass
+        const int ns = c0 + c1;
+        const float* su = surv + g * (4 * KT_CAP);   // [half 0: u | tag][half 1: u | tag]
         const int64_t b = g / N;
         const float* xpb = xp + b * Npad * CPT;
+        u64* keys = reinterpret_cast<u64*>(kbuf[warp]);
+        uint16_t* js = jbuf[warp];
+        int nb = ns;                                 // candidates that need the exact arithmetic
+        int kneed = k;                               // ... of which this many complete the set
+        int nout = 0;                                // (SET) indices already written
+        if (SET) {
+            // ---- classify by the bounds.  Slots: lane, lane + 32 over the concatenation of the two half lists ----
+            const int r = ns - k;                    // survivors that have to go
+            if (ns <= 64 && r <= 12) {
+                float u[2], w[2];
+                uint32_t tg[2], ku[2];
+                float amax = 0.0f;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int e = h * 32 + lane;
+                    u[h] = w[h] = INFINITY;
+                    tg[h] = 0u;
+                    if (e < ns) {
+                        const float* p = e < c0 ? su + e : su + 2 * KT_CAP + (e - c0);
+                        u[h] = __ldg(p);
+                        tg[h] = __ldg(reinterpret_cast<const uint32_t*>(p) + KT_CAP);
+                        const float a2 = __uint_as_float(tg[h] << 16);
+                        w[h] = __fsub_rd(u[h], a2);
+                        amax = fmaxf(amax, a2);
+                    }
+                    // unique keys: the low 6 bits carry the slot, so every REDUX below removes exactly one survivor.  Truncation
+                    // is monotone: the i-th smallest truncated key is the truncation of the i-th smallest u (empty slots: +inf)
+                    ku[h] = (kt_ord_key(u[h]) & ~63u) | (uint32_t)e;
+                }
+                // U1 = (k+1)-th largest u = r-th smallest, U0 = k-th largest u = (r+1)-th smallest: r is small (the filter keeps
+                // k plus a handful), so the smallest keys are peeled off one warp-wide integer min (REDUX) at a time.
+                uint32_t k1 = 0u, k0 = 0u;           // key 0 sorts below every float: "no such element" = -inf
+                for (int it = 0; it <= r; ++it) {
+                    const uint32_t mn = __reduce_min_sync(0xffffffffu, min(ku[0], ku[1]));
+                    k1 = k0;
+                    k0 = mn;
+                    ku[0] = ku[0] == mn ? 0xffffffffu : ku[0];
+                    ku[1] = ku[1] == mn ? 0xffffffffu : ku[1];
+                }
+                // U: an upper bound of the (k+1)-th largest u (low bits filled); W: a lower bound of the k-th largest lower
+                // bound w (w_j >= u_j - max_j 2 a_j, low bits cleared)
+                const float U = r > 0 ? kt_ord_val(k1 | 63u) : -INFINITY;
+                amax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(amax)));     // non-negative floats order as integers
+                const float W = __fsub_rd(kt_ord_val(k0 & ~63u), amax);
+                const float m = __uint_as_float(__ldg(tag + b * Npad + (g - b * N)) << 16);
+                const float Uin = __fadd_ru(U, m), Wout = __fsub_rd(W, m);
+                int nin = 0;
+                nb = 0;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int e = h * 32 + lane;
+                    const bool live = e < ns;
+                    const bool in = live && w[h] > Uin;                       // at most k - 1 others can reach it
+                    const bool out = live && !in && u[h] < Wout;              // k others certainly beat it
+                    const bool band = live && !in && !out;
+                    const unsigned bi = __ballot_sync(0xffffffffu, in), bb = __ballot_sync(0xffffffffu, band);
+                    const unsigned lt = (1u << lane) - 1u;
+                    if (in) idx_out[g * k + nin + __popc(bi & lt)] = (int32_t)(tg[h] >> 16);
+                    if (band) js[nb + __popc(bb & lt)] = (uint16_t)(tg[h] >> 16);
+                    nin += __popc(bi);
+                    nb += __popc(bb);
+                }
+                nout = nin;
+                kneed = k - nin;
+                __syncwarp();
+            } else {
+                for (int e = lane; e < ns; e += 32) {
+                    const float* p = e < c0 ? su + e : su + 2 * KT_CAP + (e - c0);
+                    js[e] = (uint16_t)(__ldg(reinterpret_cast<const uint32_t*>(p) + KT_CAP) >> 16);
+                }
+                __syncwarp();
+            }
+            if (kneed == 0) continue;
+        } else {
+            for (int e = lane; e < ns; e += 32) {
+                const float* p = e < c0 ? su + e : su + 2 * KT_CAP + (e - c0);
+                js[e] = (uint16_t)(__ldg(reinterpret_cast<const uint32_t*>(p) + KT_CAP) >> 16);
+            }
+            __syncwarp();
+        }
         // the query row itself goes to shared memory (broadcast reads in the chain): holding it in 64 registers per lane
         // would halve the number of resident warps, and this kernel lives on latency hiding
         float* xis = xi_all[warp];
         if (lane < LPR) *reinterpret_cast<float4*>(xis + lane * 4) = __ldg(reinterpret_cast<const float4*>(xpb + (g - b * N) * CPT + lane * 4));
         const float xxi = __ldg(sqnorm + g);
-        u64* keys = reinterpret_cast<u64*>(kbuf[warp]);
-        for (int half = 0; half * 32 < ns; ++half) {   // further rounds only for rows with more than 32 survivors
+        for (int half = 0; half * 32 < nb; ++half) {   // further rounds only for rows with more than 32 candidates
             const int e = half * 32 + lane;
-            uint32_t j = 0u;                             // entries past ns are uninitialised memory
-            if (e < ns) j = half == 0 ? jl : half == 1 ? jh : (uint32_t)__ldg(surv + g * KT_SURV + e);
+            const uint32_t j = e < nb ? (uint32_t)js[e] : 0u;
             float4 t[32 / RPI];
 #pragma unroll
             for (int it = 0; it < 32 / RPI; ++it) {
@@ -518,12 +559,12 @@ knn_finish_kernel(const float* __restrict__ xp, const float* __restrict__ sqnorm
             }
             const float d = fmaf(2.0f, dot, -xxi) - xxj;
             // 64-bit key: larger = nearer, equal distances -> smaller index first; 0 = empty slot (below every real key)
-            keys[e] = e < ns ? (((u64)kt_ord_key(d) << 32) | (u64)(~j)) : 0ull;
+            keys[e] = e < nb ? (((u64)kt_ord_key(d) << 32) | (u64)(~j)) : 0ull;
         }
         __syncwarp();
         // rank by counting (independent broadcast reads: no dependent shuffle network), keys are all distinct
-        const int nk = (ns + 3) & ~3;                  // slots up to the next multiple of 32 hold 0 = never greater
-        for (int half = 0; half * 32 < ns; ++half) {
+        const int nk = (nb + 3) & ~3;                  // slots up to the next multiple of 32 hold 0 = never greater
+        for (int half = 0; half * 32 < nb; ++half) {
             const u64 mine = keys[half * 32 + lane];
             int rank = 0;
 #pragma unroll 2
@@ -535,18 +576,18 @@ knn_finish_kernel(const float* __restrict__ xp, const float* __restrict__ sqnorm
                 if (q1.x > mine) ++rank;
                 if (q1.y > mine) ++rank;
             }
-            if (mine != 0ull && rank < k) {
-                idx_out[g * k + rank] = (int32_t)(~(uint32_t)mine);
-                if (dist_out) dist_out[g * k + rank] = kt_ord_val((uint32_t)(mine >> 32));
+            if (mine != 0ull && rank < kneed) {
+                idx_out[g * k + nout + rank] = (int32_t)(~(uint32_t)mine);
+                if (!SET && dist_out) dist_out[g * k + rank] = kt_ord_val((uint32_t)(mine >> 32));
             }
         }
-        __syncwarp();                                // keys are reused by the next row
+        __syncwarp();                                // keys / js are reused by the next row
     }
 }
 
 struct KtPlan {
     int Npad, Cp16, KB, CPT;
-    size_t off_xp, off_nh, off_tag, off_surv, off_cnt, off_flags, total, zero_bytes;
+    size_t off_xp, off_nh, off_nl, off_tag, off_surv, off_cnt, off_flags, total, zero_bytes;
 };
 static KtPlan kt_plan(int B, int C, int N) {
     KtPlan p;
@@ -559,12 +600,14 @@ static KtPlan kt_plan(int B, int C, int N) {
     o += (size_t)B * p.Npad * p.CPT * 4;
     p.off_nh = o;
     o += (size_t)B * p.Npad * 4;
+    p.off_nl = o;
+    o += (size_t)B * p.Npad * 4;
     p.off_tag = o;
     o += (size_t)B * p.Npad * 4;
     p.off_surv = o;
-    o += (size_t)B * N * KT_SURV * 2;
+    o += (size_t)B * N * 4 * KT_CAP * 4;
     p.off_cnt = o;
-    o += (size_t)B * N * 4;
+    o += (size_t)B * N * 2 * 4;
     o = (o + 15) / 16 * 16;
     p.off_flags = o;
     o += (size_t)B * ((N + 63) / 64) * 4;
@@ -577,28 +620,45 @@ static KtPlan kt_plan(int B, int C, int N) {
 int knn_exact_flagged(const float* x, int64_t x_bstride, int B, int C, int N, int k, const float* sqnorm, const int* flags,
                       int32_t* idx_out, float* dist_out, cudaStream_t st);
 
-static int kt_launch(const KtPlan& p, uint8_t* ws, const float* sqnorm, int B, int C, int N, int k, int32_t* idx_out, float* dist_out,
-                     float* dbg, cudaStream_t st) {
-    const size_t smem = (size_t)2 * p.KB * 16384 + (size_t)2 * p.KB * 8192 + (size_t)KT_P * KT_ROWS * 8 + sizeof(KtCtl) + 1024;
-    GFS_CUDA_OK(allow_smem(reinterpret_cast<const void*>(knn_tc_kernel<20>), smem));
-    uint16_t* surv = reinterpret_cast<uint16_t*>(ws + p.off_surv);
-    int* cnt = reinterpret_cast<int*>(ws + p.off_cnt);
-    knn_tc_kernel<20><<<dim3(p.Npad / KT_ROWS, B), KT_THREADS, smem, st>>>(
-        ws, reinterpret_cast<const float*>(ws + p.off_nh), reinterpret_cast<const uint32_t*>(ws + p.off_tag),
-        reinterpret_cast<int*>(ws + p.off_flags), N, p.Npad, p.Cp16, p.KB, k, surv, cnt, dbg);
+template <int NG, int KS>
+static int kt_launch_filter_ks(const KtPlan& p, uint8_t* ws, int B, int N, int k, float* dbg, cudaStream_t st) {
+    const size_t smem = (size_t)2 * p.KB * 16384 + (size_t)KT_BST * p.KB * 8192 + (size_t)2 * (NG / 4) * KT_ROWS * 16 + sizeof(KtCtl) + 1024;
+    GFS_CUDA_OK(allow_smem(reinterpret_cast<const void*>(knn_tc_kernel<NG, KS>), smem));
+    knn_tc_kernel<NG, KS><<<dim3(p.Npad / KT_ROWS, B), KT_THREADS, smem, st>>>(
+        ws, reinterpret_cast<const float*>(ws + p.off_nh), reinterpret_cast<const float*>(ws + p.off_nl),
+        reinterpret_cast<const uint32_t*>(ws + p.off_tag), reinterpret_cast<int*>(ws + p.off_flags), N, p.Npad, p.Cp16, p.KB, k,
+        reinterpret_cast<float*>(ws + p.off_surv), reinterpret_cast<int*>(ws + p.off_cnt), dbg);
     GFS_LAUNCH_OK("knn_tc_kernel");
+    return GFS_OK;
+}
+template <int NG>
+static int kt_launch_filter(const KtPlan& p, uint8_t* ws, int B, int N, int k, float* dbg, cudaStream_t st) {
+    switch (p.Cp16 >> 4) {
+        case 1: return kt_launch_filter_ks<NG, 1>(p, ws, B, N, k, dbg, st);
+        case 2: return kt_launch_filter_ks<NG, 2>(p, ws, B, N, k, dbg, st);
+        case 3: return kt_launch_filter_ks<NG, 3>(p, ws, B, N, k, dbg, st);
+        default: return kt_launch_filter_ks<NG, 4>(p, ws, B, N, k, dbg, st);
+    }
+}
+
+template <bool SET>
+static int kt_launch_finish(const KtPlan& p, uint8_t* ws, const float* sqnorm, int B, int N, int k, int32_t* idx_out, float* dist_out,
+                            cudaStream_t st) {
     const int64_t rows = (int64_t)B * N;
     const int sms = sm_count();
     GFS_REQUIRE(sms > 0, GFS_ERR_CUDA, "gfs_knn_tc_f32: cannot query the device");
     const float* xp = reinterpret_cast<const float*>(ws + p.off_xp);
+    const float* surv = reinterpret_cast<const float*>(ws + p.off_surv);
+    const int* cnt = reinterpret_cast<const int*>(ws + p.off_cnt);
+    const uint32_t* tag = reinterpret_cast<const uint32_t*>(ws + p.off_tag);
     if (p.CPT == 16) {
         const int64_t want = (rows + 7) / 8;
         const int grid = (int)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
-        knn_finish_kernel<16, 8><<<grid, 256, 0, st>>>(xp, sqnorm, surv, cnt, N, p.Npad, k, rows, idx_out, dist_out);
+        knn_finish_kernel<16, 8, SET><<<grid, 256, 0, st>>>(xp, sqnorm, surv, cnt, tag, N, p.Npad, k, rows, idx_out, dist_out);
     } else {
         const int64_t want = (rows + 3) / 4;
         const int grid = (int)(want < (int64_t)sms * 16 ? want : (int64_t)sms * 16);
-        knn_finish_kernel<64, 4><<<grid, 128, 0, st>>>(xp, sqnorm, surv, cnt, N, p.Npad, k, rows, idx_out, dist_out);
+        knn_finish_kernel<64, 4, SET><<<grid, 128, 0, st>>>(xp, sqnorm, surv, cnt, tag, N, p.Npad, k, rows, idx_out, dist_out);
     }
     GFS_LAUNCH_OK("knn_finish_kernel");
     return GFS_OK;
@@ -611,20 +671,22 @@ extern "C" int64_t gfs_knn_tc_workspace_bytes(int B, int C, int N) {
     return (int64_t)gfs::kt_plan(B, C, N).total;
 }
 
-static int kt_run(const float* x, int64_t x_bstride, int B, int C, int N, int k, float* sqnorm, void* workspace,
-                  int64_t workspace_bytes, int32_t* idx_out, float* dist_out, float* dbg, void* stream) {
+static int kt_run(const char* who, const float* x, int64_t x_bstride, int B, int C, int N, int k, float* sqnorm, void* workspace,
+                  int64_t workspace_bytes, int32_t* idx_out, float* dist_out, float* dbg, bool set_only, void* stream) {
     using namespace gfs;
-    GFS_REQUIRE(x && sqnorm && idx_out && workspace, GFS_ERR_BAD_ARG, "gfs_knn_tc_f32: null pointer");
-    GFS_REQUIRE(B > 0 && C > 0 && N > 0 && k > 0, GFS_ERR_BAD_ARG, "gfs_knn_tc_f32: non-positive size (B=%d C=%d N=%d k=%d)", B, C, N, k);
-    GFS_REQUIRE(k <= N, GFS_ERR_BAD_ARG, "gfs_knn_tc_f32: k=%d exceeds N=%d", k, N);
-    GFS_REQUIRE(k <= 20, GFS_ERR_UNSUPPORTED, "gfs_knn_tc_f32: k=%d > 20 is not built (use gfs_knn_f32)", k);
-    GFS_REQUIRE(C <= 64, GFS_ERR_UNSUPPORTED, "gfs_knn_tc_f32: C=%d > 64 is not built", C);
-    GFS_REQUIRE(N <= 65535, GFS_ERR_UNSUPPORTED, "gfs_knn_tc_f32: N=%d > 65535 (16-bit candidate slots)", N);
+    GFS_REQUIRE(x && sqnorm && idx_out && workspace, GFS_ERR_BAD_ARG, "%s: null pointer", who);
+    GFS_REQUIRE(B > 0 && C > 0 && N > 0 && k > 0, GFS_ERR_BAD_ARG, "%s: non-positive size (B=%d C=%d N=%d k=%d)", who, B, C, N, k);
+    GFS_REQUIRE(k <= N, GFS_ERR_BAD_ARG, "%s: k=%d exceeds N=%d", who, k, N);
+    GFS_REQUIRE(k <= 40, GFS_ERR_UNSUPPORTED, "%s: k=%d > 40 is not built (use gfs_knn_f32)", who, k);
+    GFS_REQUIRE(C <= 64, GFS_ERR_UNSUPPORTED, "%s: C=%d > 64 is not built", who, C);
+    GFS_REQUIRE(N <= 65535, GFS_ERR_UNSUPPORTED, "%s: N=%d > 65535 (16-bit candidate slots)", who, N);
+    GFS_REQUIRE((int64_t)B * N * 4 * KT_CAP < (int64_t)1 << 32, GFS_ERR_UNSUPPORTED, "%s: B*N=%lld rows exceed the 32-bit survivor offsets", who,
+                (long long)B * N);
     GFS_REQUIRE(N % 4 == 0 && x_bstride % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, GFS_ERR_UNSUPPORTED,
-                "gfs_knn_tc_f32: needs N %% 4 == 0 and 16-byte aligned rows (N=%d)", N);
+                "%s: needs N %% 4 == 0 and 16-byte aligned rows (N=%d)", who, N);
     const KtPlan p = kt_plan(B, C, N);
     GFS_REQUIRE(workspace_bytes >= (int64_t)p.total && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, GFS_ERR_BAD_ARG,
-                "gfs_knn_tc_f32: workspace of %lld bytes (256-byte aligned) needed, got %lld", (long long)p.total,
+                "%s: workspace of %lld bytes (256-byte aligned) needed, got %lld", who, (long long)p.total,
                 (long long)workspace_bytes);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     uint8_t* ws = static_cast<uint8_t*>(workspace);
@@ -632,16 +694,25 @@ static int kt_run(const float* x, int64_t x_bstride, int B, int C, int N, int k,
     knn_prep_kernel<<<dim3(p.Npad / 128, B), 128, 0, st>>>(x, x_bstride, C, N, p.Npad, p.Cp16, p.KB, p.CPT, ws,
                                                            reinterpret_cast<float*>(ws + p.off_xp),
                                                            reinterpret_cast<float*>(ws + p.off_nh),
+                                                           reinterpret_cast<float*>(ws + p.off_nl),
                                                            reinterpret_cast<uint32_t*>(ws + p.off_tag), sqnorm);
     GFS_LAUNCH_OK("knn_prep_kernel");
-    const int rc = kt_launch(p, ws, sqnorm, B, C, N, k, idx_out, dist_out, dbg, st);
+    int rc = kt_launch_filter<32>(p, ws, B, N, k, dbg, st);
+    if (rc != GFS_OK) return rc;
+    rc = set_only ? kt_launch_finish<true>(p, ws, sqnorm, B, N, k, idx_out, nullptr, st)
+                  : kt_launch_finish<false>(p, ws, sqnorm, B, N, k, idx_out, dist_out, st);
     if (rc != GFS_OK) return rc;
     return knn_exact_flagged(x, x_bstride, B, C, N, k, sqnorm, reinterpret_cast<const int*>(ws + p.off_flags), idx_out, dist_out, st);
 }
 
 extern "C" int gfs_knn_tc_f32(const float* x, int64_t x_bstride, int B, int C, int N, int k, float* sqnorm, void* workspace,
                               int64_t workspace_bytes, int32_t* idx_out, float* dist_out, void* stream) {
-    return kt_run(x, x_bstride, B, C, N, k, sqnorm, workspace, workspace_bytes, idx_out, dist_out, nullptr, stream);
+    return kt_run("gfs_knn_tc_f32", x, x_bstride, B, C, N, k, sqnorm, workspace, workspace_bytes, idx_out, dist_out, nullptr, false, stream);
+}
+
+extern "C" int gfs_knn_tc_set_f32(const float* x, int64_t x_bstride, int B, int C, int N, int k, float* sqnorm, void* workspace,
+                                  int64_t workspace_bytes, int32_t* idx_out, void* stream) {
+    return kt_run("gfs_knn_tc_set_f32", x, x_bstride, B, C, N, k, sqnorm, workspace, workspace_bytes, idx_out, nullptr, nullptr, true, stream);
 }
 
 extern "C" int gfs_knn_tc_diag_f32(const float* x, int64_t x_bstride, int B, int C, int N, int k, float* sqnorm, void* workspace,
@@ -649,7 +720,7 @@ extern "C" int gfs_knn_tc_diag_f32(const float* x, int64_t x_bstride, int B, int
                                    void* stream) {
     using namespace gfs;
     GFS_REQUIRE(filter_out && repair_flags_out, GFS_ERR_BAD_ARG, "gfs_knn_tc_diag_f32: null output");
-    const int rc = kt_run(x, x_bstride, B, C, N, k, sqnorm, workspace, workspace_bytes, idx_out, nullptr, filter_out, stream);
+    const int rc = kt_run("gfs_knn_tc_diag_f32", x, x_bstride, B, C, N, k, sqnorm, workspace, workspace_bytes, idx_out, nullptr, filter_out, false, stream);
     if (rc != GFS_OK) return rc;
     const KtPlan p = kt_plan(B, C, N);
     GFS_CUDA_OK(cudaMemcpyAsync(repair_flags_out, static_cast<uint8_t*>(workspace) + p.off_flags, (size_t)B * ((N + 63) / 64) * 4,

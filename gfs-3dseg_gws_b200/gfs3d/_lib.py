@@ -14,6 +14,7 @@ _i, _i64, _p, _f = ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_float
 SIGNATURES = {
     "gfs_knn_f32": [_p, _i64, _i, _i, _i, _i, _p, _p, _p, _p],
     "gfs_knn_tc_f32": [_p, _i64, _i, _i, _i, _i, _p, _p, _i64, _p, _p, _p],
+    "gfs_knn_tc_set_f32": [_p, _i64, _i, _i, _i, _i, _p, _p, _i64, _p, _p],
     "gfs_knn_tc_diag_f32": [_p, _i64, _i, _i, _i, _i, _p, _p, _i64, _p, _p, _p, _p],
     "gfs_pointwise_f32": [_p, _i64, _i, _i, _i, _p, _p, _i, _p, _p],
     "gfs_edgeconv_fwd": [_p, _p, _p, _p, _i, _i, _i, _p, _i64, _p, _i, _i, _p, _i, _i, _p, _p],

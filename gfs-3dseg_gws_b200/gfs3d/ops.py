@@ -71,14 +71,16 @@ KNN_IMPL = os.environ.get("GFS3D_KNN", "auto")   # "auto" | "tc" | "exact": both
 
 
 def knn_tc_eligible(C: int, N: int, k: int) -> bool:
-    return k <= 20 and C <= 64 and N <= 65535 and N % 4 == 0
+    return k <= 40 and C <= 64 and N <= 65535 and N % 4 == 0
 
 
-def knn(x: torch.Tensor, k: int, return_dist: bool = False, impl: Optional[str] = None):
+def knn(x: torch.Tensor, k: int, return_dist: bool = False, impl: Optional[str] = None, ordered: bool = True):
     """x: (B, C, N) fp32 view with unit point stride and channel stride N -> idx (B, N, k) int32
 
     impl "tc": tensor-core filter + exact finish (gfs_knn_tc_f32); "exact": the all-fp32 kernel (gfs_knn_f32);
-    "auto": tc whenever the shape is eligible.  The two produce the same indices and distances bit for bit."""
+    "auto": tc whenever the shape is eligible.  The two produce the same indices and distances bit for bit.
+    ordered=False (tc only): the same k neighbours per row in no particular order (gfs_knn_tc_set_f32) -- enough for a
+    max over the neighbours, and cheaper: only candidates the error bounds cannot decide get the exact arithmetic."""
     _need_cuda(x)
     B, C, N = x.shape
     assert x.dtype == torch.float32 and x.stride(2) == 1 and x.stride(1) == N, "x must be channel-major"
@@ -89,8 +91,11 @@ def knn(x: torch.Tensor, k: int, return_dist: bool = False, impl: Optional[str] 
     if impl == "tc" or (impl == "auto" and knn_tc_eligible(C, N, k)):
         nbytes = int(lib().gfs_knn_tc_workspace_bytes(B, C, N))
         ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
-        _call("gfs_knn_tc_f32", 4, _ptr(x), x.stride(0), B, C, N, k, _ptr(sq), _ptr(ws), nbytes, _ptr(idx), _ptr(dist),
-              _stream())
+        if ordered or return_dist:
+            _call("gfs_knn_tc_f32", 4, _ptr(x), x.stride(0), B, C, N, k, _ptr(sq), _ptr(ws), nbytes, _ptr(idx), _ptr(dist),
+                  _stream())
+        else:
+            _call("gfs_knn_tc_set_f32", 4, _ptr(x), x.stride(0), B, C, N, k, _ptr(sq), _ptr(ws), nbytes, _ptr(idx), _stream())
     else:
         _call("gfs_knn_f32", 2, _ptr(x), x.stride(0), B, C, N, k, _ptr(sq), _ptr(idx), _ptr(dist), _stream())
     return (idx, dist) if return_dist else idx

@@ -190,7 +190,7 @@ class DGCNN(nn.Module):
         cat_act = ops.new_act(M, L, x.device, zero=False)
         xin = x
         for i, (wt, bias, w2p, t2) in enumerate(layers):
-            idx = ops.knn(xin, self.k)
+            idx = ops.knn(xin, self.k, ordered=False)      # the max over k only needs the neighbour set
             pq = ops.pointwise(xin, wt, bias)
             y = ec[:, 64 * i:64 * (i + 1), :]
             ops.edgeconv(pq, idx, w2p, t2, B, N, self.k, y_cm=y, y_act=cat_act, y_act_kb=i,

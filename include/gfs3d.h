@@ -58,15 +58,23 @@ int gfs_knn_f32(const float* x, int64_t x_bstride, int B, int C, int N, int k,
                 float* sqnorm, int32_t* idx_out, float* dist_out, void* stream);
 
 /* Same result, bit for bit, as gfs_knn_f32 (model/dgcnn.py:17-23), computed as: tcgen05 bf16-split candidate filter on
- * shifted coordinates with a proven per-pair error bound -> exact pinned fp32 distances of the few survivors -> rank
- * (gfs-3dseg_gws_b200/csrc/knn_tc.cu).  k <= 20, C <= 64, N <= 65535, N % 4 == 0.  `workspace` is scratch of
- * gfs_knn_tc_workspace_bytes(B, C, N) bytes, 256-byte aligned (operand tiles, point-major copy, per-point filter terms,
- * up to 256 survivors per row, repair flags); rows with more survivors than that (floods of exact ties) are redone by
- * the all-fp32 kernel inside the same call.  Four launches (prepare, filter, finish, repair), no host synchronisation. */
+ * shifted coordinates with a per-pair error bound (two passes over the candidates: group maxima of the lower bounds give
+ * the row's threshold, then the candidates whose upper bound reaches it are recorded) -> exact pinned fp32 distances of
+ * the few survivors -> rank (gfs-3dseg_gws_b200/csrc/knn_tc.cu).  k <= 40, C <= 64, N <= 65535, N % 4 == 0.
+ * `workspace` is scratch of gfs_knn_tc_workspace_bytes(B, C, N) bytes, 256-byte aligned (operand tiles, point-major copy,
+ * per-point filter terms, up to 2 x 128 survivor records per row, repair flags); rows with more survivors than that
+ * (floods of exact ties) are redone by the all-fp32 kernel inside the same call.  Four launches (prepare, filter,
+ * finish, repair), no host synchronisation.                                                                          */
 int64_t gfs_knn_tc_workspace_bytes(int B, int C, int N);
 int gfs_knn_tc_f32(const float* x, int64_t x_bstride, int B, int C, int N, int k,
                    float* sqnorm, void* workspace, int64_t workspace_bytes,
                    int32_t* idx_out, float* dist_out, void* stream);
+/* The neighbour SET of gfs_knn_tc_f32 / gfs_knn_f32 (the same k indices per row, in no particular order, no distances):
+ * what model/dgcnn.py:118's max over the k neighbours needs.  The survivors of the filter are classified by their error
+ * bounds (certainly in / certainly out / undecided) and only the undecided band gets the pinned fp32 arithmetic.       */
+int gfs_knn_tc_set_f32(const float* x, int64_t x_bstride, int B, int C, int N, int k,
+                       float* sqnorm, void* workspace, int64_t workspace_bytes,
+                       int32_t* idx_out, void* stream);
 /* Diagnostic twin (tests): additionally dumps what the tensor-core filter saw, filter_out[b][i][j] = the upper filter value
  * u ~= x~_i.x~_j - |x~_j|^2/2 + a_j on the shifted coordinates x~ (see knn_tc.cu) as (B, N, Npad) fp32 with Npad = N rounded
  * up to 256, and the per-64-row-tile repair flags (B, ceil(N/64)) int32.                                              */

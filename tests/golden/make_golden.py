@@ -105,14 +105,15 @@ def make_gfs(name, B, N, classes, base_num, G, seed, wname):
          idx0=idx[0], idx1=idx[1], idx2=idx[2], feat_level2=f["feat_level2"].numpy())
 
 
-def make_train(name, B, N, seed):
+def make_train(name, B, N, seed, classes=13, base_num=7, G=150, wname="gfs_s3dis_weights", compact=False):
     """one training step of the real reference on CPU (model/capl.py:194-242): loss, predictions, gradients, updated BN
     running statistics.  capl.py:406 hard-codes .cuda(); it is neutralised HERE (not in the reference) by making
-    Tensor.cuda the identity for the duration of the call.  Attention dropout is set to p = 0."""
+    Tensor.cuda the identity for the duration of the call.  Attention dropout is set to p = 0.
+    compact=True (the full-size BASELINE.json configs[2] step): inputs are regenerated from the seed by the test
+    (O.synthetic_blocks / torch.randint are deterministic), only a subsample of the predictions is stored."""
     import random
     torch.manual_seed(321)
     args = ref_args()
-    classes, base_num, G = 13, 7, 150
     gp = torch.randn(G, 192, generator=torch.Generator().manual_seed(7))
     m = mpti_net_Point_GeoAsWeight_v2(classes=classes, criterion=torch.nn.CrossEntropyLoss(ignore_index=255), args=args,
                                       base_num=base_num, gp=gp.clone(), energy=0.9)
@@ -149,13 +150,15 @@ def make_train(name, B, N, seed):
             "encoder.conv.layer.0.weight", "encoder.conv.layer.4.weight", "att_learner.q_map.weight", "att_learner.v_map.weight",
             "base_learner.convs.0.0.weight", "base_learner.convs.1.1.bias"]
     after = m.state_dict()
-    save(name, x=x.numpy(), y=y.numpy().astype(np.int16), gp=gp.numpy(), fake_novel=np.array(fake_novel, np.int32), loss=np.float32(float(loss)),
-         pred=pred.numpy().astype(np.int16), base_num=np.int32(base_num), classes=np.int32(classes),
+    inputs = dict(seed=np.int32(seed), B=np.int32(B), N=np.int32(N), G=np.int32(G), pred=pred[:, ::16].numpy().astype(np.int16)) if compact else \
+        dict(x=x.numpy(), y=y.numpy().astype(np.int16), gp=gp.numpy(), pred=pred.numpy().astype(np.int16))
+    save(name, fake_novel=np.array(fake_novel, np.int32), loss=np.float32(float(loss)),
+         base_num=np.int32(base_num), classes=np.int32(classes), **inputs,
          **{"grad." + k_: grads[k_].numpy() for k_ in keep},
          **{"gradnorm." + k_: np.float32(g_.norm()) for k_, g_ in grads.items()},
          **{"after." + k_: after[k_].numpy() for k_ in after if "running" in k_ and ("edge_convs.0" in k_ or "fusion" in k_ or "conv.layer.4" in k_)})
-    # weights: identical to gfs_s3dis_weights.npz (same seeds), not stored twice
-    ref_w = np.load(os.path.join(HERE, "gfs_s3dis_weights.npz"))
+    # weights: identical to the eval fixture's (same seeds), not stored twice
+    ref_w = np.load(os.path.join(HERE, wname + ".npz"))
     assert all((ref_w[k_] == sd0[k_].numpy()).all() for k_ in ref_w.files)
 
 
@@ -336,6 +339,11 @@ if __name__ == "__main__":
         make_gfs("gfs_scannet_b2_n128", 2, 128, 21, 15, 180, seed=8765, wname="gfs_scannet_weights")
     if "train" in todo:
         make_train("train_s3dis_b4_n128", 4, 128, seed=2468)
+        # BASELINE.json configs[2]: ScanNet-shaped (21 classes, 180 GWs, base_num 15) -- a miniature and the full-size step
+        make_train("train_scannet_b4_n128", 4, 128, seed=1357, classes=21, base_num=15, G=180, wname="gfs_scannet_weights")
+    if "train_full" in todo:
+        make_train("train_scannet_b32_n2048", 32, 2048, seed=97531, classes=21, base_num=15, G=180, wname="gfs_scannet_weights",
+                   compact=True)
     if "kmeans" in todo:
         make_kmeans("kmeans_n6000_k150", 6000, 192, 150, seed=99)
         make_kmeans("kmeans_n2000_k20", 2000, 192, 20, seed=3)

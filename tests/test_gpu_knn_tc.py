@@ -94,7 +94,7 @@ def test_tc_adversarial_inputs(case):
                                               (33, 512, 1e-3, 0.0), (64, 2048, 1.0, 5.0), (9, 1024, 0.05, 3.0)])
 def test_filter_error_is_inside_the_margin(C, N, scale, offset):
     """The proof of exactness in knn_tc.cu needs |v(i,j) - D(i,j)| <= a_i + a_j for the tensor-core value v, with
-    a = 2^-15 |x~|^2 + (C+4) 2^-25 |x|^2 per point.  The diagnostic entry dumps u = v + a_j; in units of d = 2 D + const_i the
+    a = 2^-15 |x~|^2 + (2C+6) 2^-25 |x|^2 per point.  The diagnostic entry dumps u = v + a_j; in units of d = 2 D + const_i the
     requirement reads |2 (u - a_j) - d - const_i| <= 2 (a_i + a_j).  Measure it: it must stay below HALF of that."""
     ops = _ops()
     g = torch.Generator().manual_seed(C + N)
@@ -108,7 +108,7 @@ def test_filter_error_is_inside_the_margin(C, N, scale, offset):
     mu = 0.25 * ((x32[:, 0] + x32[:, N // 4]) + (x32[:, N // 2] + x32[:, 3 * (N // 4)]))       # the kernel's shift
     xc = xd - mu.double()[:, None]
     cc = (xc * xc).sum(0)
-    a = 2.0 ** -15 * cc + (C + 4) * 2.0 ** -25 * xx
+    a = 2.0 ** -15 * cc + (2 * C + 6) * 2.0 ** -25 * xx
     resid = 2.0 * (filt[0, :, :N].double() - a[None, :]) - d_true        # = |x~_i|^2 + error
     err = (resid - resid.median(dim=1, keepdim=True).values).abs()
     ratio = float((err / (2.0 * (a[:, None] + a[None, :]))).max())
@@ -145,5 +145,62 @@ def test_moderate_tie_floods_stay_on_the_fast_path():
 
 def test_tc_rejects_what_it_does_not_build():
     ops = _ops()
-    with pytest.raises(RuntimeError, match="k=21"):
-        ops.knn(torch.randn(1, 9, 128, device="cuda"), 21, impl="tc")
+    with pytest.raises(RuntimeError, match="k=41"):
+        ops.knn(torch.randn(1, 9, 128, device="cuda"), 41, impl="tc")
+
+
+def _sets_equal(a, b):
+    return torch.equal(a.sort(dim=-1).values, b.sort(dim=-1).values)
+
+
+@pytest.mark.parametrize("B,C,N,k", [(4, 64, 2048, 20), (4, 9, 2048, 20), (2, 64, 1000, 20), (3, 6, 300, 16), (1, 17, 260, 1),
+                                     (2, 64, 4096, 20), (2, 9, 320, 40), (1, 64, 1024, 40), (2, 9, 20, 20), (1, 3, 4, 1)])
+def test_set_mode_returns_the_same_neighbour_sets(B, C, N, k):
+    """gfs_knn_tc_set_f32 (bounds-classified, exact arithmetic on the undecided band only) == the ordered result as sets"""
+    ops = _ops()
+    g = torch.Generator().manual_seed(B * 1000 + C * 10 + N + 1)
+    x = (torch.randn(B, C, N, generator=g) * 0.7).cuda()
+    ref = ops.knn(x, k, impl="exact")
+    got = ops.knn(x, k, impl="tc", ordered=False)
+    torch.cuda.synchronize()
+    assert _sets_equal(ref, got)
+    assert torch.equal(O.knn_exact(x[:1].cpu(), k).sort(dim=-1).values, got[:1].cpu().sort(dim=-1).values)
+
+
+def test_set_mode_on_hard_inputs():
+    """duplicates, clusters, far-from-origin data, post-LeakyReLU features, tie floods: the set must still be the exact one
+    (exact ties at the k-th place: the lower index wins, as in the ordered kernels)"""
+    ops = _ops()
+    rng = torch.Generator().manual_seed(77)
+    for trial in range(16):
+        B, C = 2, [9, 64, 33, 12][trial % 4]
+        N = 4 * int(torch.randint(40, 600, (1,), generator=rng))
+        k = [20, 20, 7, 40][trial // 4]
+        x = torch.randn(B, C, N, generator=rng)
+        kind = trial % 4
+        if kind == 1:
+            cent = torch.randn(B, C, 8, generator=rng) * 5
+            x = cent[:, :, torch.randint(0, 8, (N,), generator=rng)] + 0.05 * x
+        elif kind == 2:
+            src = torch.randint(0, N, (N // 3,), generator=rng)
+            dst = torch.randint(0, N, (N // 3,), generator=rng)
+            x[:, :, dst] = x[:, :, src]
+        elif kind == 3:
+            x = torch.nn.functional.leaky_relu(x, 0.2) * torch.logspace(-2, 1, C).view(1, C, 1) + 30.0
+        x = x.cuda().contiguous()
+        ref = ops.knn(x, k, impl="exact")
+        got = ops.knn(x, k, impl="tc", ordered=False)
+        assert _sets_equal(ref, got), f"trial {trial}: C={C} N={N} k={k} kind={kind}"
+    x = torch.rand(1, 9, 1024, generator=rng)
+    x[:, :, 100:400] = x[:, :, 100:101]             # tie flood: repaired by the exact kernel (which writes ordered rows)
+    assert _sets_equal(ops.knn(x.cuda(), 20, impl="exact"), ops.knn(x.cuda(), 20, impl="tc", ordered=False))
+
+
+def test_tc_large_common_offset_c64():
+    """all-positive 64-channel features far from the origin relative to their spread: the fp32 term of the bound
+    dominates; the result must still be the exact one, through the filter or through the repair pass"""
+    g = torch.Generator().manual_seed(21)
+    x = (torch.rand(2, 64, 1024, generator=g) * 0.05 + 40.0)
+    (ia, da), (ib, db) = _both(x.cuda(), 20)
+    assert torch.equal(ia, ib) and torch.equal(da, db)
+    assert torch.equal(ib[:1].cpu(), O.knn_exact(x[:1], 20))
