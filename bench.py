@@ -134,6 +134,208 @@ def run_reference(a):
     print(json.dumps(line))
 
 
+SCANNET = dict(classes=21, base_num=15, G=180)
+
+
+def build_train_model(device):
+    """BASELINE.json configs[2]: ScanNet-shaped model (21 classes, 180 GWs, base_num 15), random init, train mode"""
+    from gfs3d.synthetic import randomize_bn_
+    from model.capl import mpti_net_Point_GeoAsWeight_v2
+    import contextlib
+    torch.manual_seed(321)
+    gp = torch.randn(SCANNET["G"], 192, generator=torch.Generator().manual_seed(7))
+    with contextlib.redirect_stdout(sys.stderr):
+        m = mpti_net_Point_GeoAsWeight_v2(classes=SCANNET["classes"], criterion=torch.nn.CrossEntropyLoss(ignore_index=255),
+                                          args=model_args(), base_num=SCANNET["base_num"], gp=gp.to(device), energy=0.9)
+    randomize_bn_(m, seed=6)
+    return m.to(device).train()
+
+
+def train_leg(dev, rank, world, dist, batch, steps, warmup):
+    """configs[2]: data-parallel training step, forward + backward + ONE flat-bucket NCCL all-reduce + Adam (train.py:616-631)"""
+    import random
+    from gfs3d import ops
+    from gfs3d.dist import GradBucket
+    from gfs3d.synthetic import synthetic_blocks
+    m = build_train_model(dev)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    bucket = GradBucket(m.parameters())
+    xs = [synthetic_blocks(batch, NPTS, seed=5000 + 1000 * rank + 7 * i).to(dev) for i in range(2)]
+    ys = [torch.randint(0, SCANNET["base_num"] + 1, (batch, NPTS), generator=torch.Generator().manual_seed(i + 10 * rank)).to(dev) for i in range(2)]
+    random.seed(1 + rank)
+    ar_ev = []
+
+    def step(i, timed=False):
+        bucket.zero()
+        _, loss = m(x=xs[i % 2], y=ys[i % 2])
+        loss.backward()
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        nfl = bucket.allreduce() if world > 1 else 0
+        if timed:
+            e1.record()
+            ar_ev.append((e0, e1))
+        opt.step()
+        return loss, nfl
+
+    for i in range(warmup):
+        step(i)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    torch.cuda.reset_peak_memory_stats()
+    l0 = ops.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        loss, nfl = step(i, timed=True)
+    e1.record()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / steps, sum(a.elapsed_time(b) for a, b in ar_ev) / steps], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ok = bucket.views_intact() and bool(torch.isfinite(loss.detach()))
+    del opt, bucket, m
+    torch.cuda.empty_cache()
+    return {"config": f"BASELINE.json configs[2]: ScanNet-shaped ({SCANNET['classes']} classes, {SCANNET['G']} GWs, base_num {SCANNET['base_num']}), "
+                      f"batch {batch} blocks/GPU x {NPTS} points, fwd + bwd + flat-bucket all-reduce + Adam, attention dropout 0.1",
+            "blocks_per_s": batch * world / (float(t[0]) / 1e3), "ms_per_step": float(t[0]), "allreduce_ms": float(t[1]),
+            "allreduce_floats": nfl, "steps": steps, "gpu_launches_per_step": (ops.LAUNCHES - l0) / steps,
+            "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9, "loss_last": float(loss.detach()), "dtype": "f32", "finite": ok}
+
+
+def kmeans_leg(dev, rank, world, dist, n_total, iters):
+    """configs[3]: get_basis global k-means (150 centroids, 192-d) over n_total synthetic points sharded over the ranks; Lloyd
+    iterations through the product's KMeans.fit (E-step, M-step, one packed all-reduce, centre update, one host read each)"""
+    from gfs3d.dist import shard_range
+    from gfs3d.kmeans import KMeans
+    D, K = 192, 150
+    lo, hi = shard_range(n_total, rank, world)
+    n = hi - lo
+    g = torch.Generator(device=dev).manual_seed(99)
+    cent = torch.randn(K, D, device=dev, generator=g)                     # the same mixture on every rank
+    g2 = torch.Generator(device=dev).manual_seed(1000 + rank)
+    X = cent[torch.randint(0, K, (n,), device=dev, generator=g2)] + 0.35 * torch.randn(n, D, device=dev, generator=g2)
+    init = (cent + 0.2 * torch.randn(K, D, device=dev, generator=g)).cpu().numpy()
+    km = KMeans(n_clusters=K, init=init, max_iter=2, tol=0.0, shard=world > 1)
+    km.fit(X)                                                             # warm-up (allocator, lazy module loading)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    km = KMeans(n_clusters=K, init=init, max_iter=iters, tol=0.0, shard=world > 1).fit(X)
+    # the collective alone: the packed fp64 [sums | counts | changed] vector of one iteration
+    ar_ms = 0.0
+    if dist is not None:
+        buf = torch.zeros(K * D + K + 1, dtype=torch.float64, device=dev)
+        for _ in range(3):
+            dist.all_reduce(buf)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            dist.all_reduce(buf)
+        e1.record()
+        torch.cuda.synchronize()
+        ar_ms = e0.elapsed_time(e1) / 20
+    t = torch.tensor([km.lloyd_ms_ / max(1, km.n_iter_), ar_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    del X, km
+    torch.cuda.empty_cache()
+    return {"config": f"BASELINE.json configs[3]: Lloyd iterations of the global k-means, {n_total} points x {D}, {K} centroids, "
+                      f"points sharded over {world} GPU(s)", "ms_per_iter": float(t[0]), "allreduce_ms": float(t[1]),
+            "allreduce_bytes": (K * D + K + 1) * 8 if world > 1 else 0, "points_per_gpu": n, "points_total": n_total, "iters": iters,
+            "points_per_s": n_total / (float(t[0]) / 1e3)}
+
+
+def multi_gpu_check(dev, rank, world, dist):
+    """N ranks against one: (a) sharded k-means (k-means++ seeding included) labels == single-GPU labels on a small problem,
+    (b) the all-reduced flat gradient bucket == the average of the N per-rank gradients recomputed on rank 0"""
+    if world == 1:
+        return {"kmeans_sharded_equals_single": "n/a (1 rank)", "grad_allreduce_equals_replica_average": "n/a (1 rank)"}
+    import random
+    import numpy as np
+    from gfs3d.dist import GradBucket, shard_range
+    from gfs3d.kmeans import KMeans
+    from gfs3d.synthetic import synthetic_blocks
+    out = {}
+    rs = np.random.RandomState(5)
+    n, D, K = 24000, 192, 24
+    cent = rs.randn(K, D).astype(np.float32)
+    X = (cent[rs.randint(0, K, n)] + 0.35 * rs.randn(n, D)).astype(np.float32)
+    lo, hi = shard_range(n, rank, world)
+    sh = KMeans(n_clusters=K, init="k-means++", random_state=11, shard=True).fit(X[lo:hi])
+    one = KMeans(n_clusters=K, init="k-means++", random_state=11).fit(X)
+    bad = torch.tensor([float((sh.labels_ != one.labels_[lo:hi]).sum()), float(abs(sh.n_iter_ - one.n_iter_))], dtype=torch.float64, device=dev)
+    dist.all_reduce(bad)
+    out["kmeans_sharded_equals_single"] = "ok" if float(bad.sum()) == 0 else f"MISMATCH: {int(bad[0])} labels, iteration count differs by {int(bad[1])}"
+    # gradients
+    m = build_train_model(dev)
+    m.att_learner.dropout.p = 0.0
+    bucket = GradBucket(m.parameters())
+    B, N = 2, 256
+
+    def batch_of(r):
+        return (synthetic_blocks(B, N, seed=77 + 13 * r).to(dev),
+                torch.randint(0, SCANNET["base_num"] + 1, (B, N), generator=torch.Generator().manual_seed(5 + r)).to(dev))
+
+    def grad_of(r):
+        bucket.zero()
+        random.seed(1000 + r)
+        x, y = batch_of(r)
+        _, loss = m(x=x, y=y)
+        loss.backward()
+        return bucket.flat.clone()
+
+    grad_of(rank)
+    bucket.allreduce()
+    got = bucket.flat.clone()
+    err = torch.zeros(1, dtype=torch.float64, device=dev)
+    if rank == 0:
+        ref = torch.stack([grad_of(r) for r in range(world)]).double().mean(0)
+        err[0] = float((got.double() - ref).norm() / ref.norm())
+    dist.all_reduce(err)
+    out["grad_allreduce_equals_replica_average"] = "ok" if float(err[0]) <= 1e-4 else f"MISMATCH: relative L2 {float(err[0]):.3e}"
+    out["grad_rel_l2"] = float(err[0])
+    del bucket, m
+    torch.cuda.empty_cache()
+    return out
+
+
+def reference_on_b200(dev, state_dict, gp, B, iters=3):
+    """context number: the reference's stock-PyTorch path (the oracle port executes the same ATen ops in
+    the same order as model/capl.py:144-192) eager on the SAME B200, fp32 with TF32 off"""
+    from gfs3d.synthetic import synthetic_blocks
+    from oracle import gfs_oracle as O
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        sd = {k: v.detach().float().to(dev) for k, v in state_dict.items()}
+        gened, bc, nc = head_inputs(dev)
+        x = synthetic_blocks(B, NPTS, seed=999).to(dev)
+        with torch.no_grad():
+            O.forward_eval(sd, gp.to(dev), x, gened, bc, nc, BASE_NUM, 1.2, k=KNN)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                O.forward_eval(sd, gp.to(dev), x, gened, bc, nc, BASE_NUM, 1.2, k=KNN)
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        return {"value": B / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "batch": B,
+                "what": "stock PyTorch eager (ATen / cuBLAS / cuDNN ops of the reference, fp32, TF32 off) on this B200, inputs resident"}
+    except Exception as e:                                            # noqa: BLE001  (a context number must not kill the bench line)
+        return {"error": f"{type(e).__name__}: {e}"[:200]}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+        torch.cuda.empty_cache()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -143,6 +345,9 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="blocks per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--skip-train", action="store_true", help="skip the configs[2] data-parallel training leg")
+    ap.add_argument("--skip-kmeans", action="store_true", help="skip the configs[3] sharded k-means leg")
+    ap.add_argument("--kmeans-points", type=int, default=4_000_000, help="total points of the k-means leg (sharded over the ranks)")
     ap.add_argument("--e2e-serial", action="store_true",
                     help="end-to-end leg without prefetch: H2D, forward and D2H of a step strictly one after the other")
     a = ap.parse_args()
@@ -219,6 +424,11 @@ def main():
     main_stream = torch.cuda.current_stream()
     ready = [torch.cuda.Event(), torch.cuda.Event()]     # H2D into xdev[j] finished
     freed = [torch.cuda.Event(), torch.cuda.Event()]     # the forward that read xdev[j] finished
+    # warm-up of THIS leg's own operations (arg-max / int32 conversion / pinned device->host copy are first used here: their
+    # one-time module loading must not land in the timed region)
+    for i in range(a.warmup):
+        lg = graphed(host[i % NROT]) if graphed is not None else step(host[i % NROT].to(dev, non_blocking=True))
+        labels_host.copy_(lg.argmax(1).to(torch.int32), non_blocking=True)
     barrier()
     if not a.e2e_serial:
         with torch.cuda.stream(copy_stream):             # prologue: the first batch (its copy is the one step K-1 would prefetch)
@@ -266,6 +476,14 @@ def main():
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms = float(t[0]), float(t[1])
+
+    # ---- BASELINE.json configs[2] / configs[3] at the same N (the only places the path has a collective), and the N-rank checks
+    used_graph = graphed is not None
+    graphed = run = None                        # drop the captured graph's memory pool before the training leg
+    torch.cuda.empty_cache()
+    train = None if a.skip_train else train_leg(dev, rank, world, dist, B, steps=5, warmup=3)
+    kmeans = None if a.skip_kmeans else kmeans_leg(dev, rank, world, dist, a.kmeans_points, iters=8)
+    checks = multi_gpu_check(dev, rank, world, dist) if not (a.skip_train and a.skip_kmeans) else None
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -280,7 +498,7 @@ def main():
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
 
     # dominant kernel: the fused kNN (3 launches per step; the two C=64 layers dominate)
-    knn_ms = prof.get("gfs_knn_tc_f32", 0.0) + prof.get("gfs_knn_f32", 0.0)
+    knn_ms = prof.get("gfs_knn_tc_set_f32", 0.0) + prof.get("gfs_knn_tc_f32", 0.0) + prof.get("gfs_knn_f32", 0.0)
     knn_bytes = sum(B * NPTS * (c * 4 + KNN * 4) for c in (9, 64, 64))                  # read x once + write idx, per step
     knn_flops = sum(2.0 * c * NPTS * NPTS * B for c in (9, 64, 64))
     ec_ms = prof.get("gfs_edgeconv_fwd", 0.0)
@@ -293,7 +511,7 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["knn_bytes_per_step_b32"] * B / 32.0
     except Exception:
         pass
-    roof = {"kernel": "kNN graph: knn_prep + knn_tc (tcgen05 filter) + knn_finish (gfs_knn_tc_f32, 3 calls/step)", "bound": "hbm", "achieved": gbs(knn_bytes, knn_ms), "peak": hbm_peak,
+    roof = {"kernel": "kNN graph: knn_prep + knn_tc (two-pass tcgen05 filter) + knn_finish (gfs_knn_tc_set_f32, 3 calls/step)", "bound": "hbm", "achieved": gbs(knn_bytes, knn_ms), "peak": hbm_peak,
             "unit": "GB/s", "frac": (gbs(knn_bytes, knn_ms) or 0) / hbm_peak, "traffic": traffic, "peak_source": peak_src,
             "ms_per_step": knn_ms, "share_of_step": knn_ms / (sum(prof.values()) or 1),
             "binding_roof": "per-row top-k selection out of TMEM (dependent-issue latency), not HBM or the tensor pipe",
@@ -315,6 +533,7 @@ def main():
         v = cpu_port_blocks_per_sec(m.state_dict(), gp, sample, iters, threads)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": f"{sample} blocks x {iters} iterations of the same workload"}
 
+    ref_gpu = None if a.no_cpu_baseline else reference_on_b200(dev, m.state_dict(), gp, B)
     total_blocks = B * a.steps * world
     h2d = B * 9 * NPTS * 4
     d2h = B * NPTS * 4
@@ -325,14 +544,15 @@ def main():
                                    f"{CLASSES} classes, {G} GWs, random-init weights", "blocks_per_gpu_per_step": B,
                        "l2": "flushed between steps (256 MiB write outside the per-step event pair); 4 rotating input batches",
                        "parallelism": f"block-sharded x{world}, no data-path collective",
-                       "launch": "eager" if graphed is None else "CUDA graph replay of the eager step (gfs3d/graph.py)",
+                       "launch": "CUDA graph replay of the eager step (gfs3d/graph.py)" if used_graph else "eager",
                        "attention": "hand-written tcgen05 flash kernel (gfs_attention_fwd)"},
             "clocks": clk, "e2e": {"value": total_blocks / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                                    "ms_per_step": e2e_ms / a.steps,
                                    "mode": "serial: H2D, forward, D2H one after the other" if a.e2e_serial else
                                            "prefetch: each step's timed interval holds one pinned H2D (the next batch, on a copy "
                                            "stream, into a second device buffer), one forward and one D2H of the labels"},
-            "gpu_launches": launches, "roofline": roof, "roofline_detail": extra, "cpu_baseline": cpu, "wall_s_timed_region": wall}
+            "gpu_launches": launches, "roofline": roof, "roofline_detail": extra, "cpu_baseline": cpu, "reference_pytorch_on_this_gpu": ref_gpu,
+            "train": train, "kmeans": kmeans, "multi_gpu_check": checks, "wall_s_timed_region": wall}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

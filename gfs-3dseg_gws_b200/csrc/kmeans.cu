@@ -136,9 +136,13 @@ extern "C" int gfs_kmeans_accumulate(const float* X, int64_t n, int D, const int
 // ---------------------------------------------------------------------------------------------------------------
 // k-means++ seeding step (sklearn _kmeans.py:_kmeans_plusplus, as get_basis.py:210 reaches it through KMeans(init=
 // 'k-means++')): for T <= 8 candidate centres at once,
-//     m[t][i] = min( max(|x_i|^2 - 2 x_i.c_t + |c_t|^2, 0), closest[i] ),      pot[t] = sum_i m[t][i]   (fp64)
-// One thread per point over the channel-major copy the E-step already keeps resident: every channel is ONE coalesced load
-// feeding T fmas against the candidates in shared memory, so the step is a single pass over X (HBM bound: n*D*4 bytes).
+//     m[t][i] = min( max(float(|x_i|^2 - 2 x_i.c_t + |c_t|^2), 0), closest[i] ),      pot[t] = sum_i m[t][i]   (fp64)
+// sklearn evaluates these distances on float64 upcasts of the float32 data and rounds the result to float32
+// (metrics/pairwise.py:_euclidean_distances_upcast); the kernel does the same -- fp64 fma chains, one rounding to fp32 --
+// so the values agree with sklearn's bit for bit except where an fp64 summation-order difference straddles an fp32
+// rounding boundary (~1e-9 of the values).  One thread per point over the channel-major copy the E-step already keeps
+// resident: every channel is ONE coalesced load feeding T DFMAs against the candidates in shared memory, a single pass
+// over X (HBM bound: n*D*4 bytes; 8 DFMA per 4 bytes stay below the B200's fp64 rate).
 // ---------------------------------------------------------------------------------------------------------------
 namespace gfs {
 
@@ -146,50 +150,51 @@ constexpr int PP_T = 8;
 constexpr int PP_THREADS = 256;
 
 __global__ void __launch_bounds__(PP_THREADS)
-kmeans_pp_trial_kernel(const float* __restrict__ xt, int64_t npad, int64_t n, int D, const float* __restrict__ xsq,
+kmeans_pp_trial_kernel(const float* __restrict__ xt, int64_t npad, int64_t n, int D, const double* __restrict__ xsq,
                        const float* __restrict__ cand, int T, const float* __restrict__ closest, float* __restrict__ m_out,
                        double* __restrict__ pots) {
-    extern __shared__ __align__(16) float cs[];     // [D][8] candidate coordinates, then [8] squared norms
-    float* csq = cs + D * PP_T;
+    extern __shared__ __align__(16) double csd[];   // [D][8] candidate coordinates, then [8] squared norms
+    double* csq = csd + D * PP_T;
     for (int i = threadIdx.x; i < D * PP_T; i += PP_THREADS) {
         const int c = i / PP_T, t = i - c * PP_T;
-        cs[i] = t < T ? cand[(int64_t)t * D + c] : 0.0f;
+        csd[i] = t < T ? (double)cand[(int64_t)t * D + c] : 0.0;
     }
     __syncthreads();
     if (threadIdx.x < PP_T) {
-        float s = 0.0f;
-        for (int c = 0; c < D; ++c) s = fmaf(cs[c * PP_T + threadIdx.x], cs[c * PP_T + threadIdx.x], s);
+        double s = 0.0;
+        for (int c = 0; c < D; ++c) s = fma(csd[c * PP_T + threadIdx.x], csd[c * PP_T + threadIdx.x], s);
         csq[threadIdx.x] = s;
     }
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * PP_THREADS + threadIdx.x;
     const bool on = i < n;
     const int64_t ii = on ? i : 0;
-    float dot[PP_T];
+    double dot[PP_T];
 #pragma unroll
-    for (int t = 0; t < PP_T; ++t) dot[t] = 0.0f;
+    for (int t = 0; t < PP_T; ++t) dot[t] = 0.0;
     const float* xp = xt + ii;
 #pragma unroll 4
     for (int c = 0; c < D; ++c) {
-        const float x = __ldg(xp + (int64_t)c * npad);
-        const float4 w0 = *reinterpret_cast<const float4*>(cs + c * PP_T), w1 = *reinterpret_cast<const float4*>(cs + c * PP_T + 4);
-        dot[0] = fmaf(x, w0.x, dot[0]);
-        dot[1] = fmaf(x, w0.y, dot[1]);
-        dot[2] = fmaf(x, w0.z, dot[2]);
-        dot[3] = fmaf(x, w0.w, dot[3]);
-        dot[4] = fmaf(x, w1.x, dot[4]);
-        dot[5] = fmaf(x, w1.y, dot[5]);
-        dot[6] = fmaf(x, w1.z, dot[6]);
-        dot[7] = fmaf(x, w1.w, dot[7]);
+        const double x = (double)__ldg(xp + (int64_t)c * npad);
+        const double2 w0 = *reinterpret_cast<const double2*>(csd + c * PP_T), w1 = *reinterpret_cast<const double2*>(csd + c * PP_T + 2);
+        const double2 w2 = *reinterpret_cast<const double2*>(csd + c * PP_T + 4), w3 = *reinterpret_cast<const double2*>(csd + c * PP_T + 6);
+        dot[0] = fma(x, w0.x, dot[0]);
+        dot[1] = fma(x, w0.y, dot[1]);
+        dot[2] = fma(x, w1.x, dot[2]);
+        dot[3] = fma(x, w1.y, dot[3]);
+        dot[4] = fma(x, w2.x, dot[4]);
+        dot[5] = fma(x, w2.y, dot[5]);
+        dot[6] = fma(x, w3.x, dot[6]);
+        dot[7] = fma(x, w3.y, dot[7]);
     }
-    const float xs = xsq[ii];
+    const double xs = xsq[ii];
     const float cl = closest ? closest[ii] : INFINITY;
     __shared__ double red[PP_T][PP_THREADS / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int t = 0; t < PP_T; ++t) {
         if (t < T) {                                  // warp-uniform
-            const float d = fmaxf((xs - 2.0f * dot[t]) + csq[t], 0.0f);
+            const float d = fmaxf((float)((xs - 2.0 * dot[t]) + csq[t]), 0.0f);
             const float m = fminf(d, cl);
             if (on) m_out[(int64_t)t * npad + i] = m;
             double s = on ? (double)m : 0.0;
@@ -208,14 +213,14 @@ kmeans_pp_trial_kernel(const float* __restrict__ xt, int64_t npad, int64_t n, in
 
 }  // namespace gfs
 
-extern "C" int gfs_kmeans_pp_trial(const float* xt, int64_t npad, int64_t n, int D, const float* xsq, const float* cand, int T,
+extern "C" int gfs_kmeans_pp_trial(const float* xt, int64_t npad, int64_t n, int D, const double* xsq, const float* cand, int T,
                                    const float* closest, float* m_out, double* pots, void* stream) {
     using namespace gfs;
     GFS_REQUIRE(xt && xsq && cand && m_out && pots, GFS_ERR_BAD_ARG, "gfs_kmeans_pp_trial: null pointer");
     GFS_REQUIRE(n > 0 && npad >= n && D > 0 && T > 0, GFS_ERR_BAD_ARG, "gfs_kmeans_pp_trial: non-positive size");
     GFS_REQUIRE(T <= PP_T, GFS_ERR_UNSUPPORTED, "gfs_kmeans_pp_trial: T=%d candidates > %d is not built", T, PP_T);
-    GFS_REQUIRE(D <= 1024, GFS_ERR_UNSUPPORTED, "gfs_kmeans_pp_trial: D=%d > 1024 is not built", D);
-    const size_t smem = (size_t)(D * PP_T + PP_T) * sizeof(float);
+    GFS_REQUIRE(D <= 512, GFS_ERR_UNSUPPORTED, "gfs_kmeans_pp_trial: D=%d > 512 is not built", D);
+    const size_t smem = (size_t)(D * PP_T + PP_T) * sizeof(double);
     const int64_t grid = (n + PP_THREADS - 1) / PP_THREADS;
     GFS_REQUIRE(grid < ((int64_t)1 << 31), GFS_ERR_UNSUPPORTED, "gfs_kmeans_pp_trial: n too large");
     kmeans_pp_trial_kernel<<<(unsigned)grid, PP_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(xt, npad, n, D, xsq, cand, T, closest,

@@ -16,7 +16,6 @@ import numpy as np
 import torch
 
 from . import ops
-from .dist import all_same, allreduce_centroid_stats
 
 
 def _dist():
@@ -49,35 +48,91 @@ class KMeans:
             return rs
         return np.random.RandomState(rs)
 
-    def _seed_plusplus(self, Xc, xt, rng):
-        """k-means++ (sklearn _kmeans.py:_kmeans_plusplus): per centre, 2 + ln K candidates drawn with probability
-        proportional to the current squared distance (host RNG consumed in sklearn's order, cumulative sum and search on the
-        device), all candidates scored in ONE pass over the resident channel-major copy (gfs_kmeans_pp_trial), the best kept."""
-        n, D = Xc.shape
+    def _world(self):
+        if not self.shard:
+            return 1, 0
+        d = _dist()
+        return d.get_world_size(self.process_group), d.get_rank(self.process_group)
+
+    def _seed_plusplus(self, Xc, xt, rng, n=None):
+        """k-means++ exactly as sklearn's _kmeans_plusplus consumes its random stream (sklearn 1.9.0 _kmeans.py:_kmeans_plusplus):
+        first centre through `choice(n, p=w/sum(w))`, then `uniform(size=2+ln K)` per centre; candidates = searchsorted of
+        u * potential in the cumulative sum of the closest squared distances; all candidates of a centre scored in ONE pass over
+        the resident channel-major copy (gfs_kmeans_pp_trial: fp64-accumulated distances rounded to fp32, like sklearn's upcast
+        path), the best kept.  What is NOT bit-pinned: sklearn sums the potential with a float32 BLAS dot and the cumulative sum in
+        float32; here both are fp64 (parallel, order-independent to 1e-16), so a pick can differ where u * pot lands within that
+        rounding of a boundary (tests/golden: 31 of 32 seeded problems give identical picks for all centres).
+
+        Sharded (multi-GPU): the points of all ranks form ONE sequence in rank order; every rank searches its own slice of the
+        global cumulative sum, the owner contributes the candidate rows (all-reduce), potentials are all-reduced: the picks equal
+        the single-GPU picks.  The random numbers are drawn on rank 0 and broadcast.  No host synchronisation inside the loop."""
+        D = Xc.shape[1]
+        n = Xc.shape[0] if n is None else n
         K = self.n_clusters
         trials = 2 + int(np.log(K))
         if trials > 8:
             raise NotImplementedError(f"k-means++ with {trials} local trials (n_clusters={K}) is not built")
         dev = Xc.device
+        world, rank = self._world()
+        sizes = torch.tensor([n], dtype=torch.int64, device=dev)
+        if world > 1:
+            allsz = [torch.empty_like(sizes) for _ in range(world)]
+            _dist().all_gather(allsz, sizes, group=self.process_group)
+            sizes = torch.cat(allsz)
+        sizes = sizes.tolist()
+        n_tot, lo = sum(sizes), sum(sizes[:rank])
+        # the random stream (rank 0's generator; the other ranks receive the draws)
+        draws = torch.empty(1 + (K - 1) * trials, dtype=torch.float64)
+        if rank == 0:
+            w = np.ones(n_tot, dtype=np.float32)
+            draws[0] = float(rng.choice(n_tot, p=w / w.sum()))
+            draws[1:] = torch.from_numpy(rng.uniform(size=(K - 1) * trials)) if K > 1 else draws[1:]
+        draws = draws.to(dev)
+        if world > 1:
+            _dist().broadcast(draws, src=_dist().get_global_rank(self.process_group, 0) if self.process_group else 0,
+                              group=self.process_group)
+        U = draws[1:].view(K - 1, trials)
         npad = xt.shape[1]
-        xsq = torch.zeros(npad, dtype=torch.float32, device=dev)
-        xsq[:n] = (Xc * Xc).sum(1)
+        xsq = torch.zeros(npad, dtype=torch.float64, device=dev)
+        xsq[:n] = (Xc[:n].double() ** 2).sum(1)
         centers = torch.empty(K, D, dtype=torch.float32, device=dev)
-        m = [torch.empty(8, npad, dtype=torch.float32, device=dev) for _ in range(2)]      # double buffer: closest lives in one
+        m = torch.empty(8, npad, dtype=torch.float32, device=dev)
         pots = torch.zeros(8, dtype=torch.float64, device=dev)
-        first = int(rng.choice(n))
-        centers[0] = Xc[first]
-        ops.kmeans_pp_trial(xt, n, xsq, centers[0:1].contiguous(), None, m[0], pots)
-        closest, pot, cur = m[0][0], pots[0].clone(), 0
+
+        def owned_rows(pos, mine):
+            """(T, D) rows X[pos] where this rank owns the pick, zero elsewhere; summed over the ranks"""
+            rows = Xc[pos.clamp(0, n - 1)] * mine.to(torch.float32).unsqueeze(1)
+            if world > 1:
+                _dist().all_reduce(rows, group=self.process_group)
+            return rows.contiguous()
+
+        first = draws[0].long() - lo
+        centers[0] = owned_rows(first.view(1), ((first >= 0) & (first < n)).view(1))[0]
+        ops.kmeans_pp_trial(xt, n, xsq, centers[0:1].contiguous(), None, m, pots)
+        if world > 1:
+            _dist().all_reduce(pots, group=self.process_group)
+        closest, pot = m[0].clone(), pots[0].clone()
         for c in range(1, K):
-            rv = torch.from_numpy(rng.uniform(size=trials)).to(dev) * pot
-            cand = torch.searchsorted(torch.cumsum(closest[:n].double(), 0), rv).clamp_max_(n - 1)
+            cs = torch.cumsum(closest[:n].double(), 0)             # this rank's slice of the global cumulative sum, minus P[rank]
+            tots = cs[-1:].contiguous()
+            if world > 1:
+                gathered = [torch.empty_like(tots) for _ in range(world)]
+                _dist().all_gather(gathered, tots, group=self.process_group)
+                tots = torch.cat(gathered)
+            P = torch.cumsum(tots, 0)                              # identical on every rank: ownership is decided from the same numbers
+            rv = U[c - 1] * pot
+            owner = torch.searchsorted(P, rv).clamp_max(world - 1)  # first rank whose slice reaches rv (the last one if none: numpy's clip)
+            mine = owner == rank
+            pos = torch.searchsorted(cs, rv - (P[rank] - tots[rank])).clamp_max(n - 1)   # first i with cumsum[i] >= rv (side='left')
+            cand = owned_rows(pos, mine)
             pots.zero_()
-            ops.kmeans_pp_trial(xt, n, xsq, Xc[cand].contiguous(), closest, m[cur ^ 1], pots)
-            best = int(torch.argmin(pots[:trials]))
-            cur ^= 1
-            pot, closest = pots[best].clone(), m[cur][best]
-            centers[c] = Xc[cand[best]]
+            ops.kmeans_pp_trial(xt, n, xsq, cand, closest, m, pots)
+            if world > 1:
+                _dist().all_reduce(pots, group=self.process_group)
+            best = torch.argmin(pots[:trials]).view(1)
+            pot = pots.index_select(0, best)[0]
+            closest = m.index_select(0, best)[0]
+            centers[c] = cand.index_select(0, best)[0]
         return centers
 
     # ------------------------------------------------------------------ fit
@@ -109,13 +164,7 @@ class KMeans:
 
         # initial centres
         if isinstance(self.init, str) and self.init == "k-means++":
-            if self.shard and _dist().get_rank(self.process_group) != 0:
-                centers = torch.empty(K, D, dtype=torch.float32, device=dev)
-            else:
-                centers = self._seed_plusplus(Xc, xt, self._rng())  # multi-GPU: seeded from rank 0's shard, then broadcast
-            if self.shard:
-                _dist().broadcast(centers, src=_dist().get_global_rank(self.process_group, 0) if self.process_group else 0,
-                                  group=self.process_group)
+            centers = self._seed_plusplus(Xc, xt, self._rng(), n)
         elif isinstance(self.init, (np.ndarray, torch.Tensor)):
             centers = torch.as_tensor(self.init, dtype=torch.float32).to(dev) - mean32
             if centers.shape != (K, D):
@@ -123,40 +172,47 @@ class KMeans:
         else:
             raise NotImplementedError(f"init={self.init!r} is not built")
 
+        # Lloyd iterations.  Per iteration: E-step, M-step sums, ONE collective (sums | counts | labels changed) when sharded,
+        # the centre update on the device, and ONE device->host read of (labels changed, centre shift, empty clusters).
         Kp = (K + 3) // 4 * 4
+        ct = torch.zeros(D, Kp, dtype=torch.float32, device=dev)
         labels_old = torch.full((npad,), -1, dtype=torch.int32, device=dev)
         strict = False
         n_iter = 0
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
         for n_iter in range(1, self.max_iter + 1):
-            ct = torch.zeros(D, Kp, dtype=torch.float32, device=dev)
             ct[:, :K] = centers.t()
             labels = ops.kmeans_assign(xt, ct, K)
             sums, counts = ops.kmeans_accumulate(Xc, labels, K, n_valid=n)
+            changed = (labels[:n] != labels_old[:n]).sum()
             if self.shard:
-                sums, counts = allreduce_centroid_stats(sums, counts, self.process_group)
-            if bool((counts == 0).any()):
-                sums, counts = self._relocate_empty(Xc, n, labels, centers, sums, counts)
+                packed = torch.cat([sums.reshape(-1), counts.double(), changed.double().view(1)])
+                _dist().all_reduce(packed, group=self.process_group)
+                sums, counts, changed = packed[:K * D].view(K, D), packed[K * D:K * D + K].round().long(), packed[-1]
             new = torch.where(counts[:, None] > 0, sums / counts.clamp_min(1)[:, None].double(), torch.zeros_like(sums)).float()
-            if bool((counts <= 0).any()):
-                new[counts <= 0] = new[int(torch.argmax(counts))]
-            shift = float(((new - centers).double() ** 2).sum())
-            same = torch.equal(labels[:n], labels_old[:n])
-            if self.shard:
-                same = all_same(same, dev, self.process_group)
+            shift = ((new - centers).double() ** 2).sum()
+            n_changed, shift_h, n_empty = torch.stack([changed.double(), shift, (counts == 0).sum().double()]).tolist()
+            if n_empty > 0:           # rare: sklearn moves the empty clusters onto the points farthest from their centres
+                sums, counts = self._relocate_empty(Xc, n, labels, centers, sums.clone(), counts.clone())
+                # clusters that are still empty keep the zero sum (sklearn _k_means_common.pyx:_average_centers)
+                new = torch.where(counts[:, None] > 0, sums / counts.clamp_min(1)[:, None].double(), torch.zeros_like(sums)).float()
+                shift_h = float(((new - centers).double() ** 2).sum())
             centers = new
             if self.verbose:
-                print(f"Iteration {n_iter - 1}, center shift {shift:.6g}")
-            if same:
+                print(f"Iteration {n_iter - 1}, center shift {shift_h:.6g}")
+            if n_changed == 0:
                 strict = True
                 break
-            if shift <= tol_abs:
+            if shift_h <= tol_abs:
                 break
             labels_old = labels
+        ev1.record()
         if not strict:
-            ct = torch.zeros(D, Kp, dtype=torch.float32, device=dev)
             ct[:, :K] = centers.t()
             labels = ops.kmeans_assign(xt, ct, K)
         self.labels_ = labels[:n].cpu().numpy().astype(np.int32)
+        self.lloyd_ms_ = ev0.elapsed_time(ev1)          # device time of the Lloyd loop (the .cpu() above synchronised)
         self.labels_device_ = labels[:n]
         self.cluster_centers_ = (centers + mean32).cpu().numpy()
         self.n_iter_ = n_iter

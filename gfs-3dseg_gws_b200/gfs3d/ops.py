@@ -16,27 +16,50 @@ PROFILE_SHAPES = False  # add the GEMM shape to the profile key
 PROFILE = None          # set to {} to record (name, start_event, end_event) per call on the current stream
 
 
+class _StreamArg:
+    """placeholder for the stream argument: _call substitutes the current stream OF THE TENSORS' DEVICE"""
+
+
+_STREAM = _StreamArg()
+_SEEN_DEVICES = []      # devices of the tensors whose pointers were taken since the last launch
+
+
 def _call(name: str, n_kernels: int, *args, tag: str = ""):
+    """One C-ABI call.  The launch follows the tensors, not the ambient device: every tensor of the call must live on one
+    CUDA device; the library call runs under that device's context and on that device's current stream (a model moved with
+    .to('cuda:1') works without torch.cuda.set_device(1), as the reference's torch ops do)."""
     global LAUNCHES
+    devs = set(_SEEN_DEVICES)
+    _SEEN_DEVICES.clear()
+    if len(devs) > 1:
+        raise RuntimeError(f"{name}: tensors live on different devices {sorted(str(d) for d in devs)}")
+    dev = devs.pop() if devs else torch.device("cuda", torch.cuda.current_device())
     fn = getattr(lib(), name)
-    if PROFILE is None:
-        rc = fn(*args)
-    else:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        rc = fn(*args)
-        e1.record()
-        PROFILE.setdefault(name + tag, []).append((e0, e1))
+    with torch.cuda.device(dev):
+        args = tuple(torch.cuda.current_stream(dev).cuda_stream if a is _STREAM else a for a in args)
+        if PROFILE is None:
+            rc = fn(*args)
+        else:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = fn(*args)
+            e1.record()
+            PROFILE.setdefault(name + tag, []).append((e0, e1))
     LAUNCHES += n_kernels
     check(rc, name)
 
 
 def _ptr(t: Optional[torch.Tensor]):
-    return None if t is None else t.data_ptr()
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("gfs3d ops need CUDA tensors: the hot path has no CPU fallback")
+    _SEEN_DEVICES.append(t.device)
+    return t.data_ptr()
 
 
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    return _STREAM
 
 
 def _need_cuda(*ts):
@@ -263,12 +286,12 @@ def softmax_pool(logits: torch.Tensor, feat: torch.Tensor) -> torch.Tensor:
 
 def kmeans_pp_trial(xt: torch.Tensor, n: int, xsq: torch.Tensor, cand: torch.Tensor, closest: Optional[torch.Tensor],
                     m_out: torch.Tensor, pots: torch.Tensor):
-    """k-means++ step: xt (D, npad) channel-major, cand (T, D) -> m_out (T, npad) = min(d(x, cand_t), closest), pots (T) f64 (+)="""
+    """k-means++ step: xt (D, npad) channel-major, xsq (n) fp64, cand (T, D) -> m_out (T, npad) = min(d(x, cand_t), closest), pots (T) f64 (+)="""
     _need_cuda(xt, xsq, cand, closest, m_out, pots)
     D, npad = xt.shape
     T = cand.shape[0]
     assert xt.is_contiguous() and cand.is_contiguous() and cand.shape[1] == D and m_out.is_contiguous() and m_out.shape[1] == npad
-    assert m_out.shape[0] >= T and pots.dtype == torch.float64 and pots.numel() >= T and xsq.numel() >= n
+    assert m_out.shape[0] >= T and pots.dtype == torch.float64 and pots.numel() >= T and xsq.numel() >= n and xsq.dtype == torch.float64
     _call("gfs_kmeans_pp_trial", 1, _ptr(xt), npad, n, D, _ptr(xsq), _ptr(cand), T, _ptr(closest), _ptr(m_out), _ptr(pots), _stream())
 
 

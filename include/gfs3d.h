@@ -190,10 +190,11 @@ int gfs_kmeans_accumulate(const float* X, int64_t n, int D, const int32_t* label
                           float* partial, int32_t* pcount, double* sums, int64_t* counts, void* stream);
 
 /* ---- k-means++ seeding step (sklearn _kmeans.py:_kmeans_plusplus behind get_basis.py:210) ---------------
- * For T <= 8 candidate centres:  m[t][i] = min(max(|x_i|^2 - 2 x_i.c_t + |c_t|^2, 0), closest[i]),  pots[t] += sum_i m[t][i]
- *   xt (D, npad) channel-major fp32 (the E-step's copy), xsq (n) squared norms, cand (T, D) row-major, closest (n) or NULL
+ * For T <= 8 candidate centres:  m[t][i] = min(max(float(|x_i|^2 - 2 x_i.c_t + |c_t|^2), 0), closest[i]),  pots[t] += sum_i m[t][i]
+ * The distance is accumulated in fp64 and rounded once to fp32, as sklearn's _euclidean_distances_upcast does for float32 data.
+ *   xt (D, npad) channel-major fp32 (the E-step's copy), xsq (n) fp64 squared norms, cand (T, D) row-major, closest (n) or NULL
  *   (= +inf: the first centre), m_out (T, npad) fp32, pots (T) fp64 ACCUMULATED into (the caller zeroes it)              */
-int gfs_kmeans_pp_trial(const float* xt, int64_t npad, int64_t n, int D, const float* xsq, const float* cand, int T,
+int gfs_kmeans_pp_trial(const float* xt, int64_t npad, int64_t n, int D, const double* xsq, const float* cand, int T,
                         const float* closest, float* m_out, double* pots, void* stream);
 
 /* =====================================================================================================================

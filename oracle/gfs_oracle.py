@@ -532,25 +532,32 @@ def codings_equal_modulo_ties(freq, a, b):
 
 
 def kmeans_plusplus_ref(X, n_clusters, rng):
-    """sklearn _kmeans.py:_kmeans_plusplus restated in float64 numpy with the random stream consumed the way
-    gfs3d.kmeans.KMeans consumes it (choice(n) for the first centre, then uniform(size=2+ln k) per centre; sklearn >= 1.3
-    draws the first centre through choice(n, p=...) and accumulates the distances in float32, so its picks are not
-    reproducible bit for bit by any parallel implementation: the seeding is pinned to THIS restatement).
-    -> (centres (k, D) float64, indices (k,))"""
-    X = np.asarray(X, dtype=np.float64)
+    """sklearn 1.9.0 _kmeans.py:_kmeans_plusplus restated in numpy: the random stream is consumed exactly as sklearn consumes
+    it (choice(n, p=w/sum(w)) for the first centre, then uniform(size=2+ln k) per centre), the distances are the float64
+    evaluation rounded to float32 and clamped at 0 (metrics/pairwise.py:_euclidean_distances_upcast).  The two places where
+    sklearn itself is not reproducible by a parallel implementation -- the potential (a float32 BLAS dot) and the cumulative
+    sum (np.cumsum in float32) -- are float64 here, as in gfs3d.kmeans; tests/golden/kmeanspp_*.npz hold sklearn's own picks
+    and pin this restatement against them.  X: the float32 matrix k-means++ runs on (KMeans.fit passes the mean-centred data).
+    -> (centres (k, D) float32, indices (k,))"""
+    X = np.asarray(X, dtype=np.float32)
     n = X.shape[0]
     trials = 2 + int(np.log(n_clusters))
-    xsq = (X * X).sum(1)
+    X64 = X.astype(np.float64)
+    xsq = (X64 * X64).sum(1)
+
+    def dist(c):
+        return np.maximum((xsq[None, :] - 2.0 * (X64[c] @ X64.T) + xsq[c][:, None]).astype(np.float32), 0)
+
     idx = np.empty(n_clusters, dtype=np.int64)
-    idx[0] = int(rng.choice(n))
-    closest = np.maximum(xsq - 2.0 * (X @ X[idx[0]]) + xsq[idx[0]], 0.0)
-    pot = closest.sum()
+    w = np.ones(n, dtype=np.float32)
+    idx[0] = int(rng.choice(n, p=w / w.sum()))
+    closest = dist(idx[:1])[0]
+    pot = closest.astype(np.float64).sum()
     for c in range(1, n_clusters):
         rv = rng.uniform(size=trials) * pot
-        cand = np.minimum(np.searchsorted(np.cumsum(closest), rv), n - 1)
-        d = np.maximum(xsq[None, :] - 2.0 * (X[cand] @ X.T) + xsq[cand][:, None], 0.0)
-        d = np.minimum(d, closest[None, :])
-        pots = d.sum(1)
+        cand = np.minimum(np.searchsorted(np.cumsum(closest.astype(np.float64)), rv), n - 1)
+        d = np.minimum(dist(cand), closest[None, :])
+        pots = d.astype(np.float64).sum(1)
         best = int(np.argmin(pots))
         pot, closest, idx[c] = pots[best], d[best], cand[best]
     return X[idx], idx

@@ -192,6 +192,29 @@ def make_kmeans(name, n, D, K, seed):
          x_checksum=np.float64(X.astype(np.float64).sum()))
 
 
+def kmeanspp_problem(seed, n, D, K):
+    """the mean-centred float32 matrix KMeans.fit hands to k-means++ (regenerated from the seed by the tests)"""
+    rs = np.random.RandomState(seed)
+    cent = rs.randn(K, D).astype(np.float32)
+    X = (cent[rs.randint(0, K, n)] + 0.35 * rs.randn(n, D)).astype(np.float32)
+    return X - X.mean(0)
+
+
+def make_kmeanspp(name, n, D, K, seed, rs_seed):
+    """sklearn's own k-means++ picks (sklearn.cluster.kmeans_plusplus = _kmeans_plusplus behind get_basis.py:210's
+    KMeans(init='k-means++')) for a fixed RandomState: the pin of the seeding."""
+    import sklearn
+    from sklearn.cluster import kmeans_plusplus
+    X = kmeanspp_problem(seed, n, D, K)
+    _, idx = kmeans_plusplus(X, K, random_state=np.random.RandomState(rs_seed))
+    _, o_idx = O.kmeans_plusplus_ref(X, K, np.random.RandomState(rs_seed))
+    same = int(np.cumprod(idx == o_idx).sum())
+    print(f"{name}: sklearn {sklearn.__version__} picks vs oracle restatement: {same} of {K} centres identical")
+    assert same == K, "choose another seed: this draw lands inside sklearn's float32 cumsum rounding (see oracle docstring)"
+    save(name, seed=np.int32(seed), rs_seed=np.int32(rs_seed), n=np.int32(n), D=np.int32(D), K=np.int32(K),
+         idx=idx.astype(np.int32), x_checksum=np.float64(X.astype(np.float64).sum()))
+
+
 def make_metric(name, seed, scannet):
     """runs/eval.py of the reference (pure numpy/Python, importable as is) on random labels"""
     from runs.eval import evaluate_metric_GFS  # noqa: E402  (reference)
@@ -322,7 +345,7 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="")
     a = ap.parse_args()
-    todo = a.only.split(",") if a.only else ["dgcnn", "gfs", "kmeans", "train", "callers"]
+    todo = a.only.split(",") if a.only else ["dgcnn", "gfs", "kmeans", "kmeanspp", "train", "callers"]
     if "callers" in todo:
         make_metric("metric_s3dis", seed=5, scannet=False)
         make_metric("metric_scannet", seed=6, scannet=True)
@@ -347,3 +370,6 @@ if __name__ == "__main__":
     if "kmeans" in todo:
         make_kmeans("kmeans_n6000_k150", 6000, 192, 150, seed=99)
         make_kmeans("kmeans_n2000_k20", 2000, 192, 20, seed=3)
+    if "kmeanspp" in todo:
+        make_kmeanspp("kmeanspp_n3000_k50", 3000, 192, 50, seed=2, rs_seed=102)
+        make_kmeanspp("kmeanspp_n6000_k150", 6000, 192, 150, seed=5, rs_seed=105)

@@ -131,6 +131,54 @@ def _worker(rank, world, port, out):
     n = allreduce_gradients(ps)
     ok = ok and n == 17 and torch.allclose(ps[0].grad, torch.full((3, 4), 1.5)) and torch.allclose(ps[1].grad, torch.arange(5.0) * 1.5)
     ok = ok and ps[2].grad is None
+    # GradBucket: the gradients LIVE in one flat buffer, autograd accumulates into the views, one in-place all-reduce
+    from gfs3d.dist import GradBucket
+    lin = torch.nn.Linear(4, 3)
+    with torch.no_grad():
+        lin.weight.fill_(0.5)
+        lin.bias.zero_()
+    bucket = GradBucket(lin.parameters())
+    bucket.zero()
+    xin = torch.full((2, 4), float(rank + 1))
+    lin(xin).sum().backward()
+    ok = ok and bucket.views_intact() and torch.allclose(lin.weight.grad, torch.full((3, 4), 2.0 * (rank + 1)))
+    nfl = bucket.allreduce()
+    ok = ok and nfl == 15 and torch.allclose(lin.weight.grad, torch.full((3, 4), 3.0)) and torch.allclose(lin.bias.grad, torch.full((3,), 2.0))
+    bucket.zero()
+    lin(xin).sum().backward()                      # second step: still accumulating into the same storage
+    ok = ok and bucket.views_intact() and torch.allclose(bucket.flat[:12], torch.full((12,), 2.0 * (rank + 1)))
+    # sharded k-means++ seeding (host logic of gfs3d.kmeans.KMeans._seed_plusplus; the scoring kernel is replaced by a torch
+    # stand-in with the same contract): the picks of the 2-rank run must equal the single-process picks
+    from gfs3d import kmeans as km_mod
+    from gfs3d.kmeans import KMeans
+
+    def trial_stub(xt, n_, xsq, cand, closest, m_out, pots):
+        X_ = xt[:, :n_].t().double()
+        d = (xsq[:n_][None, :] - 2.0 * (cand.double() @ X_.t()) + (cand.double() ** 2).sum(1)[:, None]).float().clamp_min(0)
+        if closest is not None:
+            d = torch.minimum(d, closest[:n_][None, :])
+        T = cand.shape[0]
+        m_out[:T, :n_] = d
+        pots[:T] += d.double().sum(1)
+
+    real = km_mod.ops.kmeans_pp_trial
+    km_mod.ops.kmeans_pp_trial = trial_stub
+    try:
+        rs2 = np.random.RandomState(3)
+        Xs = torch.from_numpy(rs2.randn(403, 6).astype(np.float32))
+        lo2, hi2 = shard_range(403, rank, world)
+
+        def seed(Xpart, shard):
+            k = KMeans(n_clusters=9, init="k-means++", shard=shard)
+            npad = (Xpart.shape[0] + 3) // 4 * 4
+            xt = torch.zeros(6, npad)
+            xt[:, :Xpart.shape[0]] = Xpart.t()
+            return k._seed_plusplus(Xpart, xt, np.random.RandomState(17))
+        c_sharded = seed(Xs[lo2:hi2].contiguous(), True)
+        c_single = seed(Xs, False)
+        ok = ok and torch.equal(c_sharded, c_single)
+    finally:
+        km_mod.ops.kmeans_pp_trial = real
     out[rank] = bool(ok)
     dist.destroy_process_group()
 

@@ -51,3 +51,21 @@ def test_sharded_kmeans_matches_single_gpu():
         p.join(300)
         assert p.exitcode == 0
     assert all(out.get(r) for r in range(world)), dict(out)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_launches_follow_the_tensors_device_not_the_ambient_one():
+    """a model / tensor on cuda:1 while the ambient device is cuda:0 (no torch.cuda.set_device): the C-ABI call must run on
+    cuda:1's context and stream, and tensors on different devices must raise instead of launching"""
+    for p in (ROOT, os.path.join(ROOT, "gfs-3dseg_gws_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from gfs3d import ops
+    from oracle import gfs_oracle as O
+    torch.cuda.set_device(0)
+    x = O.synthetic_blocks(2, 256, seed=3)
+    idx = ops.knn(x.to("cuda:1"), 20)
+    assert idx.device == torch.device("cuda", 1)
+    assert torch.equal(idx.cpu(), O.knn_exact(x, 20))
+    with pytest.raises(RuntimeError, match="different devices"):
+        ops.pointwise(x.to("cuda:1"), torch.randn(9, 128, device="cuda:0"), None)

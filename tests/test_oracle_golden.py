@@ -97,6 +97,21 @@ def test_kmeans_oracle_matches_sklearn_fixture(golden, name):
     assert np.abs(basis - g["basis"]).max() <= 1e-5
 
 
+@pytest.mark.parametrize("name", ["kmeanspp_n3000_k50", "kmeanspp_n6000_k150"])
+def test_kmeans_plusplus_oracle_reproduces_sklearns_picks(golden, name):
+    """the k-means++ restatement (sklearn's random-stream order, float64-evaluated distances rounded to float32) picks the
+    centres sklearn.cluster.kmeans_plusplus picked for the same RandomState (fixture written by make_golden.py:make_kmeanspp)"""
+    g = golden(name)
+    n, D, K = int(g["n"]), int(g["D"]), int(g["K"])
+    rs = np.random.RandomState(int(g["seed"]))
+    cent = rs.randn(K, D).astype(np.float32)
+    X = (cent[rs.randint(0, K, n)] + 0.35 * rs.randn(n, D)).astype(np.float32)
+    X = X - X.mean(0)
+    assert abs(float(X.astype(np.float64).sum()) - float(g["x_checksum"])) < 1e-9
+    _, idx = O.kmeans_plusplus_ref(X, K, np.random.RandomState(int(g["rs_seed"])))
+    assert np.array_equal(idx, g["idx"])
+
+
 def test_kmeans_assign_ties_lowest_index():
     X = np.zeros((4, 8), np.float32)
     C = np.zeros((5, 8), np.float32)      # all centroids identical -> label 0 (strict <, _k_means_lloyd.pyx:208)
