@@ -7,8 +7,9 @@
 // scale is folded into W2 the remaining "+shift, LeakyReLU" is monotone and is applied once after the max.
 //
 // Warp roles (persistent CTA, one per SM):
-//   warps 0-7  producers : cp.async gather of P'[idx] (256 B contiguous per edge) into a shared-memory ring, two slots
-//                          ahead; + Q' (registers) -> LReLU -> bf16 -> SWIZZLE_128B A tile in shared memory ->
+//   warps 0-7  producers : cp.async gather of the bf16 row P'[idx] - mu (128 B contiguous per edge, gfs_edge_pq_f32) into a
+//                          shared-memory ring, EC_NG - 1 slots ahead; + (Q' + mu) (fp32, registers) -> LReLU -> bf16 ->
+//                          SWIZZLE_128B A tile in shared memory ->
 //                          fence.proxy.async -> arrive full[stage]
 //   warp  12   MMA       : one thread issues 4 x tcgen05.mma (128x64x16) per A tile into TMEM stage acc;
 //                          tcgen05.commit -> empty[stage], accf[acc].  W2 (8 KB image) arrives once by TMA bulk copy.
@@ -25,11 +26,11 @@ constexpr int EC_PROD = 256;        // producer threads (warps 0-7)
 constexpr int EC_THREADS = EC_PROD + 128 + 32;   // + 4 epilogue warps (8-11) + 1 MMA warp (12)
 constexpr uint32_t EC_TMEM_COLS = 256;
 
-constexpr int EC_NG = 4;           // gather ring depth (slots of 128 rows x 256 B of fp32 P'); EC_NG - 1 slots are in flight
+constexpr int EC_NG = 8;           // gather ring depth (slots of 128 rows x 128 B of bf16 P'); EC_NG - 1 slots are in flight
 
 struct EcSmem {
     uint8_t A[EC_NST][16384];
-    uint8_t G[EC_NG][32768];
+    uint8_t G[EC_NG][16384];
     uint8_t W[8192];
     float shift[64];
     uint64_t full[EC_NST], empty[EC_NST], accf[EC_NACC], acce[EC_NACC], wbar;
@@ -38,7 +39,7 @@ struct EcSmem {
 
 template <bool ARGMAX>
 __global__ void __launch_bounds__(512, 1)   // 416 threads are launched; 512 caps registers at 128 (13 warps -> 4 on one SMSP)
-edgeconv_kernel(const float* __restrict__ pq, const int32_t* __restrict__ idx, const uint8_t* __restrict__ w2p,
+edgeconv_kernel(const uint8_t* __restrict__ pb, const float* __restrict__ qv, const int32_t* __restrict__ idx, const uint8_t* __restrict__ w2p,
                 const float* __restrict__ shift2, int N, int k, int64_t M, int ntiles, float* __restrict__ y_cm,
                 int64_t y_bstride, uint8_t* __restrict__ y_act, int act_kblocks, int act_kb, uint8_t* __restrict__ y_act2,
                 int act2_kblocks, int act2_kb, uint8_t* __restrict__ argmax) {
@@ -73,12 +74,15 @@ edgeconv_kernel(const float* __restrict__ pq, const int32_t* __restrict__ idx, c
 
     if (warp < 8) {
         // =============================== producers ===============================
-        // Gathers are cp.async (LDGSTS) copies into a 3-deep shared-memory ring, two neighbour slots ahead of the slot
-        // being converted, so ~64 KB of P' rows are in flight per SM without holding them in registers.  Each thread
-        // converts exactly the 32-byte pieces it copied itself, so cp.async.wait_group is the only synchronisation.
+        // Gathers are cp.async (LDGSTS) copies into an EC_NG-deep shared-memory ring, EC_NG - 1 neighbour slots ahead of the
+        // slot being converted, so ~100 KB of P' rows are in flight per SM without holding them in registers.  Each thread
+        // converts exactly the 16-byte pieces it copied itself, so cp.async.wait_group is the only synchronisation.
+        // The loop is issue bound (ncu: the epilogue warps wait for the producers), so it is written for instruction count:
+        // 32-bit row offsets (one IMAD.WIDE per copy), rows past M clamped instead of predicated, packed fp32 add / mul.
         const int q = tid & 7, rsub = tid >> 3;   // rsub 0..31: rows rsub, rsub+32, rsub+64, rsub+96
         int* idxs = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(&s) + sizeof(EcSmem));   // [128][k]
         int stage = 0, phase = 0;
+        const uint32_t gq = sw128(rsub, q);                     // the thread's piece inside a slot: rows rsub + 32 p share r & 7
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int64_t m0 = (int64_t)tile * EC_TM;
             named_bar_sync(2, EC_PROD);                          // previous tile's idx no longer needed
@@ -87,64 +91,57 @@ edgeconv_kernel(const float* __restrict__ pq, const int32_t* __restrict__ idx, c
                 const int32_t* src = idx + m0 * k;
                 for (int i = tid; i < EC_TM * k; i += EC_PROD) idxs[i] = i < lim ? __ldg(src + i) : 0;
             }
-            float4 Q[4][2];
-            int64_t base[4];   // b*N of the row's block, or -1 for rows past M
+            float2 Q[4][4];
+            uint32_t base[4];   // first row of the point's block (rows past M: the last valid point, its result is not stored)
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
-                const int64_t m = m0 + p * 32 + rsub;
-                if (m < M) {
-                    base[p] = (m / N) * N;
-                    const float4* src = reinterpret_cast<const float4*>(pq + m * 128 + 64 + q * 8);
-                    Q[p][0] = __ldg(src);
-                    Q[p][1] = __ldg(src + 1);
-                } else {
-                    base[p] = -1;
-                    Q[p][0] = Q[p][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+                int64_t m = m0 + p * 32 + rsub;
+                m = m < M ? m : M - 1;
+                base[p] = (uint32_t)((m / N) * N);
+                const float4* src = reinterpret_cast<const float4*>(qv + m * 64 + q * 8);
+                const float4 q0 = __ldg(src), q1 = __ldg(src + 1);
+                Q[p][0] = make_float2(q0.x, q0.y);
+                Q[p][1] = make_float2(q0.z, q0.w);
+                Q[p][2] = make_float2(q1.x, q1.y);
+                Q[p][3] = make_float2(q1.z, q1.w);
             }
             named_bar_sync(2, EC_PROD);                          // idx tile visible to all producer threads
 
             auto issue = [&](int kk) {
                 if (kk < k) {
-                    unsigned char* G = s.G[kk % EC_NG];
+                    unsigned char* G = s.G[kk % EC_NG] + gq;
+                    int j[4];
 #pragma unroll
-                    for (int p = 0; p < 4; ++p) {
-                        if (base[p] >= 0) {
-                            const int r = p * 32 + rsub;
-                            const int j = idxs[r * k + kk];
-                            const float* src = pq + (base[p] + j) * 128 + q * 8;
-                            unsigned char* dst = G + r * 256;
-                            cp_async16(dst + (((2 * q) ^ (r & 3)) << 4), src, 16);
-                            cp_async16(dst + (((2 * q + 1) ^ (r & 3)) << 4), src + 4, 16);
-                        }
-                    }
+                    for (int p = 0; p < 4; ++p) j[p] = idxs[(p * 32 + rsub) * k + kk];
+#pragma unroll
+                    for (int p = 0; p < 4; ++p)
+                        cp_async16(G + p * 4096, pb + (size_t)((base[p] + (uint32_t)j[p]) * 128u + (uint32_t)q * 16u), 16);
                 }
                 cp_async_commit();                               // always commit: keeps the group count uniform
             };
-            issue(0);
-            issue(1);
-            issue(2);
+#pragma unroll
+            for (int kk = 0; kk < EC_NG - 1; ++kk) issue(kk);
             for (int kk = 0; kk < k; ++kk) {
-                issue(kk + 3);
-                cp_async_wait<3>();                              // this thread's copies of slot kk have landed
+                issue(kk + EC_NG - 1);
+                cp_async_wait<EC_NG - 1>();                      // this thread's copies of slot kk have landed
                 mbar_wait(&s.empty[stage], phase ^ 1);
-                uint8_t* A = s.A[stage];
-                const unsigned char* G = s.G[kk % EC_NG];
+                uint8_t* A = s.A[stage] + gq;
+                const unsigned char* G = s.G[kk % EC_NG] + gq;
+                uint4 g4[4];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) g4[p] = *reinterpret_cast<const uint4*>(G + p * 4096);     // all four loads in flight: 8 bf16 channels of P'[j] - mu each
 #pragma unroll
                 for (int p = 0; p < 4; ++p) {
-                    const int r = p * 32 + rsub;
-                    uint4 o;
-                    if (base[p] >= 0) {
-                        const float4 v0 = *reinterpret_cast<const float4*>(G + r * 256 + (((2 * q) ^ (r & 3)) << 4));
-                        const float4 v1 = *reinterpret_cast<const float4*>(G + r * 256 + (((2 * q + 1) ^ (r & 3)) << 4));
-                        o.x = pack_bf16x2(lrelu02(v0.x + Q[p][0].x), lrelu02(v0.y + Q[p][0].y));
-                        o.y = pack_bf16x2(lrelu02(v0.z + Q[p][0].z), lrelu02(v0.w + Q[p][0].w));
-                        o.z = pack_bf16x2(lrelu02(v1.x + Q[p][1].x), lrelu02(v1.y + Q[p][1].y));
-                        o.w = pack_bf16x2(lrelu02(v1.z + Q[p][1].z), lrelu02(v1.w + Q[p][1].w));
-                    } else {
-                        o = make_uint4(0u, 0u, 0u, 0u);
+                    const uint32_t gw[4] = {g4[p].x, g4[p].y, g4[p].z, g4[p].w};
+                    uint32_t o[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        // bf16 -> fp32 is a 16-bit shift (the low half of a word is the even channel); packed add and multiply
+                        const float2 v = __fadd2_rn(make_float2(__uint_as_float(gw[e] << 16), __uint_as_float(gw[e] & 0xffff0000u)), Q[p][e]);
+                        const float2 t = __fmul2_rn(v, make_float2(0.2f, 0.2f));
+                        o[e] = pack_bf16x2(fmaxf(v.x, t.x), fmaxf(v.y, t.y));
                     }
-                    *reinterpret_cast<uint4*>(A + sw128(r, q)) = o;
+                    *reinterpret_cast<uint4*>(A + p * 4096) = make_uint4(o[0], o[1], o[2], o[3]);
                 }
                 fence_proxy_async();
                 mbar_arrive(&s.full[stage]);
@@ -201,7 +198,7 @@ edgeconv_kernel(const float* __restrict__ pq, const int32_t* __restrict__ idx, c
                 for (int c = 0; c < 16; ++c) am[c] = 0u;
             }
             for (int kk = 0; kk < k; ++kk) {
-                mbar_wait(&s.accf[acc], aphase);
+                mbar_wait_backoff(&s.accf[acc], aphase, 32);     // the epilogue is not the critical path: do not poll at full rate
                 tc_fence_after();
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -276,15 +273,17 @@ edgeconv_kernel(const float* __restrict__ pq, const int32_t* __restrict__ idx, c
 
 }  // namespace gfs
 
-extern "C" int gfs_edgeconv_fwd(const float* pq, const int32_t* idx, const void* w2_packed, const float* shift2, int B, int N,
+extern "C" int gfs_edgeconv_fwd(const void* pb, const float* q, const int32_t* idx, const void* w2_packed, const float* shift2, int B, int N,
                                 int k, float* y_cm, int64_t y_bstride, void* y_act, int y_act_kblocks, int y_act_kb,
                                 void* y_act2, int y_act2_kblocks, int y_act2_kb, uint8_t* argmax, void* stream) {
     using namespace gfs;
-    GFS_REQUIRE(pq && idx && w2_packed && shift2, GFS_ERR_BAD_ARG, "gfs_edgeconv_fwd: null pointer");
+    GFS_REQUIRE(pb && q && idx && w2_packed && shift2, GFS_ERR_BAD_ARG, "gfs_edgeconv_fwd: null pointer");
     GFS_REQUIRE(B > 0 && N > 0 && k > 0, GFS_ERR_BAD_ARG, "gfs_edgeconv_fwd: non-positive size");
     GFS_REQUIRE(k <= 64, GFS_ERR_UNSUPPORTED, "gfs_edgeconv_fwd: k=%d > 64 is not built", k);
+    GFS_REQUIRE((int64_t)B * N < ((int64_t)1 << 25), GFS_ERR_UNSUPPORTED, "gfs_edgeconv_fwd: B*N=%lld points exceed the 32-bit gather offsets",
+                (long long)B * N);
     GFS_REQUIRE(y_cm || y_act || y_act2, GFS_ERR_BAD_ARG, "gfs_edgeconv_fwd: no output requested");
-    GFS_REQUIRE((reinterpret_cast<uintptr_t>(pq) & 15) == 0 && (reinterpret_cast<uintptr_t>(w2_packed) & 15) == 0 &&
+    GFS_REQUIRE((reinterpret_cast<uintptr_t>(pb) & 15) == 0 && (reinterpret_cast<uintptr_t>(q) & 15) == 0 && (reinterpret_cast<uintptr_t>(w2_packed) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(y_act) & 15) == 0 && (reinterpret_cast<uintptr_t>(y_act2) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(argmax) & 15) == 0,
                 GFS_ERR_BAD_ARG, "gfs_edgeconv_fwd: pointers must be 16-byte aligned");
@@ -300,13 +299,13 @@ extern "C" int gfs_edgeconv_fwd(const float* pq, const int32_t* idx, const void*
     if (argmax) {
         GFS_CUDA_OK(allow_smem(reinterpret_cast<const void*>(edgeconv_kernel<true>), EC_MAX_SMEM));
         edgeconv_kernel<true><<<grid, EC_THREADS, smem, st>>>(
-            pq, idx, static_cast<const uint8_t*>(w2_packed), shift2, N, k, M, ntiles, y_cm, y_bstride,
+            static_cast<const uint8_t*>(pb), q, idx, static_cast<const uint8_t*>(w2_packed), shift2, N, k, M, ntiles, y_cm, y_bstride,
             static_cast<uint8_t*>(y_act), y_act_kblocks, y_act_kb, static_cast<uint8_t*>(y_act2), y_act2_kblocks, y_act2_kb,
             argmax);
     } else {
         GFS_CUDA_OK(allow_smem(reinterpret_cast<const void*>(edgeconv_kernel<false>), EC_MAX_SMEM));
         edgeconv_kernel<false><<<grid, EC_THREADS, smem, st>>>(
-            pq, idx, static_cast<const uint8_t*>(w2_packed), shift2, N, k, M, ntiles, y_cm, y_bstride,
+            static_cast<const uint8_t*>(pb), q, idx, static_cast<const uint8_t*>(w2_packed), shift2, N, k, M, ntiles, y_cm, y_bstride,
             static_cast<uint8_t*>(y_act), y_act_kblocks, y_act_kb, static_cast<uint8_t*>(y_act2), y_act2_kblocks, y_act2_kb,
             nullptr);
     }

@@ -17,7 +17,8 @@ SIGNATURES = {
     "gfs_knn_tc_set_f32": [_p, _i64, _i, _i, _i, _i, _p, _p, _i64, _p, _p],
     "gfs_knn_tc_diag_f32": [_p, _i64, _i, _i, _i, _i, _p, _p, _i64, _p, _p, _p, _p],
     "gfs_pointwise_f32": [_p, _i64, _i, _i, _i, _p, _p, _i, _p, _p],
-    "gfs_edgeconv_fwd": [_p, _p, _p, _p, _i, _i, _i, _p, _i64, _p, _i, _i, _p, _i, _i, _p, _p],
+    "gfs_edge_pq_f32": [_p, _i64, _i, _i, _i, _p, _p, _p, _p, _p],
+    "gfs_edgeconv_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _p, _i64, _p, _i, _i, _p, _i, _i, _p, _p],
     "gfs_pack_weight_bf16": [_p, _p, _i, _i, _p, _p],
     "gfs_cm_to_act": [_p, _i64, _i, _i, _i, _p, _i, _i, _p],
     "gfs_linear_bf16": [_p, _i, _i, _i, _p, _p, _i, _i, _i, _i, _p, _i, _i, _p, _i64, _p],

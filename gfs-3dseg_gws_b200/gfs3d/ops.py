@@ -152,6 +152,18 @@ def pointwise(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor]) -
     return out
 
 
+def edge_pq(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor]):
+    """split first EdgeConv conv: x (B,C,N) cm fp32, wt (C,128) = [s1*Wa | s1*(Wb-Wa)]^T, bias (128) ->
+    pb (B*N, 64) bf16 = P' - mu,  q (B*N, 64) fp32 = Q' + mu   (what gfs_edgeconv_fwd gathers from)"""
+    _need_cuda(x, wt, bias)
+    B, C, N = x.shape
+    assert x.stride(2) == 1 and x.stride(1) == N and wt.is_contiguous() and wt.shape == (C, 128)
+    pb = torch.empty(B * N, 64, dtype=torch.bfloat16, device=x.device)
+    q = torch.empty(B * N, 64, dtype=torch.float32, device=x.device)
+    _call("gfs_edge_pq_f32", 1, _ptr(x), x.stride(0), B, C, N, _ptr(wt), _ptr(bias), _ptr(pb), _ptr(q), _stream())
+    return pb, q
+
+
 def pack_weight(w: torch.Tensor, row_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
     """w (R, K) fp32 -> bf16 tiles [ceil(K/64)][R x 64], K-major SWIZZLE_128B, optional per-row scale folded in"""
     _need_cuda(w, row_scale)
@@ -171,14 +183,15 @@ def cm_to_act(x: torch.Tensor, act: torch.Tensor, kb0: int):
     _call("gfs_cm_to_act", 1, _ptr(x), x.stride(0), B, C, N, _ptr(act), act.shape[1], kb0, _stream())
 
 
-def edgeconv(pq, idx, w2_packed, shift2, B, N, k, y_cm=None, y_act=None, y_act_kb=0, y_act2=None, y_act2_kb=0,
+def edgeconv(pbq, idx, w2_packed, shift2, B, N, k, y_cm=None, y_act=None, y_act_kb=0, y_act2=None, y_act2_kb=0,
              argmax=None):
     """fused EdgeConv given the graph; writes into the provided destinations"""
-    _need_cuda(pq, idx, w2_packed, shift2)
+    pb, q = pbq                     # from edge_pq
+    _need_cuda(pb, q, idx, w2_packed, shift2)
     if y_cm is not None:
         assert y_cm.stride(2) == 1 and y_cm.stride(1) == N and y_cm.shape[1] == 64
     _call("gfs_edgeconv_fwd", 1, 
-        _ptr(pq), _ptr(idx), _ptr(w2_packed), _ptr(shift2), B, N, k,
+        _ptr(pb), _ptr(q), _ptr(idx), _ptr(w2_packed), _ptr(shift2), B, N, k,
         _ptr(y_cm), 0 if y_cm is None else y_cm.stride(0),
         _ptr(y_act), 0 if y_act is None else y_act.shape[1], y_act_kb,
         _ptr(y_act2), 0 if y_act2 is None else y_act2.shape[1], y_act2_kb,

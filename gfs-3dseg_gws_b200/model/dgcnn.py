@@ -7,7 +7,7 @@ Public surface kept from the reference (file:line of what each replaces):
   DGCNN(...).forward(x)             model/dgcnn.py:93-127
   BaseLearner, DGCNNSeg_att         model/dgcnn.py:130-202
 
-Eval-mode forward = per layer: gfs_knn_f32 -> gfs_pointwise_f32 (split conv1) -> gfs_edgeconv_fwd (tcgen05 conv2 + max),
+Eval-mode forward = per layer: gfs_knn_tc_set_f32 -> gfs_edge_pq_f32 (split conv1) -> gfs_edgeconv_fwd (tcgen05 conv2 + max),
 then gfs_linear_bf16 x2 for the 192->512->256 MLP.  There is no PyTorch fallback: on a machine without the CUDA library
 the forward raises.
 """
@@ -191,7 +191,7 @@ class DGCNN(nn.Module):
         xin = x
         for i, (wt, bias, w2p, t2) in enumerate(layers):
             idx = ops.knn(xin, self.k, ordered=False)      # the max over k only needs the neighbour set
-            pq = ops.pointwise(xin, wt, bias)
+            pq = ops.edge_pq(xin, wt, bias)
             y = ec[:, 64 * i:64 * (i + 1), :]
             ops.edgeconv(pq, idx, w2p, t2, B, N, self.k, y_cm=y, y_act=cat_act, y_act_kb=i,
                          y_act2=level1_act if i == 0 else None, y_act2_kb=level1_kb)

@@ -88,12 +88,20 @@ int gfs_knn_tc_diag_f32(const float* x, int64_t x_bstride, int B, int C, int N, 
 int gfs_pointwise_f32(const float* x, int64_t x_bstride, int B, int C, int N,
                       const float* wt, const float* bias, int O, float* out, void* stream);
 
+/* ---- the split first EdgeConv conv in the layout gfs_edgeconv_fwd gathers from (model/dgcnn.py:26-42 + :53, SURVEY a3')
+ * wt (C, 128) = [s1*Wa | s1*(Wb-Wa)]^T, bias (128) = [0 | t1]:  P' = first 64 outputs, Q' = last 64.  Only P'[j] + Q'[i] is ever
+ * used, so a per-block constant mu (the image of a point inside the block's cloud) moves from P' to Q':
+ *   pb (B*N, 64) bf16 = P' - mu      (a neighbour's row: one contiguous 128-byte gather)
+ *   q  (B*N, 64) fp32 = Q' + mu                                                                                      */
+int gfs_edge_pq_f32(const float* x, int64_t x_bstride, int B, int C, int N, const float* wt, const float* bias,
+                    void* pb, float* q, void* stream);
+
 /* ---- fused EdgeConv given the graph: model/dgcnn.py:35-41 (gather, x_j - x_i, cat), :56-58 (LeakyReLU of conv1,
  * conv2, BN2 eval, LeakyReLU) and :118 (max over k).  h1 = LReLU(P'[j] + Q'[i]) is formed in shared memory as a
  * bf16 UMMA operand, conv2 runs on tcgen05 with the accumulator in TMEM, max over k is taken on the accumulator
  * (BN2 scale is folded into w2, so +shift and LeakyReLU commute with max) -- the (B,2C,N,k) edge tensor and the
  * (B,64,N,k) activations never exist in memory.
- *   pq        (B*N, 128) fp32 = [P' | Q'] from gfs_pointwise_f32
+ *   pb, q     (B*N, 64) bf16 = P' - mu  and  (B*N, 64) fp32 = Q' + mu  from gfs_edge_pq_f32
  *   idx       (B, N, k) int32
  *   w2_packed 64x64 bf16, K-major SWIZZLE_128B image of diag(s2) W2 (gfs_pack_weight_bf16)
  *   shift2    64 floats (BN2 beta - mean*s2)
@@ -101,7 +109,7 @@ int gfs_pointwise_f32(const float* x, int64_t x_bstride, int B, int C, int N,
  *   y_act     bf16 act output tile column `y_act_kb` of a matrix with y_act_kblocks 64-col blocks (may be NULL)
  *   y_act2    second optional bf16 act destination (same arguments)
  *   argmax    optional (B*N, 64) uint8: neighbour slot that produced the max (for the backward scatter)        */
-int gfs_edgeconv_fwd(const float* pq, const int32_t* idx, const void* w2_packed, const float* shift2,
+int gfs_edgeconv_fwd(const void* pb, const float* q, const int32_t* idx, const void* w2_packed, const float* shift2,
                      int B, int N, int k,
                      float* y_cm, int64_t y_bstride,
                      void* y_act, int y_act_kblocks, int y_act_kb,

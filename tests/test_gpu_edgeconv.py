@@ -94,7 +94,7 @@ def test_edgeconv_fused_vs_reference_formula(B, C, N, k):
     wt = torch.cat([s1[:, None] * wa, s1[:, None] * (wb - wa)], dim=0).t().contiguous()      # (C, 128)
     bias = torch.cat([torch.zeros(64), t1])
     xc = x.cuda()
-    pq = ops.pointwise(xc, wt.cuda(), bias.cuda())
+    pq = ops.edge_pq(xc, wt.cuda(), bias.cuda())
     w2p = ops.pack_weight(w2.cuda(), s2.cuda())
     y = torch.empty(B, 64, N, device="cuda")
     act = ops.new_act(B * N, 3, "cuda")
