@@ -22,8 +22,9 @@ namespace gfs {
 constexpr int EC_TM = 128;
 constexpr int EC_NST = 4;
 constexpr int EC_NACC = 4;
-constexpr int EC_PROD = 256;        // producer threads (warps 0-7)
-constexpr int EC_THREADS = EC_PROD + 128 + 32;   // + 4 epilogue warps (8-11) + 1 MMA warp (12)
+constexpr int EC_PROD = 512;        // producer threads (warps 0-15): the producers are latency bound, 4 per scheduler hide it
+constexpr int EC_PW = EC_PROD / 32;
+constexpr int EC_THREADS = EC_PROD + 128 + 128;  // + 4 epilogue warps (16-19) + the MMA warp (20) and 3 idle warps (one warpgroup: setmaxnreg)
 constexpr uint32_t EC_TMEM_COLS = 256;
 
 constexpr int EC_NG = 8;           // gather ring depth (slots of 128 rows x 128 B of bf16 P'); EC_NG - 1 slots are in flight
@@ -38,7 +39,7 @@ struct EcSmem {
 };
 
 template <bool ARGMAX>
-__global__ void __launch_bounds__(512, 1)   // 416 threads are launched; 512 caps registers at 128 (13 warps -> 4 on one SMSP)
+__global__ void __launch_bounds__(EC_THREADS, 1)   // 80 registers at launch; setmaxnreg: producers 64, epilogue 128, MMA group 56
 edgeconv_kernel(const uint8_t* __restrict__ pb, const float* __restrict__ qv, const int32_t* __restrict__ idx, const uint8_t* __restrict__ w2p,
                 const float* __restrict__ shift2, int N, int k, int64_t M, int ntiles, float* __restrict__ y_cm,
                 int64_t y_bstride, uint8_t* __restrict__ y_act, int act_kblocks, int act_kb, uint8_t* __restrict__ y_act2,
@@ -49,15 +50,15 @@ edgeconv_kernel(const uint8_t* __restrict__ pb, const float* __restrict__ qv, co
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid < 64) s.shift[tid] = shift2[tid];
-    if (warp == 12) {
+    if (warp == EC_PW + 4) {
         if (lane == 0) {
             for (int i = 0; i < EC_NST; ++i) {
-                mbar_init(&s.full[i], EC_PROD);
+                mbar_init(&s.full[i], EC_PW);        // one arrive per producer WARP: hundreds of arrives on one mbarrier serialise
                 mbar_init(&s.empty[i], 1);
             }
             for (int i = 0; i < EC_NACC; ++i) {
                 mbar_init(&s.accf[i], 1);
-                mbar_init(&s.acce[i], 128);
+                mbar_init(&s.acce[i], 4);
             }
             mbar_init(&s.wbar, 1);
             mbar_fence_init();
@@ -72,17 +73,18 @@ edgeconv_kernel(const uint8_t* __restrict__ pb, const float* __restrict__ qv, co
     tc_fence_after();
     const uint32_t tmem = s.tmem_base;
 
-    if (warp < 8) {
+    if (warp < EC_PW) {
         // =============================== producers ===============================
+        reg_dealloc<64>();
         // Gathers are cp.async (LDGSTS) copies into an EC_NG-deep shared-memory ring, EC_NG - 1 neighbour slots ahead of the
         // slot being converted, so ~100 KB of P' rows are in flight per SM without holding them in registers.  Each thread
         // converts exactly the 16-byte pieces it copied itself, so cp.async.wait_group is the only synchronisation.
         // The loop is issue bound (ncu: the epilogue warps wait for the producers), so it is written for instruction count:
         // 32-bit row offsets (one IMAD.WIDE per copy), rows past M clamped instead of predicated, packed fp32 add / mul.
-        const int q = tid & 7, rsub = tid >> 3;   // rsub 0..31: rows rsub, rsub+32, rsub+64, rsub+96
+        const int q = tid & 7, rsub = tid >> 3;   // rsub 0..63: rows rsub, rsub+64
         int* idxs = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(&s) + sizeof(EcSmem));   // [128][k]
         int stage = 0, phase = 0;
-        const uint32_t gq = sw128(rsub, q);                     // the thread's piece inside a slot: rows rsub + 32 p share r & 7
+        const uint32_t gq = sw128(rsub, q);                     // the thread's piece inside a slot: rows rsub + 64 p share r & 7
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int64_t m0 = (int64_t)tile * EC_TM;
             named_bar_sync(2, EC_PROD);                          // previous tile's idx no longer needed
@@ -91,11 +93,11 @@ edgeconv_kernel(const uint8_t* __restrict__ pb, const float* __restrict__ qv, co
                 const int32_t* src = idx + m0 * k;
                 for (int i = tid; i < EC_TM * k; i += EC_PROD) idxs[i] = i < lim ? __ldg(src + i) : 0;
             }
-            float2 Q[4][4];
-            uint32_t base[4];   // first row of the point's block (rows past M: the last valid point, its result is not stored)
+            float2 Q[2][4];
+            uint32_t base[2];   // first row of the point's block (rows past M: the last valid point, its result is not stored)
 #pragma unroll
-            for (int p = 0; p < 4; ++p) {
-                int64_t m = m0 + p * 32 + rsub;
+            for (int p = 0; p < 2; ++p) {
+                int64_t m = m0 + p * 64 + rsub;
                 m = m < M ? m : M - 1;
                 base[p] = (uint32_t)((m / N) * N);
                 const float4* src = reinterpret_cast<const float4*>(qv + m * 64 + q * 8);
@@ -110,12 +112,12 @@ edgeconv_kernel(const uint8_t* __restrict__ pb, const float* __restrict__ qv, co
             auto issue = [&](int kk) {
                 if (kk < k) {
                     unsigned char* G = s.G[kk % EC_NG] + gq;
-                    int j[4];
+                    int j[2];
 #pragma unroll
-                    for (int p = 0; p < 4; ++p) j[p] = idxs[(p * 32 + rsub) * k + kk];
+                    for (int p = 0; p < 2; ++p) j[p] = idxs[(p * 64 + rsub) * k + kk];
 #pragma unroll
-                    for (int p = 0; p < 4; ++p)
-                        cp_async16(G + p * 4096, pb + (size_t)((base[p] + (uint32_t)j[p]) * 128u + (uint32_t)q * 16u), 16);
+                    for (int p = 0; p < 2; ++p)
+                        cp_async16(G + p * 8192, pb + (size_t)((base[p] + (uint32_t)j[p]) * 128u + (uint32_t)q * 16u), 16);
                 }
                 cp_async_commit();                               // always commit: keeps the group count uniform
             };
@@ -127,11 +129,11 @@ edgeconv_kernel(const uint8_t* __restrict__ pb, const float* __restrict__ qv, co
                 mbar_wait(&s.empty[stage], phase ^ 1);
                 uint8_t* A = s.A[stage] + gq;
                 const unsigned char* G = s.G[kk % EC_NG] + gq;
-                uint4 g4[4];
+                uint4 g4[2];
 #pragma unroll
-                for (int p = 0; p < 4; ++p) g4[p] = *reinterpret_cast<const uint4*>(G + p * 4096);     // all four loads in flight: 8 bf16 channels of P'[j] - mu each
+                for (int p = 0; p < 2; ++p) g4[p] = *reinterpret_cast<const uint4*>(G + p * 8192);     // both loads in flight: 8 bf16 channels of P'[j] - mu each
 #pragma unroll
-                for (int p = 0; p < 4; ++p) {
+                for (int p = 0; p < 2; ++p) {
                     const uint32_t gw[4] = {g4[p].x, g4[p].y, g4[p].z, g4[p].w};
                     uint32_t o[4];
 #pragma unroll
@@ -141,10 +143,11 @@ edgeconv_kernel(const uint8_t* __restrict__ pb, const float* __restrict__ qv, co
                         const float2 t = __fmul2_rn(v, make_float2(0.2f, 0.2f));
                         o[e] = pack_bf16x2(fmaxf(v.x, t.x), fmaxf(v.y, t.y));
                     }
-                    *reinterpret_cast<uint4*>(A + p * 4096) = make_uint4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<uint4*>(A + p * 8192) = make_uint4(o[0], o[1], o[2], o[3]);
                 }
                 fence_proxy_async();
-                mbar_arrive(&s.full[stage]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s.full[stage]);
                 if (++stage == EC_NST) {
                     stage = 0;
                     phase ^= 1;
@@ -152,9 +155,10 @@ edgeconv_kernel(const uint8_t* __restrict__ pb, const float* __restrict__ qv, co
             }
             cp_async_wait<0>();
         }
-    } else if (warp == 12) {
-        // =============================== MMA issuer ===============================
-        if (lane == 0) {
+    } else if (warp >= EC_PW + 4) {
+        // =============================== MMA issuer (warp 20; warps 21-23 only complete its warpgroup) ===============================
+        reg_dealloc<56>();
+        if (warp == EC_PW + 4 && lane == 0) {
             mbar_wait(&s.wbar, 0);
             const uint32_t idesc = umma_idesc_bf16(128, 64);
             const uint64_t bdesc = umma_desc_sw128(smem_u32(s.W));
@@ -184,7 +188,8 @@ edgeconv_kernel(const uint8_t* __restrict__ pb, const float* __restrict__ qv, co
         __syncwarp();
     } else {
         // =============================== epilogue ===============================
-        const int quarter = warp - 8;            // == warp % 4: the TMEM lane quarter this warp may read
+        reg_alloc<128>();
+        const int quarter = warp - EC_PW;        // == warp % 4: the TMEM lane quarter this warp may read
         const int row = quarter * 32 + lane;
         const uint32_t tlane = (uint32_t)(quarter * 32) << 16;
         int acc = 0, aphase = 0;
@@ -220,7 +225,8 @@ edgeconv_kernel(const uint8_t* __restrict__ pb, const float* __restrict__ qv, co
                     }
                 }
                 tc_fence_before();
-                mbar_arrive(&s.acce[acc]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s.acce[acc]);
                 if (++acc == EC_NACC) {
                     acc = 0;
                     aphase ^= 1;
@@ -265,7 +271,7 @@ edgeconv_kernel(const uint8_t* __restrict__ pb, const float* __restrict__ qv, co
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 12) {
+    if (warp == EC_PW + 4) {
         tc_fence_after();
         tmem_dealloc(tmem, EC_TMEM_COLS);
     }

@@ -154,6 +154,11 @@ struct KtCtl {
     uint32_t tmem_base;
 };
 
+// mask |= bit if v >= thr: a compare and a predicated OR
+__device__ __forceinline__ void kt_mask_ge(uint32_t& mask, float v, float thr, uint32_t bit) {
+    asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(mask) : "f"(v), "f"(thr), "r"(bit));
+}
+
 // bitonic sorting network on registers, descending; every index is a compile-time constant after unrolling
 template <int NG>
 __device__ __forceinline__ void kt_sort_desc(float (&a)[NG]) {
@@ -344,15 +349,22 @@ knn_tc_kernel(const uint8_t* __restrict__ ops, const float* __restrict__ nh, con
         }
 
         // ---------------- pass B: append every candidate whose upper bound reaches the threshold ----------------
-        // 32-bit record offsets from the (uniform) base pointer: one IMAD.WIDE per predicated store instead of 64-bit pointer chains
+        // The scan is two instructions per candidate (compare, predicated OR into a bit mask) next to the packed add; the few
+        // hits (~1 % of the candidates) are then peeled off the mask and written as {u, tag} records.  The filter values of
+        // the chunk are staged in the thread's own shared-memory slot (the exchange area of the threshold step, now free)
+        // because a hit's value has to be fetched by a run-time index.
+        // 32-bit record offsets from the (uniform) base pointer: one IMAD.WIDE per store instead of 64-bit pointer chains
         const int64_t g = (int64_t)b * N + (valid ? n : 0);
         const uint32_t off0 = (uint32_t)(g * 2 + half) * (uint32_t)(2 * KT_CAP);     // [u: KT_CAP floats][tag: KT_CAP words]
         uint32_t off = off0;
         const uint32_t olim = off0 + (KT_CAP - 32);
         // the base comes from shared memory, not from the parameter bank: it then lives in a register pair instead of being
-        // re-loaded from the constant bank for every candidate
+        // re-loaded from the constant bank for every record
         uint32_t* const survw = reinterpret_cast<uint32_t*>(s.surv_base);
         bool ovf = false;
+        named_bar_sync(1, 32 * KT_SELW);                          // every thread has read the other half's maxima: xch is free
+        float4* const stg = xch + (tid - 64);                     // float4 q of this thread's chunk lives at stg[q * 512]
+        const float* const stgf = reinterpret_cast<const float*>(stg);
         for (int st = nst; st < 2 * nst; ++st) {
             const int ts = st % KT_TST;
             mbar_wait(&s.d_full[ts], (st / KT_TST) & 1);
@@ -365,35 +377,31 @@ knn_tc_kernel(const uint8_t* __restrict__ ops, const float* __restrict__ nh, con
             }
             const float* cst = s.cst[ts] + half * 32;
             const uint32_t* tgs = s.tag[ts] + half * 32;
-            float v[32];
+            uint32_t m0 = 0u, m1 = 0u;                            // two chains: even / odd pairs
 #pragma unroll
             for (int c = 0; c < 32; c += 4) {
                 const float4 h4 = *reinterpret_cast<const float4*>(cst + c);
                 const float2 s0 = __fadd2_rn(make_float2(__uint_as_float(r[c]), __uint_as_float(r[c + 1])), make_float2(h4.x, h4.y));
                 const float2 s1 = __fadd2_rn(make_float2(__uint_as_float(r[c + 2]), __uint_as_float(r[c + 3])), make_float2(h4.z, h4.w));
-                v[c] = s0.x;
-                v[c + 1] = s0.y;
-                v[c + 2] = s1.x;
-                v[c + 3] = s1.y;
+                stg[(c >> 2) * (32 * KT_SELW)] = make_float4(s0.x, s0.y, s1.x, s1.y);
+                kt_mask_ge(m0, s0.x, thr, 1u << c);
+                kt_mask_ge(m0, s0.y, thr, 1u << (c + 1));
+                kt_mask_ge(m1, s1.x, thr, 1u << (c + 2));
+                kt_mask_ge(m1, s1.y, thr, 1u << (c + 3));
             }
             if (dbg && valid) {   // diagnostic entry only: dump the filter value u = D' - |x~_j|^2/2 + a_j
                 float* o = dbg + ((int64_t)b * N + n) * Npad + (st - nst) * KT_COLS + half * 32;
 #pragma unroll
-                for (int c = 0; c < 32; ++c) o[c] = v[c];
+                for (int c = 0; c < 32; ++c) o[c] = stgf[(c >> 2) * (128 * KT_SELW) + (c & 3)];
             }
-#pragma unroll
-            for (int c = 0; c < 32; c += 4) {
-                const uint4 t4 = *reinterpret_cast<const uint4*>(tgs + c);
-                const uint32_t tg[4] = {t4.x, t4.y, t4.z, t4.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    if (v[c + e] >= thr) {
-                        uint32_t* const rec = survw + off;          // one IMAD.WIDE.U32, two stores with immediate offsets
-                        rec[0] = __float_as_uint(v[c + e]);
-                        rec[KT_CAP] = tg[e];
-                        ++off;
-                    }
-                }
+            uint32_t mask = m0 | m1;
+            while (mask) {                                        // ascending column order
+                const int c = __ffs(mask) - 1;
+                mask &= mask - 1;
+                uint32_t* const rec = survw + off;                // one IMAD.WIDE.U32, two stores with immediate offsets
+                rec[0] = __float_as_uint(stgf[(c >> 2) * (128 * KT_SELW) + (c & 3)]);
+                rec[KT_CAP] = tgs[c];
+                ++off;
             }
             tc_fence_before();
             __syncwarp();
