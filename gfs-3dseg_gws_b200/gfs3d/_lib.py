@@ -24,6 +24,8 @@ SIGNATURES = {
     "gfs_linear_bf16": [_p, _i, _i, _i, _p, _p, _i, _i, _i, _i, _p, _i, _i, _p, _i64, _p],
     "gfs_attention_fwd": [_p, _i, _i, _i, _i, _f, _p, _i64, _p, _i, _i, _p],
     "gfs_gw_project": [_p, _i64, _i, _i, _i, _p, _i, _i, _p, _i, _i, _p, _p, _p],
+    "gfs_gw_project_tc": [_p, _i64, _i, _i, _i, _p, _i, _i, _p, _i, _i, _p, _p, _p, _i64, _p],
+    "gfs_kmeans_assign_tc": [_p, _i64, _i64, _i, _p, _i, _i, _p, _p, _p, _i64, _p],
     "gfs_cos_logits": [_p, _i64, _i, _i, _i, _p, _i, _i, _p, _i, _p, _f, _p, _p],
     "gfs_softmax_pool": [_p, _p, _i64, _i, _i, _i, _i, _p, _p, _p, _p],
     "gfs_refine_proto": [_p, _p, _p, _i, _i, _i, _i, _p, _p],
@@ -45,7 +47,8 @@ SIGNATURES = {
 }
 UTILITIES = {"gfs_version": (_i, []), "gfs_last_error_string": (ctypes.c_char_p, []),
              "gfs_device_sm_count": (_i, []), "gfs_kmeans_partials": (_i, []),
-             "gfs_knn_tc_workspace_bytes": (_i64, [_i, _i, _i])}
+             "gfs_knn_tc_workspace_bytes": (_i64, [_i, _i, _i]),
+             "gfs_rowsel_tc_workspace_bytes": (_i64, [_i64, _i])}
 
 _lib = None
 

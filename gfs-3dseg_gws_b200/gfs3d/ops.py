@@ -221,17 +221,30 @@ def attention(qkv_act: torch.Tensor, kb_q: int, B: int, N: int, scale: float, y_
           0 if y_cm is None else y_cm.stride(0), _ptr(y_act), 0 if y_act is None else y_act.shape[1], y_kb, _stream())
 
 
+ROWSEL_IMPL = os.environ.get("GFS3D_ROWSEL", "auto")   # "auto" | "tc" | "fp32": identical assignments / labels
+
+
 def gw_project(ec: torch.Tensor, gp_l2t: torch.Tensor, G: int, cosine_act: Optional[torch.Tensor] = None, kb0: int = 0,
-               want_cm: bool = False):
-    """ec (B, D, N) cm fp32; gp_l2t (D, Gp) -> assignment (B, N) int32 [, cosine_feat (B, G, N) fp32]"""
+               want_cm: bool = False, impl: Optional[str] = None):
+    """ec (B, D, N) cm fp32; gp_l2t (D, Gp) -> assignment (B, N) int32 [, cosine_feat (B, G, N) fp32]
+
+    impl "tc": tcgen05 product + pinned fp32 re-check of near-ties (gfs_gw_project_tc); "fp32": the all-fp32 kernel
+    (gfs_gw_project); "auto": tc whenever the shape is eligible.  The assignments are identical."""
     _need_cuda(ec, gp_l2t, cosine_act)
     B, D, N = ec.shape
     assert ec.stride(2) == 1 and ec.stride(1) == N and gp_l2t.is_contiguous() and gp_l2t.shape[0] == D
     Gp = gp_l2t.shape[1]
     assign = torch.empty(B, N, dtype=torch.int32, device=ec.device)
     cm = torch.empty(B, G, N, dtype=torch.float32, device=ec.device) if want_cm else None
-    _call("gfs_gw_project", 1, _ptr(ec), ec.stride(0), B, D, N, _ptr(gp_l2t), G, Gp, _ptr(cosine_act),
-                               0 if cosine_act is None else cosine_act.shape[1], kb0, _ptr(cm), _ptr(assign), _stream())
+    impl = impl or ROWSEL_IMPL
+    if impl == "tc" or (impl == "auto" and D % 64 == 0 and D <= 256 and N % 128 == 0 and Gp <= 192 and Gp % 64 == 0):
+        nbytes = int(lib().gfs_rowsel_tc_workspace_bytes(B * N, D))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=ec.device)
+        _call("gfs_gw_project_tc", 4, _ptr(ec), ec.stride(0), B, D, N, _ptr(gp_l2t), G, Gp, _ptr(cosine_act),
+              0 if cosine_act is None else cosine_act.shape[1], kb0, _ptr(cm), _ptr(assign), _ptr(ws), nbytes, _stream())
+    else:
+        _call("gfs_gw_project", 1, _ptr(ec), ec.stride(0), B, D, N, _ptr(gp_l2t), G, Gp, _ptr(cosine_act),
+                                   0 if cosine_act is None else cosine_act.shape[1], kb0, _ptr(cm), _ptr(assign), _stream())
     return assign, cm
 
 
@@ -308,8 +321,11 @@ def kmeans_pp_trial(xt: torch.Tensor, n: int, xsq: torch.Tensor, cand: torch.Ten
     _call("gfs_kmeans_pp_trial", 1, _ptr(xt), npad, n, D, _ptr(xsq), _ptr(cand), T, _ptr(closest), _ptr(m_out), _ptr(pots), _stream())
 
 
-def kmeans_assign(xt: torch.Tensor, centers_t: torch.Tensor, K: int, want_score: bool = False):
-    """xt (D, n) fp32, centers_t (D, Kp) fp32 zero padded -> labels (n) int32"""
+def kmeans_assign(xt: torch.Tensor, centers_t: torch.Tensor, K: int, want_score: bool = False, impl: Optional[str] = None):
+    """xt (D, n) fp32, centers_t (D, Kp) fp32 zero padded -> labels (n) int32
+
+    impl "tc": tcgen05 product + pinned fp32 re-check of near-ties (gfs_kmeans_assign_tc); "fp32": gfs_kmeans_assign;
+    "auto": tc when the shape is eligible and no scores are requested.  The labels are identical."""
     _need_cuda(xt, centers_t)
     D, n = xt.shape
     assert xt.is_contiguous() and centers_t.is_contiguous() and centers_t.shape[0] == D
@@ -317,7 +333,13 @@ def kmeans_assign(xt: torch.Tensor, centers_t: torch.Tensor, K: int, want_score:
     cnorm = torch.empty(Kp, dtype=torch.float32, device=xt.device)
     labels = torch.empty(n, dtype=torch.int32, device=xt.device)
     score = torch.empty(n, dtype=torch.float32, device=xt.device) if want_score else None
-    _call("gfs_kmeans_assign", 2, _ptr(xt), n, D, _ptr(centers_t), K, Kp, _ptr(cnorm), _ptr(labels), _ptr(score), _stream())
+    impl = impl or ROWSEL_IMPL
+    if (impl == "tc" or (impl == "auto" and D % 64 == 0 and D <= 256 and Kp <= 192)) and not want_score:
+        nbytes = int(lib().gfs_rowsel_tc_workspace_bytes(n, D))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=xt.device)
+        _call("gfs_kmeans_assign_tc", 6, _ptr(xt), n, n, D, _ptr(centers_t), K, Kp, _ptr(cnorm), _ptr(labels), _ptr(ws), nbytes, _stream())
+    else:
+        _call("gfs_kmeans_assign", 2, _ptr(xt), n, D, _ptr(centers_t), K, Kp, _ptr(cnorm), _ptr(labels), _ptr(score), _stream())
     return (labels, score) if want_score else labels
 
 

@@ -191,6 +191,17 @@ int gfs_joint_histogram_i32(const int32_t* a, const int32_t* b, int64_t n, int N
  *   cnorm     workspace, Kp floats;  labels (n) int32;  score optional (n) fp32 = |c|^2 - 2 x.c of the winner          */
 int gfs_kmeans_assign(const float* xt, int64_t n, int D, const float* centers_t, int K, int Kp,
                       float* cnorm, int32_t* labels, float* score, void* stream);
+/* The same two results on tcgen05 (gfs-3dseg_gws_b200/csrc/rowsel_tc.cu): bf16 hi/lo split product with fp32 accumulation in
+ * TMEM; rows whose best and second best score are closer than the product's error bound are re-evaluated with the pinned fp32
+ * chain, so the assignment / label is the one gfs_gw_project / gfs_kmeans_assign return, bit for bit; the GW softmax features
+ * (bf16 act tiles, 2e-2 tolerance) come from the tensor-core values.  D % 64 == 0, D <= 256, <= 192 entries; GW: N % 128 == 0.
+ * workspace: gfs_rowsel_tc_workspace_bytes(rows, D) bytes, 256-byte aligned (packed dictionary image, re-check list).        */
+int64_t gfs_rowsel_tc_workspace_bytes(int64_t rows, int D);
+int gfs_gw_project_tc(const float* ec, int64_t ec_bstride, int B, int D, int N, const float* gp_l2t, int G, int Gp,
+                      void* cosine_act, int kblocks, int kb0, float* cosine_cm, int32_t* assignment,
+                      void* workspace, int64_t workspace_bytes, void* stream);
+int gfs_kmeans_assign_tc(const float* xt, int64_t n, int64_t npad, int D, const float* centers_t, int K, int Kp,
+                         float* cnorm, int32_t* labels, void* workspace, int64_t workspace_bytes, void* stream);
 /* deterministic centroid sums over X (n, D) row-major: partial (P, K, D) fp32 + pcount (P, K) int32 workspaces with
  * P = gfs_kmeans_partials() (one per SM); sums (K, D) fp64 and counts (K) int64 are reduced in a fixed order.       */
 int gfs_kmeans_partials(void);

@@ -172,3 +172,34 @@ def test_kmeans_pp_trial_matches_a_float64_evaluation():
     assert float((m[:T, :n].cpu().double() - ref).abs().max()) <= 4e-5          # fp64 accumulation, ONE rounding to fp32 (d ~ 400)
     assert float(((pots[:T].cpu() - ref.sum(1)).abs() / ref.sum(1)).max()) <= 1e-5
     assert float(pots[T:].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("n,D,K,kind", [(6000, 192, 150, "mixture"), (50000, 192, 150, "mixture"), (4096, 64, 20, "mixture"),
+                                        (20000, 128, 180, "uniform"), (3000, 192, 150, "duplicate_centres"),
+                                        (2048, 192, 7, "zeros"), (10000, 256, 64, "offset")])
+def test_tensor_core_assign_returns_the_pinned_labels(n, D, K, kind):
+    """gfs_kmeans_assign_tc (bf16 hi/lo tcgen05 product, pinned fp32 re-check of the rows its error bound cannot decide) must
+    return the labels of the all-fp32 kernel and of the oracle, bit for bit -- including exact ties (lowest index wins)"""
+    from gfs3d import ops
+    X, rs = _mixture(n, D, K, seed=n + K)
+    if kind == "uniform":
+        X = rs.rand(n, D).astype(np.float32)               # no cluster structure: many near-ties
+    if kind == "offset":
+        X = (X * 0.05 + 20.0).astype(np.float32)           # far from the origin relative to the spread
+    if kind == "zeros":
+        X[:] = 0
+    C = X[rs.choice(n, K, replace=False)].copy()
+    if kind == "duplicate_centres":
+        C[K // 2:] = C[:K - K // 2]                        # exact ties between a centre and its copy
+    n4 = (n + 3) // 4 * 4
+    Kp = (K + 3) // 4 * 4
+    ct = np.zeros((D, Kp), np.float32)
+    ct[:, :K] = C.T
+    xt = torch.zeros(D, n4, device="cuda")
+    xt[:, :n] = torch.from_numpy(np.ascontiguousarray(X.T)).cuda()
+    ctd = torch.from_numpy(ct).cuda()
+    ref = ops.kmeans_assign(xt, ctd, K, impl="fp32")
+    got = ops.kmeans_assign(xt, ctd, K, impl="tc")
+    torch.cuda.synchronize()
+    assert torch.equal(ref, got), f"{int((ref != got).sum())} labels differ between the tensor-core and the fp32 kernel"
+    assert np.array_equal(got[:n].cpu().numpy(), O.kmeans_assign_exact(X, C))

@@ -264,3 +264,31 @@ def test_refine_proto_kernel_matches_the_reference_formula():
     got = ops.refine_proto(pp.cuda(), q.cuda(), gen.cuda(), base).cpu()
     assert float((got - ref).abs().max()) <= 2e-6
     assert float(w[0, 3]) == 0.0
+
+
+@pytest.mark.parametrize("B,N,G,kind", [(2, 256, 150, "random"), (4, 2048, 150, "random"), (2, 128, 180, "random"), (1, 128, 64, "random"),
+                                        (2, 256, 150, "duplicate_words"), (1, 128, 150, "zeros")])
+def test_gw_projection_tensor_core_equals_fp32_kernel(B, N, G, kind):
+    """gfs_gw_project_tc: assignments identical to the all-fp32 kernel (near-ties are re-evaluated with the pinned chain),
+    softmax features within the bf16 tolerance of the fp32 ones"""
+    ops = _ops()
+    g = torch.Generator().manual_seed(G * 7 + N)
+    ec = torch.randn(B, 192, N, generator=g).abs() * 0.3
+    gp = torch.randn(G, 192, generator=g)
+    if kind == "duplicate_words":
+        gp[G // 2:] = gp[:G - G // 2]                    # exact ties: the lower index must win
+    if kind == "zeros":
+        ec.zero_()
+    Gp = (G + 63) // 64 * 64
+    gp_l2t = torch.zeros(192, Gp)
+    gp_l2t[:, :G] = F.normalize(gp, dim=1).t()
+    out = {}
+    for impl in ("fp32", "tc"):
+        act = ops.new_act(B * N, Gp // 64 + 1, "cuda")
+        assign, cm = ops.gw_project(ec.cuda(), gp_l2t.cuda(), G, cosine_act=act, kb0=1, want_cm=True, impl=impl)
+        torch.cuda.synchronize()
+        out[impl] = (assign.cpu(), cm.cpu(), ops.act_to_dense(act, B * N).float().cpu())
+    assert torch.equal(out["fp32"][0], out["tc"][0]), f"{int((out['fp32'][0] != out['tc'][0]).sum())} assignments differ"
+    if kind != "zeros":
+        assert rel_err(out["tc"][1], out["fp32"][1].double()) <= 1e-3
+        assert rel_err(out["tc"][2], out["fp32"][2].double()) <= 8e-3
