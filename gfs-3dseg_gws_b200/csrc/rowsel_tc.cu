@@ -13,42 +13,48 @@
 // row) and overwrites their result.  Features (the softmax of the cosines) carry a 2e-2 tolerance and are taken from the
 // tensor-core values directly.
 //
-// Persistent CTA, 16 warps:
-//   warps 0-7   producers: fp32 channel-major points (coalesced over the 128 points of the tile) -> bf16 hi / lo operand
+// Persistent CTA, 24 warps:
+//   warps 0-15  producers: fp32 channel-major points (coalesced over the 128 points of the tile) -> bf16 hi / lo operand
 //               tiles in shared memory (K-major SWIZZLE_128B, 64 channels per stage), partial squared norms
-//   warp  8     TMA: the dictionary's packed hi / lo image (rowsel_pack_kernel), 2 x 24 KiB per stage
-//   warp  9     MMA issue (warp-uniform loop, one elected lane): 12 x tcgen05.mma 128x192x16 per stage
-//   warps 12-15 epilogue: tcgen05.ld, best / second best, (GW) softmax features as bf16 act tiles, ambiguity test
+//   (the dictionary's packed hi / lo image, rowsel_pack_kernel, is loaded ONCE per CTA by TMA and stays resident: 48 KiB per 64 channels)
+//   warp  16    MMA issue (warp-uniform loop, one elected lane): 12 x tcgen05.mma 128x192x16 per stage
+//   warps 20-23 epilogue: tcgen05.ld, best / second best, (GW) softmax features as bf16 act tiles, ambiguity test
+#include <cstddef>
+
 #include "fp32_tile.cuh"
 
 namespace gfs {
 
 constexpr int RT_ROWS = 128;      // points per tile
 constexpr int RT_N = 192;         // dictionary columns of one MMA (zero padded)
-constexpr int RT_THREADS = 512;
+constexpr int RT_PW = 16;          // producer warps: four 16-channel quarters of a 64-channel stage x 128 points
+constexpr int RT_THREADS = 32 * RT_PW + 32 + 96 + 128;   // + MMA warp (16), 3 idle warps, 4 epilogue warps (20-23)
 constexpr uint32_t RT_BTILE = RT_N * 128;   // bytes of one 64-channel dictionary tile (hi or lo)
 
-struct RtSmem {
-    uint8_t A[2][2][16384];       // [stage][hi | lo]  128 points x 64 channels
-    uint8_t B[2][2][RT_BTILE];    // [stage][hi | lo]  192 entries x 64 channels
-    float xn[4][2][RT_ROWS];      // [tile & 3][channel half] partial squared norms
-    uint64_t a_full[2], a_empty[2], b_full[2], b_empty[2], accf[2], acce[2];
+struct RtCtl {
+    uint64_t a_full[2], a_empty[2], b_full, accf[2], acce[2];
     uint32_t tmem_base;
 };
+struct RtSmem {                   // 1024-byte aligned; every operand tile starts on a 1024-byte boundary (SWIZZLE_128B)
+    uint8_t A[2][2][16384];       // [stage][hi | lo]  128 points x 64 channels
+    float xn[4][4][RT_ROWS];      // [tile & 3][channel quarter] partial squared norms
+    float cn[RT_N + 64];          // k-means: squared norms of the centres (padded: B below stays 1024-byte aligned)
+    uint8_t B[1][2][RT_BTILE];    // [k-block][hi | lo]  192 entries x 64 channels: the WHOLE dictionary stays resident (D/64 k-blocks,
+                                  // then the RtCtl block)
+};
+static_assert(offsetof(RtSmem, B) % 1024 == 0, "dictionary tiles must be 1024-byte aligned");
 
 enum { RT_GW = 0, RT_KMEANS = 1 };
 
 // dict_t (D, Gp) fp32 channel-major -> per 64-channel block: [hi tile | lo tile], 192 rows x 128 B, K-major SWIZZLE_128B.
 // Also the largest squared norm of an entry (k-means: scales the ambiguity bound).
-__global__ void rowsel_pack_kernel(const float* __restrict__ dict_t, int D, int G, int Gp, uint8_t* __restrict__ img,
-                                   float* __restrict__ cmax2) {
+__global__ void rowsel_pack_kernel(const float* __restrict__ dict_t, int D, int G, int Gp, uint8_t* __restrict__ img) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int chunks = D >> 3;
     if (i >= RT_N * chunks) return;
     const int j = i / chunks, qq = i - j * chunks;          // entry, 8-channel chunk
     const int kb = qq >> 3, q = qq & 7;
     uint32_t hp[4], lp[4];
-    float n2 = 0.0f;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         const int c = qq * 8 + 2 * e;
@@ -59,21 +65,55 @@ __global__ void rowsel_pack_kernel(const float* __restrict__ dict_t, int D, int 
         hh.y = h1;
         hp[e] = *reinterpret_cast<uint32_t*>(&hh);
         lp[e] = pack_bf16x2(v0 - __bfloat162float(h0), v1 - __bfloat162float(h1));
-        n2 = fmaf(v0, v0, fmaf(v1, v1, n2));
     }
     uint8_t* t = img + (size_t)kb * 2 * RT_BTILE;
     *reinterpret_cast<uint4*>(t + sw128(j, q)) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
     *reinterpret_cast<uint4*>(t + RT_BTILE + sw128(j, q)) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
-    // an upper bound of max_j |c_j|^2 is all that is needed: sum the chunk maxima's contributions per entry with atomics on
-    // the ordered bit pattern of a non-negative float (chunks of one entry add up)
-    if (cmax2) atomicAdd(cmax2 + 1 + j, n2);
 }
-__global__ void rowsel_cmax_kernel(float* __restrict__ cmax2, int G) {      // cmax2[0] = max_j cmax2[1 + j]
+// k-means: the largest squared norm of a centre scales the ambiguity bound; also clears the re-check counter
+__global__ void rowsel_cmax_kernel(const float* __restrict__ cnorm, int G, float* __restrict__ cmax2, int32_t* __restrict__ cnt) {
     float m = 0.0f;
-    for (int j = threadIdx.x; j < G; j += 32) m = fmaxf(m, cmax2[1 + j]);
+    if (cnorm)
+        for (int j = threadIdx.x; j < G; j += 32) m = fmaxf(m, cnorm[j]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (threadIdx.x == 0) cmax2[0] = m;
+    if (threadIdx.x == 0) {
+        cmax2[0] = m;
+        *cnt = 0;
+    }
+}
+
+// best, second best and the FIRST index of the best among 32 scores held in registers.  MAXM: larger is better.
+// A tournament tree (a pair keeps its best and its runner-up; merging two pairs is three independent min/max), not a
+// running update: the epilogue thread is alone on its scheduler slot and would otherwise crawl along one dependent chain.
+template <bool MAXM>
+__device__ __forceinline__ void rt_best2(const float (&v)[32], float& best, float& second, int& idx) {
+    float m[16], r2[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        m[i] = MAXM ? fmaxf(v[2 * i], v[2 * i + 1]) : fminf(v[2 * i], v[2 * i + 1]);
+        r2[i] = MAXM ? fminf(v[2 * i], v[2 * i + 1]) : fmaxf(v[2 * i], v[2 * i + 1]);
+    }
+#pragma unroll
+    for (int w = 8; w >= 1; w >>= 1) {
+#pragma unroll
+        for (int i = 0; i < w; ++i) {
+            const float a = m[i], b = m[i + w];
+            if (MAXM) {
+                m[i] = fmaxf(a, b);
+                r2[i] = fmaxf(fmaxf(fminf(a, b), r2[i]), r2[i + w]);
+            } else {
+                m[i] = fminf(a, b);
+                r2[i] = fminf(fminf(fmaxf(a, b), r2[i]), r2[i + w]);
+            }
+        }
+    }
+    best = m[0];
+    second = r2[0];
+    int ix = 31;
+#pragma unroll
+    for (int c = 30; c >= 0; --c) ix = v[c] == best ? c : ix;
+    idx = ix;
 }
 
 template <int MODE>
@@ -83,21 +123,25 @@ rowsel_tc_kernel(const float* __restrict__ x, int64_t bstride, int64_t cstride, 
                  uint8_t* __restrict__ cos_act, int kblocks, int kb0, float* __restrict__ cos_cm, int32_t* __restrict__ sel,
                  int32_t* __restrict__ recheck, int32_t* __restrict__ recheck_cnt) {
     extern __shared__ unsigned char smem_raw[];
-    RtSmem& s = *reinterpret_cast<RtSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+    RtSmem& sm = *reinterpret_cast<RtSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nkb = D >> 6;
+    RtCtl& s = *reinterpret_cast<RtCtl*>(reinterpret_cast<uint8_t*>(&sm) + offsetof(RtSmem, B) + (size_t)nkb * 2 * RT_BTILE);
 
-    if (warp == 9) {
+    if (tid < RT_N) sm.cn[tid] = (cnorm && tid < G) ? cnorm[tid] : 0.0f;
+    if (warp == RT_PW) {
         if (lane == 0) {
             for (int i = 0; i < 2; ++i) {
-                mbar_init(&s.a_full[i], 8);
+                mbar_init(&s.a_full[i], RT_PW);
                 mbar_init(&s.a_empty[i], 1);
-                mbar_init(&s.b_full[i], 1);
-                mbar_init(&s.b_empty[i], 1);
                 mbar_init(&s.accf[i], 1);
                 mbar_init(&s.acce[i], 4);
             }
+            mbar_init(&s.b_full, 1);
             mbar_fence_init();
+            // the dictionary image: one TMA bulk copy per k-block, once per CTA
+            mbar_arrive_expect_tx(&s.b_full, (uint32_t)nkb * 2u * RT_BTILE);
+            for (int kb = 0; kb < nkb; ++kb) tma_load_1d(sm.B[kb][0], img + (size_t)kb * 2 * RT_BTILE, 2u * RT_BTILE, &s.b_full);
         }
         __syncwarp();
         tmem_alloc(&s.tmem_base, 512);
@@ -107,85 +151,80 @@ rowsel_tc_kernel(const float* __restrict__ x, int64_t bstride, int64_t cstride, 
     tc_fence_after();
     const uint32_t tmem = s.tmem_base;
 
-    if (warp < 8) {
+    if (warp < RT_PW) {
         // =============================== producers ===============================
-        const int r = tid & 127, half = tid >> 7;           // point row, channel half of the 64-channel stage
-        int it = 0;                                           // (tile, kb) stage counter
-        int lt = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
-            const int64_t m = (int64_t)tile * RT_ROWS + r;
-            const bool valid = m < M;
+        // One flat sequence of (tile, 64-channel block) stages; the channels of the next TWO stages (also across a tile
+        // boundary) are in flight in registers while the current one is converted: the loop is bound by DRAM latency otherwise.
+        const int r = tid & 127, qt = tid >> 7;             // point row, 16-channel quarter of the 64-channel stage
+        const int my_tiles = blockIdx.x < ntiles ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+        const int S = my_tiles * nkb;
+        auto load16 = [&](int it, float (&dst)[16]) {         // stage it = (tile it / nkb, block it % nkb)
+            const int lt_ = it / nkb, kb_ = it - lt_ * nkb;
+            const int64_t m = ((int64_t)blockIdx.x + (int64_t)lt_ * gridDim.x) * RT_ROWS + r;
+            const bool valid = it < S && m < M;
+            const int64_t mm = valid ? m : 0;
             const float* xp;
             if (MODE == RT_GW) {
-                const int64_t b = (valid ? m : 0) / N;
-                xp = x + b * bstride + ((valid ? m : 0) - b * N);
+                const int64_t b = mm / N;
+                xp = x + b * bstride + (mm - b * N);
             } else {
-                xp = x + (valid ? m : 0);
+                xp = x + mm;
             }
-            float nrm = 0.0f;
-            float v[32];
+            xp += (int64_t)(kb_ * 64 + qt * 16) * cstride;
 #pragma unroll
-            for (int c = 0; c < 32; ++c) v[c] = valid ? __ldg(xp + (int64_t)(half * 32 + c) * cstride) : 0.0f;
-            for (int kb = 0; kb < nkb; ++kb, ++it) {
-                const int st = it & 1;
-                float vn[32];                                  // the next stage's channels are in flight while this one is converted
-                if (kb + 1 < nkb) {
+            for (int c = 0; c < 16; ++c) dst[c] = valid ? __ldg(xp + (int64_t)c * cstride) : 0.0f;
+        };
+        float v0[16], v1[16], v2[16];
+        load16(0, v0);
+        load16(1, v1);
+        float nrm = 0.0f;
+        int lt = 0, kb = 0;
+        for (int it = 0; it < S; ++it) {
+            const int st = it & 1;
+            load16(it + 2, v2);
+            mbar_wait(&s.a_empty[st], ((it >> 1) & 1) ^ 1);
+            uint8_t* ah = sm.A[st][0];
+            uint8_t* al = sm.A[st][1];
+            if (kb == 0) nrm = 0.0f;
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) vn[c] = valid ? __ldg(xp + (int64_t)((kb + 1) * 64 + half * 32 + c) * cstride) : 0.0f;
+            for (int q = 0; q < 2; ++q) {
+                uint32_t hp[4], lp[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float a0 = v0[q * 8 + 2 * e], a1 = v0[q * 8 + 2 * e + 1];
+                    // hi = the two values rounded to bf16 (one packed conversion), lo = the rounded residuals
+                    const uint32_t h = pack_bf16x2(a0, a1);
+                    hp[e] = h;
+                    lp[e] = pack_bf16x2(a0 - __uint_as_float(h << 16), a1 - __uint_as_float(h & 0xffff0000u));
+                    nrm = fmaf(a0, a0, fmaf(a1, a1, nrm));
                 }
-                mbar_wait(&s.a_empty[st], ((it >> 1) & 1) ^ 1);
-                uint8_t* ah = s.A[st][0];
-                uint8_t* al = s.A[st][1];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    uint32_t hp[4], lp[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float v0 = v[q * 8 + 2 * e], v1 = v[q * 8 + 2 * e + 1];
-                        const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
-                        __nv_bfloat162 hh;
-                        hh.x = h0;
-                        hh.y = h1;
-                        hp[e] = *reinterpret_cast<uint32_t*>(&hh);
-                        lp[e] = pack_bf16x2(v0 - __bfloat162float(h0), v1 - __bfloat162float(h1));
-                        nrm = fmaf(v0, v0, fmaf(v1, v1, nrm));
-                    }
-                    const uint32_t o = sw128(r, half * 4 + q);
-                    *reinterpret_cast<uint4*>(ah + o) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-                    *reinterpret_cast<uint4*>(al + o) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
-                }
-                // the partial norm goes out BEFORE the tile's last arrive: that release orders it before the epilogue's read
-                if (kb == nkb - 1) s.xn[lt & 3][half][r] = nrm;
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&s.a_full[st]);
-                if (kb + 1 < nkb) {
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) v[c] = vn[c];
-                }
+                const uint32_t o = sw128(r, qt * 2 + q);
+                *reinterpret_cast<uint4*>(ah + o) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+                *reinterpret_cast<uint4*>(al + o) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
             }
-        }
-    } else if (warp == 8) {
-        // =============================== TMA: dictionary tiles ===============================
-        if (lane == 0) {
-            int it = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const int st = it & 1;
-                    mbar_wait(&s.b_empty[st], ((it >> 1) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&s.b_full[st], 2u * RT_BTILE);
-                    tma_load_1d(s.B[st][0], img + (size_t)kb * 2 * RT_BTILE, 2u * RT_BTILE, &s.b_full[st]);
-                }
+            // the partial norm goes out BEFORE the tile's last arrive: that release orders it before the epilogue's read
+            if (kb == nkb - 1) sm.xn[lt & 3][qt][r] = nrm;
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s.a_full[st]);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                v0[c] = v1[c];
+                v1[c] = v2[c];
+            }
+            if (++kb == nkb) {
+                kb = 0;
+                ++lt;
             }
         }
-        __syncwarp();
-    } else if (warp == 9) {
+    } else if (warp == RT_PW) {
         // =============================== MMA issue ===============================
         const uint32_t idesc = umma_idesc_bf16(128, RT_N);
-        const uint64_t a0 = umma_desc_sw128(smem_u32(s.A[0][0]));
-        const uint64_t b0 = umma_desc_sw128(smem_u32(s.B[0][0]));
+        const uint64_t a0 = umma_desc_sw128(smem_u32(sm.A[0][0]));
+        const uint64_t b0 = umma_desc_sw128(smem_u32(sm.B[0][0]));
         constexpr uint32_t A_ST = 2 * 16384 >> 4, A_LO = 16384 >> 4, B_ST = 2 * RT_BTILE >> 4, B_LO = RT_BTILE >> 4;
         int it = 0, lt = 0;
+        mbar_wait(&s.b_full, 0);
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
             const int acc = lt & 1;
             mbar_wait(&s.acce[acc], ((lt >> 1) & 1) ^ 1);
@@ -193,10 +232,9 @@ rowsel_tc_kernel(const float* __restrict__ x, int64_t bstride, int64_t cstride, 
             for (int kb = 0; kb < nkb; ++kb, ++it) {
                 const int st = it & 1;
                 mbar_wait(&s.a_full[st], (it >> 1) & 1);
-                mbar_wait(&s.b_full[st], (it >> 1) & 1);
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint64_t aB = a0 + (uint64_t)(st * A_ST), bB = b0 + (uint64_t)(st * B_ST);
+                    const uint64_t aB = a0 + (uint64_t)(st * A_ST), bB = b0 + (uint64_t)(kb * B_ST);
                     const uint32_t d = tmem + acc * 256;
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
@@ -205,13 +243,12 @@ rowsel_tc_kernel(const float* __restrict__ x, int64_t bstride, int64_t cstride, 
                         umma_bf16(d, aB + A_LO + ks * 2, bB + ks * 2, idesc, 1u);
                     }
                     umma_commit(&s.a_empty[st]);
-                    umma_commit(&s.b_empty[st]);
                     if (kb == nkb - 1) umma_commit(&s.accf[acc]);
                 }
                 __syncwarp();
             }
         }
-    } else if (warp >= 12) {
+    } else if (warp >= RT_PW + 4) {
         // =============================== epilogue: one thread per point ===============================
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
@@ -224,7 +261,7 @@ rowsel_tc_kernel(const float* __restrict__ x, int64_t bstride, int64_t cstride, 
             tc_fence_after();
             const int64_t m = (int64_t)tile * RT_ROWS + row;
             const bool valid = m < M;
-            const float nrm = s.xn[lt & 3][0][row] + s.xn[lt & 3][1][row];
+            const float nrm = (sm.xn[lt & 3][0][row] + sm.xn[lt & 3][1][row]) + (sm.xn[lt & 3][2][row] + sm.xn[lt & 3][3][row]);
             const uint32_t t0 = tbase + acc * 256;
             uint32_t rr[32];
             float b1, b2;
@@ -236,16 +273,18 @@ rowsel_tc_kernel(const float* __restrict__ x, int64_t bstride, int64_t cstride, 
                 for (int ch = 0; ch * 32 < G; ++ch) {
                     tmem_ld32(t0 + ch * 32, rr);
                     tmem_ld_wait32(rr);
+                    float lg[32];
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        const float lg = ch * 32 + c < G ? __uint_as_float(rr[c]) * inv : -INFINITY;
-                        if (lg > b1) {
-                            b2 = b1;
-                            b1 = lg;
-                            i1 = ch * 32 + c;
-                        } else {
-                            b2 = fmaxf(b2, lg);
-                        }
+                    for (int c = 0; c < 32; ++c) lg[c] = ch * 32 + c < G ? __uint_as_float(rr[c]) * inv : -INFINITY;
+                    float cb, cs;
+                    int ci;
+                    rt_best2<true>(lg, cb, cs, ci);
+                    if (cb > b1) {                       // an equal best in a later chunk keeps the earlier (lower) index
+                        b2 = fmaxf(b1, cs);
+                        b1 = cb;
+                        i1 = ch * 32 + ci;
+                    } else {
+                        b2 = fmaxf(b2, cb);
                     }
                 }
                 float sum = 0.0f;
@@ -286,17 +325,24 @@ rowsel_tc_kernel(const float* __restrict__ x, int64_t bstride, int64_t cstride, 
                 for (int ch = 0; ch * 32 < G; ++ch) {
                     tmem_ld32(t0 + ch * 32, rr);
                     tmem_ld_wait32(rr);
+                    float sc[32];
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        const int col = ch * 32 + c;
-                        const float sc = col < G ? fmaf(-2.0f, __uint_as_float(rr[c]), __ldg(cnorm + (col < G ? col : 0))) : INFINITY;
-                        if (sc < b1) {
-                            b2 = b1;
-                            b1 = sc;
-                            i1 = col;
-                        } else {
-                            b2 = fminf(b2, sc);
-                        }
+                    for (int c = 0; c < 32; c += 4) {
+                        const float4 cn4 = *reinterpret_cast<const float4*>(sm.cn + ch * 32 + c);
+                        sc[c] = ch * 32 + c < G ? fmaf(-2.0f, __uint_as_float(rr[c]), cn4.x) : INFINITY;
+                        sc[c + 1] = ch * 32 + c + 1 < G ? fmaf(-2.0f, __uint_as_float(rr[c + 1]), cn4.y) : INFINITY;
+                        sc[c + 2] = ch * 32 + c + 2 < G ? fmaf(-2.0f, __uint_as_float(rr[c + 2]), cn4.z) : INFINITY;
+                        sc[c + 3] = ch * 32 + c + 3 < G ? fmaf(-2.0f, __uint_as_float(rr[c + 3]), cn4.w) : INFINITY;
+                    }
+                    float cb, cs;
+                    int ci;
+                    rt_best2<false>(sc, cb, cs, ci);
+                    if (cb < b1) {                       // an equal best in a later chunk keeps the earlier (lower) index
+                        b2 = fminf(b1, cs);
+                        b1 = cb;
+                        i1 = ch * 32 + ci;
+                    } else {
+                        b2 = fminf(b2, cb);
                     }
                 }
             }
@@ -318,7 +364,7 @@ rowsel_tc_kernel(const float* __restrict__ x, int64_t bstride, int64_t cstride, 
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) {
+    if (warp == RT_PW) {
         tc_fence_after();
         tmem_dealloc(tmem, 512);
     }
@@ -344,14 +390,29 @@ rowsel_recheck_kernel(const float* __restrict__ x, int64_t bstride, int64_t cstr
         }
         float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         float nrm = 0.0f;
-        for (int c = 0; c < D; ++c) {
-            const float a = __ldg(xp + (int64_t)c * cstride);
-            nrm = fmaf(a, a, nrm);
-            const float* g = dict_t + (int64_t)c * Gp;
+        // the row's channels are fetched 32 at a time (one per lane, all in flight together) and broadcast by shuffles, so the
+        // pinned chains below contain no dependent global load; the dictionary loads of a block are independent of the chain
+        for (int c0 = 0; c0 < D; c0 += 32) {
+            const float xv = c0 + lane < D ? __ldg(xp + (int64_t)(c0 + lane) * cstride) : 0.0f;
+#pragma unroll 1
+            for (int c1 = 0; c1 < 32 && c0 + c1 < D; c1 += 8) {
+                float gv[8][6];                      // 48 dictionary values in flight before the first fma needs one
 #pragma unroll
-            for (int j = 0; j < 6; ++j) {
-                const int col = j * 32 + lane;
-                if (col < G) acc[j] = fmaf(a, __ldg(g + col), acc[j]);
+                for (int c2 = 0; c2 < 8; ++c2) {
+                    const float* g = dict_t + (int64_t)(c0 + c1 + c2) * Gp;
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) gv[c2][j] = (j * 32 + lane < G && c0 + c1 + c2 < D) ? __ldg(g + j * 32 + lane) : 0.0f;
+                }
+#pragma unroll
+                for (int c2 = 0; c2 < 8; ++c2) {
+                    if (c0 + c1 + c2 < D) {          // uniform
+                        const float a = __shfl_sync(0xffffffffu, xv, c1 + c2);
+                        nrm = fmaf(a, a, nrm);
+#pragma unroll
+                        for (int j = 0; j < 6; ++j)
+                            if (j * 32 + lane < G) acc[j] = fmaf(a, gv[c2][j], acc[j]);
+                    }
+                }
             }
         }
         float best = MODE == RT_GW ? -INFINITY : INFINITY;
@@ -390,8 +451,8 @@ static RtPlan rt_plan(int64_t rows, int D) {
     RtPlan p;
     p.off_img = 0;
     size_t o = (size_t)(D >> 6) * 2 * RT_BTILE;
-    p.off_cmax = o;                       // 1 + 192 floats
-    o += 256 * 4;
+    p.off_cmax = o;
+    o += 256;
     p.off_cnt = o;
     o += 256;
     p.off_list = o;
@@ -411,16 +472,16 @@ static int rt_run(const char* who, const float* x, int64_t bstride, int64_t cstr
     float* cmax2 = reinterpret_cast<float*>(ws + p.off_cmax);
     int32_t* cnt = reinterpret_cast<int32_t*>(ws + p.off_cnt);
     int32_t* list = reinterpret_cast<int32_t*>(ws + p.off_list);
-    GFS_CUDA_OK(cudaMemsetAsync(ws + p.off_cmax, 0, p.off_list - p.off_cmax, st));
     const int pk = RT_N * (D >> 3);
-    rowsel_pack_kernel<<<(pk + 255) / 256, 256, 0, st>>>(dict_t, D, G, Gp, ws, cmax2);
+    rowsel_pack_kernel<<<(pk + 255) / 256, 256, 0, st>>>(dict_t, D, G, Gp, ws);
     GFS_LAUNCH_OK("rowsel_pack_kernel");
-    rowsel_cmax_kernel<<<1, 32, 0, st>>>(cmax2, G);
+    rowsel_cmax_kernel<<<1, 32, 0, st>>>(MODE == RT_KMEANS ? cnorm : nullptr, G, cmax2, cnt);
     GFS_LAUNCH_OK("rowsel_cmax_kernel");
     const int ntiles = (int)((M + RT_ROWS - 1) / RT_ROWS);
     const int sms = sm_count();
     GFS_REQUIRE(sms > 0, GFS_ERR_CUDA, "%s: cannot query the device", who);
-    const size_t smem = sizeof(RtSmem) + 1024;
+    const size_t smem = offsetof(RtSmem, B) + (size_t)(D >> 6) * 2 * RT_BTILE + sizeof(RtCtl) + 1024;
+    GFS_REQUIRE(smem <= 227 * 1024, GFS_ERR_UNSUPPORTED, "%s: D=%d: the resident dictionary does not fit shared memory (use the fp32 entry point)", who, D);
     GFS_CUDA_OK(allow_smem(reinterpret_cast<const void*>(rowsel_tc_kernel<MODE>), smem));
     rowsel_tc_kernel<MODE><<<ntiles < sms ? ntiles : sms, RT_THREADS, smem, st>>>(
         x, bstride, cstride, D, N, M, ntiles, ws, G, Gp, cnorm, cmax2, static_cast<uint8_t*>(cos_act), kblocks, kb0, cos_cm, sel, list, cnt);
@@ -433,7 +494,7 @@ static int rt_run(const char* who, const float* x, int64_t bstride, int64_t cstr
 }  // namespace gfs
 
 extern "C" int64_t gfs_rowsel_tc_workspace_bytes(int64_t rows, int D) {
-    if (rows <= 0 || D <= 0 || D % 64 != 0 || D > 256) return 0;
+    if (rows <= 0 || D <= 0 || D % 64 != 0 || D > 192) return 0;
     return (int64_t)gfs::rt_plan(rows, D).total;
 }
 
@@ -443,7 +504,7 @@ extern "C" int gfs_gw_project_tc(const float* ec, int64_t ec_bstride, int B, int
     using namespace gfs;
     GFS_REQUIRE(ec && gp_l2t && assignment, GFS_ERR_BAD_ARG, "gfs_gw_project_tc: null pointer");
     GFS_REQUIRE(B > 0 && D > 0 && N > 0 && G > 0, GFS_ERR_BAD_ARG, "gfs_gw_project_tc: non-positive size");
-    GFS_REQUIRE(D % 64 == 0 && D <= 256, GFS_ERR_UNSUPPORTED, "gfs_gw_project_tc: D=%d (need a multiple of 64, <= 256; use gfs_gw_project)", D);
+    GFS_REQUIRE(D % 64 == 0 && D <= 192, GFS_ERR_UNSUPPORTED, "gfs_gw_project_tc: D=%d (need a multiple of 64, <= 192; use gfs_gw_project)", D);
     GFS_REQUIRE(N % 128 == 0, GFS_ERR_UNSUPPORTED, "gfs_gw_project_tc: N=%d (need a multiple of 128; use gfs_gw_project)", N);
     GFS_REQUIRE(G <= Gp && Gp <= RT_N && Gp % 64 == 0, GFS_ERR_UNSUPPORTED, "gfs_gw_project_tc: G=%d Gp=%d (need G <= Gp <= 192, Gp %% 64 == 0)", G, Gp);
     GFS_REQUIRE((reinterpret_cast<uintptr_t>(cosine_act) & 15) == 0, GFS_ERR_BAD_ARG, "gfs_gw_project_tc: cosine_act must be 16-byte aligned");
@@ -458,7 +519,7 @@ extern "C" int gfs_kmeans_assign_tc(const float* xt, int64_t n, int64_t npad, in
     GFS_REQUIRE(xt && centers_t && cnorm && labels, GFS_ERR_BAD_ARG, "gfs_kmeans_assign_tc: null pointer");
     GFS_REQUIRE(n > 0 && npad >= n && D > 0 && K > 0, GFS_ERR_BAD_ARG, "gfs_kmeans_assign_tc: non-positive size");
     GFS_REQUIRE(n < (int64_t)1 << 31, GFS_ERR_UNSUPPORTED, "gfs_kmeans_assign_tc: n=%lld exceeds 2^31 per shard", (long long)n);
-    GFS_REQUIRE(D % 64 == 0 && D <= 256, GFS_ERR_UNSUPPORTED, "gfs_kmeans_assign_tc: D=%d (need a multiple of 64, <= 256; use gfs_kmeans_assign)", D);
+    GFS_REQUIRE(D % 64 == 0 && D <= 192, GFS_ERR_UNSUPPORTED, "gfs_kmeans_assign_tc: D=%d (need a multiple of 64, <= 192; use gfs_kmeans_assign)", D);
     GFS_REQUIRE(K <= Kp && Kp <= RT_N, GFS_ERR_UNSUPPORTED, "gfs_kmeans_assign_tc: K=%d Kp=%d (need K <= Kp <= 192)", K, Kp);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     sqnorm_kernel<<<dim3((Kp + 255) / 256, 1), 256, 0, st>>>(centers_t, 0, D, Kp, cnorm);

@@ -237,7 +237,7 @@ def gw_project(ec: torch.Tensor, gp_l2t: torch.Tensor, G: int, cosine_act: Optio
     assign = torch.empty(B, N, dtype=torch.int32, device=ec.device)
     cm = torch.empty(B, G, N, dtype=torch.float32, device=ec.device) if want_cm else None
     impl = impl or ROWSEL_IMPL
-    if impl == "tc" or (impl == "auto" and D % 64 == 0 and D <= 256 and N % 128 == 0 and Gp <= 192 and Gp % 64 == 0):
+    if impl == "tc" or (impl == "auto" and D % 64 == 0 and D <= 192 and N % 128 == 0 and Gp <= 192 and Gp % 64 == 0):
         nbytes = int(lib().gfs_rowsel_tc_workspace_bytes(B * N, D))
         ws = torch.empty(nbytes, dtype=torch.uint8, device=ec.device)
         _call("gfs_gw_project_tc", 4, _ptr(ec), ec.stride(0), B, D, N, _ptr(gp_l2t), G, Gp, _ptr(cosine_act),
@@ -334,7 +334,7 @@ def kmeans_assign(xt: torch.Tensor, centers_t: torch.Tensor, K: int, want_score:
     labels = torch.empty(n, dtype=torch.int32, device=xt.device)
     score = torch.empty(n, dtype=torch.float32, device=xt.device) if want_score else None
     impl = impl or ROWSEL_IMPL
-    if (impl == "tc" or (impl == "auto" and D % 64 == 0 and D <= 256 and Kp <= 192)) and not want_score:
+    if (impl == "tc" or (impl == "auto" and D % 64 == 0 and D <= 192 and Kp <= 192)) and not want_score:
         nbytes = int(lib().gfs_rowsel_tc_workspace_bytes(n, D))
         ws = torch.empty(nbytes, dtype=torch.uint8, device=xt.device)
         _call("gfs_kmeans_assign_tc", 6, _ptr(xt), n, n, D, _ptr(centers_t), K, Kp, _ptr(cnorm), _ptr(labels), _ptr(ws), nbytes, _stream())

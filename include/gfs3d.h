@@ -194,7 +194,7 @@ int gfs_kmeans_assign(const float* xt, int64_t n, int D, const float* centers_t,
 /* The same two results on tcgen05 (gfs-3dseg_gws_b200/csrc/rowsel_tc.cu): bf16 hi/lo split product with fp32 accumulation in
  * TMEM; rows whose best and second best score are closer than the product's error bound are re-evaluated with the pinned fp32
  * chain, so the assignment / label is the one gfs_gw_project / gfs_kmeans_assign return, bit for bit; the GW softmax features
- * (bf16 act tiles, 2e-2 tolerance) come from the tensor-core values.  D % 64 == 0, D <= 256, <= 192 entries; GW: N % 128 == 0.
+ * (bf16 act tiles, 2e-2 tolerance) come from the tensor-core values.  D % 64 == 0, D <= 192, <= 192 entries; GW: N % 128 == 0.
  * workspace: gfs_rowsel_tc_workspace_bytes(rows, D) bytes, 256-byte aligned (packed dictionary image, re-check list).        */
 int64_t gfs_rowsel_tc_workspace_bytes(int64_t rows, int D);
 int gfs_gw_project_tc(const float* ec, int64_t ec_bstride, int B, int D, int N, const float* gp_l2t, int G, int Gp,
