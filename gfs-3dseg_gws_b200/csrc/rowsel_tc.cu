@@ -44,7 +44,7 @@ struct RtSmem {                   // 1024-byte aligned; every operand tile start
 };
 static_assert(offsetof(RtSmem, B) % 1024 == 0, "dictionary tiles must be 1024-byte aligned");
 
-enum { RT_GW = 0, RT_KMEANS = 1 };
+enum { RT_GW = 0, RT_KMEANS = 1, RT_KMEANS_PM = 2 };   // _PM: points are rows of a row-major (n, D) matrix (contiguous 128-point tiles)
 
 // dict_t (D, Gp) fp32 channel-major -> per 64-channel block: [hi tile | lo tile], 192 rows x 128 B, K-major SWIZZLE_128B.
 // Also the largest squared norm of an entry (k-means: scales the ambiguity bound).
@@ -163,6 +163,19 @@ rowsel_tc_kernel(const float* __restrict__ x, int64_t bstride, int64_t cstride, 
             const int64_t m = ((int64_t)blockIdx.x + (int64_t)lt_ * gridDim.x) * RT_ROWS + r;
             const bool valid = it < S && m < M;
             const int64_t mm = valid ? m : 0;
+            if (MODE == RT_KMEANS_PM) {
+                // point-major: the thread's 16 channels are 64 contiguous bytes of its own row
+                const float4* xp4 = reinterpret_cast<const float4*>(x + mm * D + kb_ * 64 + qt * 16);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float4 t = valid ? __ldg(xp4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    dst[4 * c] = t.x;
+                    dst[4 * c + 1] = t.y;
+                    dst[4 * c + 2] = t.z;
+                    dst[4 * c + 3] = t.w;
+                }
+                return;
+            }
             const float* xp;
             if (MODE == RT_GW) {
                 const int64_t b = mm / N;
@@ -253,7 +266,7 @@ rowsel_tc_kernel(const float* __restrict__ x, int64_t bstride, int64_t cstride, 
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
         const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16);
-        const float cmax = MODE == RT_KMEANS ? sqrtf(__ldg(cmax2)) : 0.0f;
+        const float cmax = MODE != RT_GW ? sqrtf(__ldg(cmax2)) : 0.0f;
         int lt = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
             const int acc = lt & 1;
@@ -385,6 +398,8 @@ rowsel_recheck_kernel(const float* __restrict__ x, int64_t bstride, int64_t cstr
         if (MODE == RT_GW) {
             const int64_t b = m / N;
             xp = x + b * bstride + (m - b * N);
+        } else if (MODE == RT_KMEANS_PM) {
+            xp = x + m * D;                          // cstride == 1
         } else {
             xp = x + m;
         }
@@ -475,7 +490,7 @@ static int rt_run(const char* who, const float* x, int64_t bstride, int64_t cstr
     const int pk = RT_N * (D >> 3);
     rowsel_pack_kernel<<<(pk + 255) / 256, 256, 0, st>>>(dict_t, D, G, Gp, ws);
     GFS_LAUNCH_OK("rowsel_pack_kernel");
-    rowsel_cmax_kernel<<<1, 32, 0, st>>>(MODE == RT_KMEANS ? cnorm : nullptr, G, cmax2, cnt);
+    rowsel_cmax_kernel<<<1, 32, 0, st>>>(MODE != RT_GW ? cnorm : nullptr, G, cmax2, cnt);
     GFS_LAUNCH_OK("rowsel_cmax_kernel");
     const int ntiles = (int)((M + RT_ROWS - 1) / RT_ROWS);
     const int sms = sm_count();
@@ -513,17 +528,22 @@ extern "C" int gfs_gw_project_tc(const float* ec, int64_t ec_bstride, int B, int
                          assignment, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int gfs_kmeans_assign_tc(const float* xt, int64_t n, int64_t npad, int D, const float* centers_t, int K, int Kp, float* cnorm,
-                                    int32_t* labels, void* workspace, int64_t workspace_bytes, void* stream) {
+extern "C" int gfs_kmeans_assign_tc(const float* X, int64_t n, int64_t ld, int point_major, int D, const float* centers_t, int K, int Kp,
+                                    float* cnorm, int32_t* labels, void* workspace, int64_t workspace_bytes, void* stream) {
     using namespace gfs;
-    GFS_REQUIRE(xt && centers_t && cnorm && labels, GFS_ERR_BAD_ARG, "gfs_kmeans_assign_tc: null pointer");
-    GFS_REQUIRE(n > 0 && npad >= n && D > 0 && K > 0, GFS_ERR_BAD_ARG, "gfs_kmeans_assign_tc: non-positive size");
+    GFS_REQUIRE(X && centers_t && cnorm && labels, GFS_ERR_BAD_ARG, "gfs_kmeans_assign_tc: null pointer");
+    GFS_REQUIRE(n > 0 && D > 0 && K > 0, GFS_ERR_BAD_ARG, "gfs_kmeans_assign_tc: non-positive size");
+    GFS_REQUIRE(point_major ? ld == D : ld >= n, GFS_ERR_BAD_ARG, "gfs_kmeans_assign_tc: leading dimension %lld does not fit the layout", (long long)ld);
     GFS_REQUIRE(n < (int64_t)1 << 31, GFS_ERR_UNSUPPORTED, "gfs_kmeans_assign_tc: n=%lld exceeds 2^31 per shard", (long long)n);
     GFS_REQUIRE(D % 64 == 0 && D <= 192, GFS_ERR_UNSUPPORTED, "gfs_kmeans_assign_tc: D=%d (need a multiple of 64, <= 192; use gfs_kmeans_assign)", D);
     GFS_REQUIRE(K <= Kp && Kp <= RT_N, GFS_ERR_UNSUPPORTED, "gfs_kmeans_assign_tc: K=%d Kp=%d (need K <= Kp <= 192)", K, Kp);
+    GFS_REQUIRE((reinterpret_cast<uintptr_t>(X) & 15) == 0, GFS_ERR_BAD_ARG, "gfs_kmeans_assign_tc: X must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     sqnorm_kernel<<<dim3((Kp + 255) / 256, 1), 256, 0, st>>>(centers_t, 0, D, Kp, cnorm);
     GFS_LAUNCH_OK("sqnorm_kernel");
-    return rt_run<RT_KMEANS>("gfs_kmeans_assign_tc", xt, 0, npad, D, 1, n, centers_t, K, Kp, cnorm, nullptr, 0, 0, nullptr, labels, workspace,
+    if (point_major)
+        return rt_run<RT_KMEANS_PM>("gfs_kmeans_assign_tc", X, 0, 1, D, 1, n, centers_t, K, Kp, cnorm, nullptr, 0, 0, nullptr, labels, workspace,
+                                    workspace_bytes, st);
+    return rt_run<RT_KMEANS>("gfs_kmeans_assign_tc", X, 0, ld, D, 1, n, centers_t, K, Kp, cnorm, nullptr, 0, 0, nullptr, labels, workspace,
                              workspace_bytes, st);
 }

@@ -25,7 +25,7 @@ SIGNATURES = {
     "gfs_attention_fwd": [_p, _i, _i, _i, _i, _f, _p, _i64, _p, _i, _i, _p],
     "gfs_gw_project": [_p, _i64, _i, _i, _i, _p, _i, _i, _p, _i, _i, _p, _p, _p],
     "gfs_gw_project_tc": [_p, _i64, _i, _i, _i, _p, _i, _i, _p, _i, _i, _p, _p, _p, _i64, _p],
-    "gfs_kmeans_assign_tc": [_p, _i64, _i64, _i, _p, _i, _i, _p, _p, _p, _i64, _p],
+    "gfs_kmeans_assign_tc": [_p, _i64, _i64, _i, _i, _p, _i, _i, _p, _p, _p, _i64, _p],
     "gfs_cos_logits": [_p, _i64, _i, _i, _i, _p, _i, _i, _p, _i, _p, _f, _p, _p],
     "gfs_softmax_pool": [_p, _p, _i64, _i, _i, _i, _i, _p, _p, _p, _p],
     "gfs_refine_proto": [_p, _p, _p, _i, _i, _i, _i, _p, _p],

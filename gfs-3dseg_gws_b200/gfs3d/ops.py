@@ -337,10 +337,29 @@ def kmeans_assign(xt: torch.Tensor, centers_t: torch.Tensor, K: int, want_score:
     if (impl == "tc" or (impl == "auto" and D % 64 == 0 and D <= 192 and Kp <= 192)) and not want_score:
         nbytes = int(lib().gfs_rowsel_tc_workspace_bytes(n, D))
         ws = torch.empty(nbytes, dtype=torch.uint8, device=xt.device)
-        _call("gfs_kmeans_assign_tc", 6, _ptr(xt), n, n, D, _ptr(centers_t), K, Kp, _ptr(cnorm), _ptr(labels), _ptr(ws), nbytes, _stream())
+        _call("gfs_kmeans_assign_tc", 6, _ptr(xt), n, n, 0, D, _ptr(centers_t), K, Kp, _ptr(cnorm), _ptr(labels), _ptr(ws), nbytes, _stream())
     else:
         _call("gfs_kmeans_assign", 2, _ptr(xt), n, D, _ptr(centers_t), K, Kp, _ptr(cnorm), _ptr(labels), _ptr(score), _stream())
     return (labels, score) if want_score else labels
+
+
+def kmeans_assign_rows(X: torch.Tensor, centers_t: torch.Tensor, K: int) -> torch.Tensor:
+    """X (n, D) fp32 ROW-major (the M-step's layout), centers_t (D, Kp) -> labels (n) int32 through gfs_kmeans_assign_tc: a
+    128-point tile is one contiguous piece of HBM.  Same labels as kmeans_assign on the transposed copy."""
+    _need_cuda(X, centers_t)
+    n, D = X.shape
+    assert X.is_contiguous() and centers_t.is_contiguous() and centers_t.shape[0] == D
+    Kp = centers_t.shape[1]
+    cnorm = torch.empty(Kp, dtype=torch.float32, device=X.device)
+    labels = torch.empty(n, dtype=torch.int32, device=X.device)
+    nbytes = int(lib().gfs_rowsel_tc_workspace_bytes(n, D))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=X.device)
+    _call("gfs_kmeans_assign_tc", 6, _ptr(X), n, D, 1, D, _ptr(centers_t), K, Kp, _ptr(cnorm), _ptr(labels), _ptr(ws), nbytes, _stream())
+    return labels
+
+
+def kmeans_rows_eligible(D: int, Kp: int) -> bool:
+    return ROWSEL_IMPL != "fp32" and D % 64 == 0 and D <= 192 and Kp <= 192
 
 
 def kmeans_accumulate(X: torch.Tensor, labels: torch.Tensor, K: int, n_valid: Optional[int] = None):

@@ -200,7 +200,9 @@ int64_t gfs_rowsel_tc_workspace_bytes(int64_t rows, int D);
 int gfs_gw_project_tc(const float* ec, int64_t ec_bstride, int B, int D, int N, const float* gp_l2t, int G, int Gp,
                       void* cosine_act, int kblocks, int kb0, float* cosine_cm, int32_t* assignment,
                       void* workspace, int64_t workspace_bytes, void* stream);
-int gfs_kmeans_assign_tc(const float* xt, int64_t n, int64_t npad, int D, const float* centers_t, int K, int Kp,
+/* X: point_major = 0: (D, ld) channel-major as gfs_kmeans_assign takes it (ld >= n);  point_major = 1: (n, D) row-major (ld = D),
+ * the layout the M-step reads -- a 128-point tile is then one contiguous piece of HBM.                                   */
+int gfs_kmeans_assign_tc(const float* X, int64_t n, int64_t ld, int point_major, int D, const float* centers_t, int K, int Kp,
                          float* cnorm, int32_t* labels, void* workspace, int64_t workspace_bytes, void* stream);
 /* deterministic centroid sums over X (n, D) row-major: partial (P, K, D) fp32 + pcount (P, K) int32 workspaces with
  * P = gfs_kmeans_partials() (one per SM); sums (K, D) fp64 and counts (K) int64 are reduced in a fixed order.       */

@@ -32,6 +32,8 @@ a = ops.kmeans_assign(xt, ct, K, impl="fp32"); b = ops.kmeans_assign(xt, ct, K, 
 print(json.dumps({"kmeans_labels_equal": bool(torch.equal(a, b))}))
 for impl in ("fp32", "tc"):
     print(json.dumps({"kmeans": impl, "n": n, "ms": time_ms(lambda: ops.kmeans_assign(xt, ct, K, impl=impl))}), flush=True)
+c = ops.kmeans_assign_rows(X, ct, K)
+print(json.dumps({"kmeans": "tc rows", "n": n, "equal": bool(torch.equal(a, c)), "ms": time_ms(lambda: ops.kmeans_assign_rows(X, ct, K))}), flush=True)
 # how many rows does the tensor-core path hand to the pinned re-check?
 from gfs3d._lib import lib
 def recheck_count_gw():

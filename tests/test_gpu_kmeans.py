@@ -203,3 +203,5 @@ def test_tensor_core_assign_returns_the_pinned_labels(n, D, K, kind):
     torch.cuda.synchronize()
     assert torch.equal(ref, got), f"{int((ref != got).sum())} labels differ between the tensor-core and the fp32 kernel"
     assert np.array_equal(got[:n].cpu().numpy(), O.kmeans_assign_exact(X, C))
+    rows = ops.kmeans_assign_rows(torch.from_numpy(X).cuda(), ctd, K)            # the row-major (M-step) layout
+    assert torch.equal(rows, ref[:n]), "point-major tensor-core path differs"
