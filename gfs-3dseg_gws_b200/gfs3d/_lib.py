@@ -35,6 +35,7 @@ SIGNATURES = {
     "gfs_kmeans_pp_trial": [_p, _i64, _i64, _i, _p, _p, _i, _p, _p, _p, _p],
     # training path
     "gfs_gemm_f32": [_p, _i64, _i, _i64, _p, _i64, _i, _i64, _p, _i64, _i, _i64, _p, _i, _i, _i, _i, _i, _p, _i, _p],
+    "gfs_gemm_tf32": [_p, _i64, _i, _i64, _p, _i64, _i, _i64, _p, _i64, _i, _i64, _p, _i, _i, _i, _i, _i, _p, _i, _i, _p],
     "gfs_bn_stats": [_p, _i64, _i, _i64, _p, _p, _p, _p],
     "gfs_bn_act_fwd": [_p, _i64, _p, _i64, _i, _i64, _p, _p, _f, _p],
     "gfs_bn_act_bwd": [_p, _i64, _p, _i64, _p, _i64, _i, _i64, _p, _p, _p, _p, _f, _p, _p, _p, _p],

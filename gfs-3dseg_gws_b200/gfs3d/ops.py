@@ -382,13 +382,27 @@ def kmeans_accumulate(X: torch.Tensor, labels: torch.Tensor, K: int, n_valid: Op
 # =====================================================================================================================
 # training path: raw wrappers (fp32, channel-major (C, M) 2-D tensors)
 # =====================================================================================================================
+# the training path's GEMMs (csrc/gemm_tf32.cu, csrc/gemm_f32.cu):
+#   "tf32x3" tcgen05 kind::tf32 with hi/lo operand pairs (3 MMAs per k-step): fp32-grade products on the tensor pipe (default)
+#   "tf32"   one tf32 product per k-step: 2^-10 relative; fine for a forward pass, too coarse for the backward (branch flips)
+#   "f32"    packed-FFMA2 CUDA cores
+TRAIN_GEMM = os.environ.get("GFS_TRAIN_GEMM", "tf32x3")
+
+
 def gemm_f32(A, lda, a_trans, B, ldb, b_trans, R, Ncols, K, C, ldc, c_trans=False, bias=None, batch=1, a_bs=0, b_bs=0, c_bs=0,
-             splitk=1, accumulate=False):
+             splitk=1, accumulate=False, impl=None):
     _need_cuda(A, B, C, bias)
+    impl = impl or TRAIN_GEMM
+    if impl not in ("tf32x3", "tf32", "f32"):
+        raise ValueError(f"unknown GEMM implementation {impl!r}")
     ws = torch.empty(splitk * R * Ncols, dtype=torch.float32, device=C.device) if splitk > 1 else None
-    _call("gfs_gemm_f32", 2 if splitk > 1 else 1, _ptr(A), lda, int(a_trans), a_bs, _ptr(B), ldb, int(b_trans), b_bs, _ptr(C), ldc,
-          int(c_trans), c_bs, _ptr(bias), R, Ncols, K, batch, splitk, _ptr(ws), int(accumulate), _stream(),
-          tag=(f"[{R}x{Ncols}x{K} b{batch} t{int(a_trans)}{int(b_trans)}{int(c_trans)} sk{splitk}]" if PROFILE_SHAPES else ""))
+    tag = f"[{R}x{Ncols}x{K} b{batch} t{int(a_trans)}{int(b_trans)}{int(c_trans)} sk{splitk}]" if PROFILE_SHAPES else ""
+    head = (_ptr(A), lda, int(a_trans), a_bs, _ptr(B), ldb, int(b_trans), b_bs, _ptr(C), ldc, int(c_trans), c_bs, _ptr(bias), R, Ncols, K,
+            batch, splitk, _ptr(ws), int(accumulate))
+    if impl == "f32":
+        _call("gfs_gemm_f32", 2 if splitk > 1 else 1, *head, _stream(), tag=tag)
+    else:
+        _call("gfs_gemm_tf32", 2 if splitk > 1 else 1, *head, int(impl == "tf32x3"), _stream(), tag=("x3" if impl == "tf32x3" else "") + tag)
     return C
 
 

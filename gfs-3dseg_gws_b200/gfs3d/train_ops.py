@@ -11,6 +11,11 @@ from . import ops
 BN_EPS = 1e-5
 
 
+def _exact():
+    """GEMM implementation for products that feed a cancellation: never the single-pass tf32"""
+    return "f32" if ops.TRAIN_GEMM == "f32" else "tf32x3"
+
+
 def to_cm(x):
     """(B, C, N) -> (C, B*N) contiguous"""
     B, C, N = x.shape
@@ -106,7 +111,10 @@ class EdgeConvTrain(torch.autograd.Function):
         Wa, Wb = W1f[:, :C], W1f[:, C:]
         Wpq = torch.cat([Wa, Wb - Wa], dim=0).contiguous()                          # (128, C): [P | Q] = Wpq x
         pq = torch.empty(M, 128, dtype=torch.float32, device=x.device)
-        ops.gemm_f32(Wpq, C, True, x, M, False, 128, M, C, pq, 128, c_trans=True)   # point-major rows for the gather
+        # fp32-grade products are REQUIRED here (and in the two matching backward GEMMs): H = P[j] + Q[i] is
+        # W_a (x_j - x_i) + W_b x_i evaluated as a DIFFERENCE of per-point terms, so an operand rounding of 2^-11 |W_a x| (plain
+        # tf32) would be of the order of the neighbour differences themselves
+        ops.gemm_f32(Wpq, C, True, x, M, False, 128, M, C, pq, 128, c_trans=True, impl=_exact())   # point-major rows for the gather
         H = ops.edge_gather(pq, idx, B, N, k)                                       # (64, E), pre-BN1
         del pq
         g1f, b1f, g2f, b2f = (t.detach().contiguous().float() for t in (g1, b1, g2, b2))
@@ -138,11 +146,11 @@ class EdgeConvTrain(torch.autograd.Function):
         dpq = ops.edge_scatter(dH, idx, B, N, k)                                    # (M, 128): scatter-add over the graph
         del dH
         dWpq = torch.empty(128, C, dtype=torch.float32, device=x.device)
-        ops.gemm_f32(dpq, 128, False, x, M, True, 128, C, M, dWpq, C, splitk=ops._splitk(M))
+        ops.gemm_f32(dpq, 128, False, x, M, True, 128, C, M, dWpq, C, splitk=ops._splitk(M), impl=_exact())
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(C, M, dtype=torch.float32, device=x.device)
-            ops.gemm_f32(Wpq, C, False, dpq, 128, True, C, M, 128, dx, M)
+            ops.gemm_f32(Wpq, C, False, dpq, 128, True, C, M, 128, dx, M, impl=_exact())
         dW1 = torch.cat([dWpq[:64] - dWpq[64:], dWpq[64:]], dim=1).reshape(64, 2 * C, 1, 1)
         return dx, None, dW1, sgx1, sg1, dW2.reshape(64, 64, 1, 1), sgx2, sg2, None, None, None
 

@@ -234,6 +234,17 @@ int gfs_gemm_f32(const float* A, int64_t lda, int a_trans, int64_t a_bstride,
                  float* C, int64_t ldc, int c_trans, int64_t c_bstride,
                  const float* bias, int R, int Ncols, int K, int batch, int splitk, float* workspace, int accumulate, void* stream);
 
+/* the same contract on the tensor cores (csrc/gemm_tf32.cu): tcgen05.mma kind::tf32, fp32 accumulation in TMEM; operands are
+ * rounded to tf32 (round-to-nearest) on their way into shared memory.
+ *   split3 == 0: one product per k-step,  |C - exact| <= 2^-10 * sum_k |Aop||Bop|
+ *   split3 != 0: 3xTF32 -- operands kept as hi + lo tf32 pairs, hi*hi + hi*lo + lo*hi per k-step: fp32-grade products
+ *                (~1e-6); this is what the training path calls (the backward pass needs it, see the file header)        */
+int gfs_gemm_tf32(const float* A, int64_t lda, int a_trans, int64_t a_bstride,
+                  const float* B, int64_t ldb, int b_trans, int64_t b_bstride,
+                  float* C, int64_t ldc, int c_trans, int64_t c_bstride,
+                  const float* bias, int R, int Ncols, int K, int batch, int splitk, float* workspace, int accumulate, int split3,
+                  void* stream);
+
 /* BatchNorm with batch statistics (nn.BatchNorm1d/2d in training mode, model/dgcnn.py:54-55,73-74): biased variance      */
 /* workspace: 2*16*C doubles (per-channel partial sums, combined in a fixed order)                                          */
 int gfs_bn_stats(const float* x, int64_t ld, int C, int64_t M, double* workspace, float* mean, float* var, void* stream);
