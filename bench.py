@@ -95,26 +95,60 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def reference_forward(device, state_dict, gp):
+    """(kind, fn): fn(x) -> logits through the reference's OWN model classes (model/capl.py:144-192, unmodified byte copies
+    staged by oracle/make_ref.py under oracle/_ref/reference; kind "reference") or, when they have not been staged, through the
+    oracle port (oracle/gfs_oracle.py:forward_eval, the same ATen ops in the same order; kind "port")."""
+    import contextlib
+    import importlib
+    from oracle import make_ref
+    gened, bc, nc = head_inputs(device)
+    ref = make_ref.ref_dir()
+    if ref is None:
+        from oracle import gfs_oracle as O
+        sd = {k: v.detach().float().to(device) for k, v in state_dict.items()}
+        gpd = gp.to(device)
+        return "port", lambda x: O.forward_eval(sd, gpd, x, gened, bc, nc, BASE_NUM, 1.2, k=KNN)[0]
+    ours = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "model" or k.startswith("model.")}
+    import types
+    pkg = types.ModuleType("model")                                  # the reference's model/ has no __init__.py (namespace package):
+    pkg.__path__ = [os.path.join(ref, "model")]                      # a regular package of the same name would shadow it
+    sys.modules["model"] = pkg
+    try:
+        capl = importlib.import_module("model.capl")                 # the reference's model package, not this repo's
+    finally:
+        for k in [k for k in sys.modules if k == "model" or k.startswith("model.")]:
+            del sys.modules[k]
+        sys.modules.update(ours)
+    assert os.path.abspath(capl.__file__).startswith(os.path.abspath(ref))
+    with contextlib.redirect_stdout(sys.stderr):
+        m = capl.mpti_net_Point_GeoAsWeight_v2(classes=CLASSES, criterion=torch.nn.CrossEntropyLoss(ignore_index=255), args=model_args(),
+                                               base_num=BASE_NUM, gp=gp.to(device), energy=0.9)
+    m.load_state_dict({k: v.detach().float().cpu() for k, v in state_dict.items()})
+    m = m.to(device).eval()
+    return "reference", lambda x: m(x=x, y=None, eval_model=True, gen_proto=False, gened_proto=gened, base_class_coding=bc,
+                                    novel_class_coding=nc)[0]
+
+
 def cpu_port_blocks_per_sec(state_dict, gp, sample_blocks, iters, threads):
-    """the oracle port (same ATen ops as the reference's CPU path, oracle/gfs_oracle.py) on the host cores"""
+    """the reference's CPU path on the host cores: (blocks/s, kind) -- see reference_forward"""
     from gfs3d.synthetic import synthetic_blocks
-    from oracle import gfs_oracle as O
     torch.set_num_threads(threads)
-    sd = {k: v.detach().float().cpu() for k, v in state_dict.items()}
-    gened, bc, nc = head_inputs("cpu")
+    kind, fwd = reference_forward("cpu", state_dict, gp)
     x = synthetic_blocks(sample_blocks, NPTS, seed=999)
     with torch.no_grad():
-        O.forward_eval(sd, gp.cpu(), x[:1], gened, bc, nc, BASE_NUM, 1.2, k=KNN)     # warm-up
+        fwd(x[:1])     # warm-up
         t0 = time.perf_counter()
         for _ in range(iters):
-            O.forward_eval(sd, gp.cpu(), x, gened, bc, nc, BASE_NUM, 1.2, k=KNN)
+            fwd(x)
         dt = time.perf_counter() - t0
-    return sample_blocks * iters / dt
+    return sample_blocks * iters / dt, kind
 
 
 def run_reference(a):
-    """--impl reference: the reference's own CPU implementation of the path (Python/ATen; restated in oracle/ because
-    /root/reference cannot travel to the GPU box), all host threads, bounded sample per step."""
+    """--impl reference: the reference's own CPU implementation of the path -- its unmodified model classes when
+    oracle/make_ref.py staged them (oracle/_ref, git-ignored, travels with the snapshot), else the oracle port --
+    all host threads, bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -122,13 +156,13 @@ def run_reference(a):
     m, gp = build_model("cpu")
     sample = 4
     t0 = time.perf_counter()
-    v = cpu_port_blocks_per_sec(m.state_dict(), gp, sample, max(1, a.steps), threads)
+    v, kind = cpu_port_blocks_per_sec(m.state_dict(), gp, sample, max(1, a.steps), threads)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": 1e3 * sample / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": f"GFS eval forward, S3DIS-shaped blocks N={NPTS} C=9 k={KNN}, {CLASSES} classes, {G} GWs",
                        "blocks_per_step": sample, "note": "CPU path, bounded sample of the batch=32 workload"},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": f"{sample} blocks x {max(1, a.steps)} steps"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "sample": f"{sample} blocks x {max(1, a.steps)} steps"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.perf_counter() - t0}
     print(json.dumps(line))
@@ -309,25 +343,23 @@ def reference_on_b200(dev, state_dict, gp, B, iters=3):
     """context number: the reference's stock-PyTorch path (the oracle port executes the same ATen ops in
     the same order as model/capl.py:144-192) eager on the SAME B200, fp32 with TF32 off"""
     from gfs3d.synthetic import synthetic_blocks
-    from oracle import gfs_oracle as O
     old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
     try:
-        sd = {k: v.detach().float().to(dev) for k, v in state_dict.items()}
-        gened, bc, nc = head_inputs(dev)
+        kind, fwd = reference_forward(dev, state_dict, gp)
         x = synthetic_blocks(B, NPTS, seed=999).to(dev)
         with torch.no_grad():
-            O.forward_eval(sd, gp.to(dev), x, gened, bc, nc, BASE_NUM, 1.2, k=KNN)
+            fwd(x)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(iters):
-                O.forward_eval(sd, gp.to(dev), x, gened, bc, nc, BASE_NUM, 1.2, k=KNN)
+                fwd(x)
             e1.record()
             torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / iters
-        return {"value": B / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "batch": B,
+        return {"value": B / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "batch": B, "kind": kind,
                 "what": "stock PyTorch eager (ATen / cuBLAS / cuDNN ops of the reference, fp32, TF32 off) on this B200, inputs resident"}
     except Exception as e:                                            # noqa: BLE001  (a context number must not kill the bench line)
         return {"error": f"{type(e).__name__}: {e}"[:200]}
@@ -530,8 +562,8 @@ def main():
     if not a.no_cpu_baseline:
         threads = os.cpu_count() or 1
         sample, iters = 4, 3
-        v = cpu_port_blocks_per_sec(m.state_dict(), gp, sample, iters, threads)
-        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": f"{sample} blocks x {iters} iterations of the same workload"}
+        v, kind = cpu_port_blocks_per_sec(m.state_dict(), gp, sample, iters, threads)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "sample": f"{sample} blocks x {iters} iterations of the same workload"}
 
     ref_gpu = None if a.no_cpu_baseline else reference_on_b200(dev, m.state_dict(), gp, B)
     total_blocks = B * a.steps * world

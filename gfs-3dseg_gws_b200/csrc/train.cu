@@ -114,6 +114,77 @@ __global__ void bn_bwd_finish_kernel(const double* __restrict__ part, int C, int
     sum_gx[c] = (float)q;
 }
 
+// The same two kernels for the BatchNorm that feeds max-over-k (model/dgcnn.py:55-58,118): the incoming gradient is dy (C, Mp)
+// at the arg-max edge of every (channel, point) and zero on the other k-1 edges, so the (C, Mp*k) tensor gfs_max_over_k_bwd would
+// write is never built: the sums run over the Mp arg-max edges only, the apply pass reads dy / arg per point.
+__global__ void __launch_bounds__(512)
+bn_bwd_reduce_argmax_kernel(const float* __restrict__ dy, int64_t lddy, const uint8_t* __restrict__ arg, int k,
+                            const float* __restrict__ x, int64_t ldx, int64_t Mp, const float* __restrict__ mean,
+                            const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                            float slope, double* __restrict__ part) {
+    __shared__ double red[16];
+    const int c = blockIdx.x;
+    const float mu = mean[c], is = invstd[c], ga = gamma[c], be = beta[c];
+    const float* dr = dy + (int64_t)c * lddy;
+    const uint8_t* ar = arg + (int64_t)c * Mp;
+    const float* xr = x + (int64_t)c * ldx;
+    const int64_t per = (Mp + gridDim.y - 1) / gridDim.y;
+    const int64_t i0 = per * blockIdx.y, i1 = (i0 + per) < Mp ? (i0 + per) : Mp;
+    double s = 0.0, q = 0.0;
+    for (int64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+        const float xh = (xr[i * k + ar[i]] - mu) * is;
+        const float u = fmaf(ga, xh, be);
+        const float g = dr[i] * (u > 0.0f ? 1.0f : slope);
+        s += g;
+        q += (double)g * xh;
+    }
+    s = block_sum(s, red);
+    q = block_sum(q, red);
+    if (threadIdx.x == 0) {
+        part[((int64_t)c * gridDim.y + blockIdx.y) * 2 + 0] = s;
+        part[((int64_t)c * gridDim.y + blockIdx.y) * 2 + 1] = q;
+    }
+}
+
+// VEC = 4: k % 4 == 0 and 16-byte aligned rows -> four consecutive edges of ONE point per thread (float4 in / out)
+template <int VEC>
+__global__ void bn_bwd_apply_argmax_kernel(const float* __restrict__ dy, int64_t lddy, const uint8_t* __restrict__ arg, int k,
+                                           const float* __restrict__ x, int64_t ldx, float* __restrict__ dx, int64_t lddx, int64_t Mp,
+                                           const float* __restrict__ mean, const float* __restrict__ invstd,
+                                           const float* __restrict__ gamma, const float* __restrict__ beta, float slope,
+                                           const float* __restrict__ sum_g, const float* __restrict__ sum_gx) {
+    const int c = blockIdx.y;
+    const int64_t E = Mp * k;
+    const float mu = mean[c], is = invstd[c], ga = gamma[c], be = beta[c];
+    const float a = sum_g[c] / (float)E, b = sum_gx[c] / (float)E, kk = ga * is;
+    const float* dr = dy + (int64_t)c * lddy;
+    const uint8_t* ar = arg + (int64_t)c * Mp;
+    const float* xr = x + (int64_t)c * ldx;
+    float* o = dx + (int64_t)c * lddx;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v * VEC < E; v += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = v * VEC;
+        const int64_t p = i / k;
+        const int slot0 = (int)(i - p * k), hit = (int)__ldg(ar + p) - slot0;     // arg-max edge is element `hit` of this group
+        float xin[VEC], out[VEC];
+        if (VEC == 4) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(xr + i));
+            xin[0] = t.x; xin[1] = t.y; xin[2] = t.z; xin[3] = t.w;
+        } else {
+            xin[0] = __ldg(xr + i);
+        }
+        const float d = (hit >= 0 && hit < VEC) ? __ldg(dr + p) : 0.0f;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            const float xh = (xin[e] - mu) * is;
+            const float u = fmaf(ga, xh, be);
+            const float g = (e == hit) ? d * (u > 0.0f ? 1.0f : slope) : 0.0f;
+            out[e] = kk * (g - a - xh * b);
+        }
+        if (VEC == 4) *reinterpret_cast<float4*>(o + i) = make_float4(out[0], out[1], out[2], out[3]);
+        else o[i] = out[0];
+    }
+}
+
 // dx = gamma * invstd * (g - sum_g / M - xhat * sum_gx / M)
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, int64_t lddy, const float* __restrict__ x, int64_t ldx,
                                     float* __restrict__ dx, int64_t lddx, int64_t M, const float* __restrict__ mean,
@@ -166,31 +237,44 @@ edge_gather_kernel(const float* __restrict__ pq, const int32_t* __restrict__ idx
         for (int c = 0; c < 64; ++c) H[(int64_t)c * E + e] = T[c][threadIdx.x];
 }
 
-// backward of the gather: dP[j] += dH[:, e], dQ[i] += dH[:, e]   (dpq must be zeroed; fp32 atomics -> order not fixed)
-__global__ void __launch_bounds__(128)
-edge_scatter_kernel(const float* __restrict__ dH, const int32_t* __restrict__ idx, int N, int k, int64_t E, float* __restrict__ dpq) {
-    __shared__ float T[64][129];
-    const int64_t e0 = (int64_t)blockIdx.x * 128;
-    {
-        const int64_t e = e0 + threadIdx.x;
-        for (int c = 0; c < 64; ++c) T[c][threadIdx.x] = e < E ? dH[(int64_t)c * E + e] : 0.0f;
+// backward of the gather: dP[j] += dH[:, e] (j = idx[e]), dQ[i] = sum_slot dH[:, i*k + slot]   (the P half of dpq must be zeroed)
+// A CTA owns ES_PPB consecutive points = ES_PPB*k consecutive edges, staged channel-major through shared memory.  The Q half
+// needs no atomics (all k edges of a point are in the tile: one plain store per channel, fixed summation order); the P half goes
+// out as 16-byte vector reductions (red.global.add.v4.f32, sm_90+): 16 per edge instead of 64 scalar atomics.  The order in which
+// different CTAs add into one dP row is not fixed -- the only non-deterministic summation of the training path.
+constexpr int ES_PPB = 8;
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(256)
+edge_scatter_kernel(const float* __restrict__ dH, const int32_t* __restrict__ idx, int N, int k, int64_t Mp, int64_t E,
+                    float* __restrict__ dpq) {
+    extern __shared__ float T[];                        // [64][EL + 1]
+    const int EL = ES_PPB * k, LD = EL + 1;
+    const int64_t i0 = (int64_t)blockIdx.x * ES_PPB;
+    const int64_t e0 = i0 * k;
+    const int np = (int)((Mp - i0) < ES_PPB ? (Mp - i0) : ES_PPB);
+    const int ne = np * k;
+    for (int t = threadIdx.x; t < 64 * EL; t += 256) {
+        const int c = t / EL, el = t - c * EL;
+        T[c * LD + el] = el < ne ? __ldg(dH + (int64_t)c * E + e0 + el) : 0.0f;
     }
     __syncthreads();
-    const int q = threadIdx.x & 7, sub = threadIdx.x >> 3;
-    for (int p = 0; p < 8; ++p) {
-        const int el = p * 16 + sub;
-        const int64_t e = e0 + el;
-        if (e >= E) continue;
-        const int64_t i = e / k;
-        const int64_t j = (i / N) * N + idx[e];
-        float* P = dpq + j * 128 + q * 8;
-        float* Q = dpq + i * 128 + 64 + q * 8;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const float v = T[q * 8 + u][el];
-            atomicAdd(P + u, v);
-            atomicAdd(Q + u, v);
-        }
+    for (int t = threadIdx.x; t < 64 * np; t += 256) {
+        const int p = t >> 6, c = t & 63;
+        const float* r = T + c * LD + p * k;
+        float sum = 0.0f;
+        for (int sl = 0; sl < k; ++sl) sum += r[sl];
+        dpq[(i0 + p) * 128 + 64 + c] = sum;
+    }
+    for (int t = threadIdx.x; t < ne * 16; t += 256) {
+        const int el = t >> 4, q = t & 15;
+        const int64_t i = i0 + el / k;
+        const int64_t j = (i / N) * N + __ldg(idx + e0 + el);
+        const float* r = T + (4 * q) * LD + el;
+        red_add_v4(dpq + j * 128 + 4 * q, r[0], r[LD], r[2 * LD], r[3 * LD]);
     }
 }
 
@@ -307,6 +391,32 @@ extern "C" int gfs_bn_act_bwd(const float* dy, int64_t lddy, const float* x, int
     return GFS_OK;
 }
 
+extern "C" int gfs_bn_act_bwd_argmax(const float* dy, int64_t lddy, const uint8_t* arg, int k, const float* x, int64_t ldx, float* dx,
+                                     int64_t lddx, int C, int64_t Mp, const float* mean, const float* invstd, const float* gamma,
+                                     const float* beta, float slope, double* workspace, float* sum_g, float* sum_gx, void* stream) {
+    GFS_REQUIRE(dy && arg && x && dx && mean && invstd && gamma && beta && workspace && sum_g && sum_gx && C > 0 && Mp > 0 && k > 0 && k <= 255,
+                GFS_ERR_BAD_ARG, "gfs_bn_act_bwd_argmax: bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int S = Mp >= 65536 ? BN_SPLIT : 1;
+    bn_bwd_reduce_argmax_kernel<<<dim3(C, S), 512, 0, st>>>(dy, lddy, arg, k, x, ldx, Mp, mean, invstd, gamma, beta, slope, workspace);
+    GFS_LAUNCH_OK("bn_bwd_reduce_argmax_kernel");
+    bn_bwd_finish_kernel<<<(C + 127) / 128, 128, 0, st>>>(workspace, C, S, sum_g, sum_gx);
+    GFS_LAUNCH_OK("bn_bwd_finish_kernel");
+    const int64_t E = Mp * k;
+    const bool vec = (k % 4 == 0) && (ldx % 4 == 0) && (lddx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(dx) & 15) == 0);
+    const int64_t items = vec ? E / 4 : E;
+    const unsigned gx = (unsigned)((items + 1023) / 1024 < 2048 ? (items + 1023) / 1024 : 2048);
+    if (vec)
+        bn_bwd_apply_argmax_kernel<4><<<dim3(gx, C), 256, 0, st>>>(dy, lddy, arg, k, x, ldx, dx, lddx, Mp, mean, invstd, gamma, beta, slope,
+                                                                   sum_g, sum_gx);
+    else
+        bn_bwd_apply_argmax_kernel<1><<<dim3(gx, C), 256, 0, st>>>(dy, lddy, arg, k, x, ldx, dx, lddx, Mp, mean, invstd, gamma, beta, slope,
+                                                                   sum_g, sum_gx);
+    GFS_LAUNCH_OK("bn_bwd_apply_argmax_kernel");
+    return GFS_OK;
+}
+
 extern "C" int gfs_edge_gather(const float* pq, const int32_t* idx, int B, int N, int k, float* H, void* stream) {
     GFS_REQUIRE(pq && idx && H && B > 0 && N > 0 && k > 0, GFS_ERR_BAD_ARG, "gfs_edge_gather: bad argument");
     const int64_t E = (int64_t)B * N * k;
@@ -317,8 +427,11 @@ extern "C" int gfs_edge_gather(const float* pq, const int32_t* idx, int B, int N
 
 extern "C" int gfs_edge_scatter(const float* dH, const int32_t* idx, int B, int N, int k, float* dpq, void* stream) {
     GFS_REQUIRE(dH && idx && dpq && B > 0 && N > 0 && k > 0, GFS_ERR_BAD_ARG, "gfs_edge_scatter: bad argument");
-    const int64_t E = (int64_t)B * N * k;
-    edge_scatter_kernel<<<(unsigned)((E + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(dH, idx, N, k, E, dpq);
+    GFS_REQUIRE(k <= 64, GFS_ERR_UNSUPPORTED, "gfs_edge_scatter: k <= 64");
+    const int64_t Mp = (int64_t)B * N, E = Mp * k;
+    const size_t smem = (size_t)64 * (ES_PPB * k + 1) * sizeof(float);
+    GFS_CUDA_OK(allow_smem(reinterpret_cast<const void*>(edge_scatter_kernel), (size_t)64 * (ES_PPB * 64 + 1) * sizeof(float)));
+    edge_scatter_kernel<<<(unsigned)((Mp + ES_PPB - 1) / ES_PPB), 256, smem, static_cast<cudaStream_t>(stream)>>>(dH, idx, N, k, Mp, E, dpq);
     GFS_LAUNCH_OK("edge_scatter_kernel");
     return GFS_OK;
 }

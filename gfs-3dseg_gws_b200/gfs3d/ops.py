@@ -461,6 +461,20 @@ def bn_act_bwd(dy, x, mean, invstd, gamma, beta, slope):
     return dx, sg, sgx
 
 
+def bn_act_bwd_argmax(dy, arg, k, x, mean, invstd, gamma, beta, slope):
+    """bn_act_bwd(max_over_k_bwd(dy, arg, k), x, ...) without the (C, Mp*k) gradient in between"""
+    C, E = x.shape
+    Mp = arg.shape[1]
+    assert E == Mp * k and dy.shape == arg.shape
+    dx = torch.empty(C, E, dtype=torch.float32, device=x.device)
+    sg = torch.empty(C, dtype=torch.float32, device=x.device)
+    sgx = torch.empty(C, dtype=torch.float32, device=x.device)
+    ws = torch.empty(2 * 16 * C, dtype=torch.float64, device=x.device)
+    _call("gfs_bn_act_bwd_argmax", 3, _ptr(dy), dy.stride(0), _ptr(arg), k, _ptr(x), x.stride(0), _ptr(dx), E, C, Mp, _ptr(mean),
+          _ptr(invstd), _ptr(gamma), _ptr(beta), float(slope), _ptr(ws), _ptr(sg), _ptr(sgx), _stream())
+    return dx, sg, sgx
+
+
 def edge_gather(pq, idx, B, N, k):
     H = torch.empty(64, B * N * k, dtype=torch.float32, device=pq.device)
     _call("gfs_edge_gather", 1, _ptr(pq), _ptr(idx), B, N, k, _ptr(H), _stream())

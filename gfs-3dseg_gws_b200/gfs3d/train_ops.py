@@ -135,9 +135,8 @@ class EdgeConvTrain(torch.autograd.Function):
     def backward(ctx, dy, *_):
         x, idx, Wpq, W2f, H, h1, Z, m1, is1, g1, b1, m2, is2, g2, b2, arg = ctx.saved_tensors
         B, N, k, C, M = ctx.dims
-        dA = ops.max_over_k_bwd(dy.contiguous(), arg, k)                            # (64, E): dy at the arg-max edge
-        dZ, sg2, sgx2 = ops.bn_act_bwd(dA, Z, m2, is2, g2, b2, 0.2)
-        del dA
+        # dy lives at the arg-max edge only: BN2's backward reads (dy, arg) directly, the (64, E) sparse gradient is never built
+        dZ, sg2, sgx2 = ops.bn_act_bwd_argmax(dy.contiguous(), arg, k, Z, m2, is2, g2, b2, 0.2)
         dW2 = ops.conv_wgrad(dZ, h1)
         dh1 = ops.conv_dgrad(W2f, dZ)
         del dZ

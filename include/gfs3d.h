@@ -255,6 +255,12 @@ int gfs_bn_act_fwd(const float* x, int64_t ldx, float* y, int64_t ldy, int C, in
 int gfs_bn_act_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, float* dx, int64_t lddx, int C, int64_t M,
                    const float* mean, const float* invstd, const float* gamma, const float* beta, float slope,
                    double* workspace, float* sum_g, float* sum_gx, void* stream);
+/* the same for the BatchNorm in front of max-over-k (model/dgcnn.py:55-58,118): dy (C, Mp) is the gradient at the arg-max edge
+ * arg[c, p] (< k) of every (channel, point), zero on the other edges; x and dx are the (C, Mp*k) per-edge tensors.  Replaces
+ * gfs_max_over_k_bwd + gfs_bn_act_bwd without building the (C, Mp*k) gradient in between.                                   */
+int gfs_bn_act_bwd_argmax(const float* dy, int64_t lddy, const uint8_t* arg, int k, const float* x, int64_t ldx, float* dx,
+                          int64_t lddx, int C, int64_t Mp, const float* mean, const float* invstd, const float* gamma,
+                          const float* beta, float slope, double* workspace, float* sum_g, float* sum_gx, void* stream);
 
 /* edge tensor of model/dgcnn.py:35-41 after the split first conv: H[c, e] = P[j(e), c] + Q[i(e), c]  (pq point-major (M,128)) */
 int gfs_edge_gather(const float* pq, const int32_t* idx, int B, int N, int k, float* H, void* stream);

@@ -1,2 +1,3 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests/test_gpu_reference_callers.py -q -s -x 2>&1 | tail -30
+timeout 900 python -m pytest tests/test_gpu_train.py -q --tb=short 2>&1 | grep -v "^model using\|^$\|^     +" | tail -30
+timeout 300 python scripts/bench_train.py --steps 5 > gpurun_out/r2i_train.json 2> gpurun_out/r2i_train.err; tail -3 gpurun_out/r2i_train.err

@@ -111,6 +111,41 @@ def test_conv_bn_act_function_vs_autograd(train_gemm):
         assert max(errs.values()) <= TOL, (slope, errs)
 
 
+@pytest.mark.parametrize("Mp,k", [(1000, 20), (70000, 20), (333, 7), (64, 40)])
+def test_bn_backward_through_max_over_k_without_the_sparse_tensor(Mp, k):
+    """gfs_bn_act_bwd_argmax == gfs_bn_act_bwd(gfs_max_over_k_bwd(dy, arg)) (model/dgcnn.py:55-58,118 backward)"""
+    from gfs3d import ops
+    g = torch.Generator().manual_seed(Mp + k)
+    C = 64
+    Z = torch.randn(C, Mp * k, generator=g).cuda()
+    dy = torch.randn(C, Mp, generator=g).cuda()
+    arg = torch.randint(0, k, (C, Mp), generator=g, dtype=torch.uint8).cuda()
+    ga, be = (1 + 0.3 * torch.randn(C, generator=g)).cuda(), (0.2 * torch.randn(C, generator=g)).cuda()
+    mean, var = ops.bn_stats(Z)
+    invstd = torch.rsqrt(var + 1e-5)
+    dA = ops.max_over_k_bwd(dy, arg, k)
+    want = ops.bn_act_bwd(dA, Z, mean, invstd, ga, be, 0.2)
+    got = ops.bn_act_bwd_argmax(dy, arg, k, Z, mean, invstd, ga, be, 0.2)
+    for a, b, name in zip(got, want, ("dx", "sum_g", "sum_gx")):
+        assert rel_err(a, b) <= 2e-6, name
+
+
+@pytest.mark.parametrize("B,N,k", [(2, 128, 20), (1, 100, 7), (3, 64, 40), (1, 2048, 20)])
+def test_edge_scatter_vs_index_add(B, N, k):
+    """backward of the edge gather (model/dgcnn.py:35-41): dP[j] += dH[e], dQ[i] = sum over the point's k edges"""
+    from gfs3d import ops
+    g = torch.Generator().manual_seed(B * N + k)
+    E = B * N * k
+    dH = torch.randn(64, E, generator=g)
+    idx = torch.randint(0, N, (B, N, k), generator=g)
+    ref = torch.zeros(B * N, 128, dtype=torch.float64)
+    j = (idx + torch.arange(B).view(B, 1, 1) * N).reshape(-1)
+    ref[:, :64].index_add_(0, j, dH.double().t())
+    ref[:, 64:] = dH.double().t().reshape(B * N, k, 64).sum(1)
+    got = ops.edge_scatter(dH.cuda(), idx.int().cuda(), B, N, k)
+    assert rel_err(got, ref) <= 2e-6
+
+
 @pytest.mark.parametrize("B,C,N,k", [(2, 9, 128, 20), (1, 64, 256, 20), (3, 64, 100, 7)])
 def test_edgeconv_train_function_vs_autograd(B, C, N, k, train_gemm):
     TOL = TOLS[train_gemm]
