@@ -282,9 +282,16 @@ extern "C" int gfs_gemm_tf32(const float* A, int64_t lda, int a_trans, int64_t a
     while (tmem_cols < NB) tmem_cols *= 2;
     const dim3 grid((Ncols + 127) / 128, (R + NB - 1) / NB, batch * splitk);
     GFS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, GFS_ERR_UNSUPPORTED, "gfs_gemm_tf32: grid too large");
-    // two shared-memory stages when at least two CTAs still fit on an SM, otherwise one (the other resident CTAs overlap)
+    // Resident CTAs per SM are what keeps enough loads in flight for these HBM-bound shapes (measured: 4 CTAs x 1 stage beat
+    // 2 CTAs x 2 stages by 15 % over the training step), so the second shared-memory stage -- MMAs of chunk c overlapping the
+    // loads of chunk c+1 inside one CTA -- is only taken when it costs no residency (limits: 4 CTAs by registers, 512 TMEM columns)
     const size_t stage = (size_t)(split3 ? 2 : 1) * (16384 + (size_t)NB * 128);
-    const int stages = 2 * stage <= 110 * 1024 ? 2 : 1;
+    auto resident = [&](int st) {
+        const int by_smem = (int)((227 * 1024) / (1024 + st * stage + 1024));
+        const int by_tmem = 512 / tmem_cols;
+        return by_smem < by_tmem ? (by_smem < 4 ? by_smem : 4) : (by_tmem < 4 ? by_tmem : 4);
+    };
+    const int stages = resident(2) == resident(1) ? 2 : 1;
     const size_t smem = 1024 + stages * stage;
     float* out = splitk > 1 ? workspace : C;
     if (split3) {

@@ -407,7 +407,9 @@ def gemm_f32(A, lda, a_trans, B, ldb, b_trans, R, Ncols, K, C, ldc, c_trans=Fals
 
 
 def _splitk(K):
-    return int(max(1, min(512, K // 2048)))
+    """CTAs along the contraction of a weight gradient (K = points or edges).  The tensor-core kernel wants >= 2 waves of CTAs
+    on 148 SMs even for the narrow (O, I) outputs, so its chunks are 512 long; the CUDA-core kernel keeps 2048."""
+    return int(max(1, min(512, K // (2048 if TRAIN_GEMM == "f32" else 512))))
 
 
 def conv_fwd(W, x, bias=None):
