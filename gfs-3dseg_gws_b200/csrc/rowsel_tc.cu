@@ -389,15 +389,32 @@ rowsel_tc_kernel(const float* __restrict__ x, int64_t bstride, int64_t cstride, 
 }
 
 // One warp per listed row: the pinned fp32 chains (c ascending) of every dictionary entry, exactly as rowsel.cu evaluates
-// them; the winner (ties -> lowest index) overwrites the tensor-core result.
+// them; the winner (ties -> lowest index) overwrites the tensor-core result.  A row is a chain of D/8 dictionary batches
+// (48 L2 loads each); the batches are double buffered in registers so that the loads of batch b+1 fly while the 8 x 7 fmas
+// of batch b issue, and the row itself is staged in shared memory once (broadcast LDS instead of a shuffle per channel).
+// (Measured alternatives, r2: four rows per warp to reuse the dictionary values divides the L2 traffic by four but leaves
+// only ~250 warps on the GPU for ~1000 ambiguous rows: slower.  The re-check is latency bound, not traffic bound.)
+constexpr int RC_WARPS = 8;
 template <int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * RC_WARPS)
 rowsel_recheck_kernel(const float* __restrict__ x, int64_t bstride, int64_t cstride, int D, int N, const float* __restrict__ dict_t,
                       int G, int Gp, const float* __restrict__ cnorm, const int32_t* __restrict__ recheck,
                       const int32_t* __restrict__ recheck_cnt, int32_t* __restrict__ sel) {
-    const int lane = threadIdx.x & 31;
+    __shared__ float xs_all[RC_WARPS][256];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    float* xs = xs_all[wib];
     const int nrows = *recheck_cnt;
-    for (int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < nrows; w += gridDim.x * (blockDim.x >> 5)) {
+    const int nb = (D + 7) >> 3;
+    auto load = [&](float (&g)[8][6], int bk) {
+#pragma unroll
+        for (int c2 = 0; c2 < 8; ++c2) {
+            const int c = bk * 8 + c2;
+            const float* gp = dict_t + (int64_t)c * Gp;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) g[c2][j] = (j * 32 + lane < G && c < D) ? __ldg(gp + j * 32 + lane) : 0.0f;
+        }
+    };
+    for (int w = blockIdx.x * RC_WARPS + wib; w < nrows; w += gridDim.x * RC_WARPS) {
         const int64_t m = recheck[w];
         const float* xp;
         if (MODE == RT_GW) {
@@ -408,32 +425,32 @@ rowsel_recheck_kernel(const float* __restrict__ x, int64_t bstride, int64_t cstr
         } else {
             xp = x + m;
         }
+        float ga[8][6], gb[8][6];
+        load(ga, 0);
+        __syncwarp();
+        for (int c = lane; c < D; c += 32) xs[c] = __ldg(xp + (int64_t)c * cstride);
+        __syncwarp();
         float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         float nrm = 0.0f;
-        // the row's channels are fetched 32 at a time (one per lane, all in flight together) and broadcast by shuffles, so the
-        // pinned chains below contain no dependent global load; the dictionary loads of a block are independent of the chain
-        for (int c0 = 0; c0 < D; c0 += 32) {
-            const float xv = c0 + lane < D ? __ldg(xp + (int64_t)(c0 + lane) * cstride) : 0.0f;
-#pragma unroll 1
-            for (int c1 = 0; c1 < 32 && c0 + c1 < D; c1 += 8) {
-                float gv[8][6];                      // 48 dictionary values in flight before the first fma needs one
+        auto compute = [&](const float (&g)[8][6], int bk) {
 #pragma unroll
-                for (int c2 = 0; c2 < 8; ++c2) {
-                    const float* g = dict_t + (int64_t)(c0 + c1 + c2) * Gp;
+            for (int c2 = 0; c2 < 8; ++c2) {
+                const int c = bk * 8 + c2;
+                if (c < D) {                         // uniform
+                    const float a = xs[c];
+                    nrm = fmaf(a, a, nrm);
 #pragma unroll
-                    for (int j = 0; j < 6; ++j) gv[c2][j] = (j * 32 + lane < G && c0 + c1 + c2 < D) ? __ldg(g + j * 32 + lane) : 0.0f;
-                }
-#pragma unroll
-                for (int c2 = 0; c2 < 8; ++c2) {
-                    if (c0 + c1 + c2 < D) {          // uniform
-                        const float a = __shfl_sync(0xffffffffu, xv, c1 + c2);
-                        nrm = fmaf(a, a, nrm);
-#pragma unroll
-                        for (int j = 0; j < 6; ++j)
-                            if (j * 32 + lane < G) acc[j] = fmaf(a, gv[c2][j], acc[j]);
-                    }
+                    for (int j = 0; j < 6; ++j)
+                        if (j * 32 + lane < G) acc[j] = fmaf(a, g[c2][j], acc[j]);
                 }
             }
+        };
+#pragma unroll 1
+        for (int bk = 0; bk < nb; bk += 2) {
+            if (bk + 1 < nb) load(gb, bk + 1);
+            compute(ga, bk);
+            if (bk + 2 < nb) load(ga, bk + 2);
+            if (bk + 1 < nb) compute(gb, bk + 1);
         }
         float best = MODE == RT_GW ? -INFINITY : INFINITY;
         int bi = 0x7fffffff;

@@ -303,7 +303,7 @@ def softmax_pool(logits: torch.Tensor, feat: torch.Tensor) -> torch.Tensor:
     assert logits.is_contiguous() and feat.stride(2) == 1 and feat.stride(1) == N
     dev = feat.device
     stats = torch.empty(B * CLS * 2, dtype=torch.float32, device=dev)
-    partial = torch.empty(B * ((N + 127) // 128) * CLS * D, dtype=torch.float32, device=dev)
+    partial = torch.empty(B * ((N + 63) // 64) * CLS * D, dtype=torch.float32, device=dev)
     out = torch.empty(B, CLS, D, dtype=torch.float32, device=dev)
     _call("gfs_softmax_pool", 3, _ptr(logits), _ptr(feat), feat.stride(0), B, CLS, D, N, _ptr(stats), _ptr(partial),
                                  _ptr(out), _stream())

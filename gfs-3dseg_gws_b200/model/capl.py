@@ -49,6 +49,7 @@ class mpti_net_Point_GeoAsWeight_v2(nn.Module):
         self.energy = energy
         print('model using energy: {}'.format(self.energy))
         self._folded = _Folded()
+        self._warned_eval_grad = False
 
     # ------------------------------------------------------------------ weight folding for the head
     def _prepare(self, device):
@@ -78,6 +79,17 @@ class mpti_net_Point_GeoAsWeight_v2(nn.Module):
             self._folded.key, self._folded.data = key, data
         return self._folded.data
 
+    def invalidate_folded(self):
+        """drop every folded / packed inference weight of the model.  The caches are keyed on (id, tensor._version) of the
+        parameters and buffers, which optimiser steps, load_state_dict and in-place ops bump; edits through ``.data`` (EMA,
+        weight surgery) do not -- call this after such an edit."""
+        for mod in self.modules():
+            f = getattr(mod, "_folded", None)
+            if isinstance(f, _Folded):
+                f.key = f.data = None
+            if hasattr(mod, "_key") and hasattr(mod, "_wp"):
+                mod._key = mod._wp = None
+
     # ------------------------------------------------------------------ fused feature extraction
     def _features(self, x, need_semantic=False):
         """-> (point_feat (B,128,N) fp32 cm, assignment (B,N) int32, semantic (B,192,N) fp32 or None)"""
@@ -85,6 +97,14 @@ class mpti_net_Point_GeoAsWeight_v2(nn.Module):
             return self._features_train(x, need_semantic)
         if not x.is_cuda:
             raise RuntimeError("the GW model needs CUDA tensors: the hot path has no CPU fallback")
+        if torch.is_grad_enabled() and not self._warned_eval_grad and any(p.requires_grad for p in self.encoder.parameters()):
+            # the fused inference kernels build no autograd graph: with model.eval() and gradients enabled the reference would
+            # back-propagate into the backbone (running-stat BatchNorm), this path would silently leave those gradients at zero
+            import warnings
+            warnings.warn("GFS drop-in: eval-mode features are computed by the fused inference kernels and carry no autograd graph; "
+                          "only the prototypes receive gradients. Call under torch.no_grad(), or model.train() to fine-tune the "
+                          "backbone.", RuntimeWarning, stacklevel=3)
+            self._warned_eval_grad = True
         hd = self._prepare(x.device)
         x = _cm(x)
         B, _, N = x.shape

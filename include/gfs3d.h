@@ -167,7 +167,7 @@ int gfs_cos_logits(const float* feat, int64_t feat_bstride, int B, int D, int N,
 /* ---- prototype refinement: model/capl.py:245-287 (post_refine_proto_v2), softmax over POINTS then pred @ feat^T ---
  *   logits (B, CLS, N) fp32 (= get_pred output);  feat cm (B, D, N);  out pred_proto (B, CLS, D) fp32 (un-normalised
  *   sum_n softmax_n(logits)[b,c,n] * feat[b,:,n]); the tiny gating arithmetic stays in the host wrapper.
- *   workspaces: stats (B*CLS*2) floats, partial (B * ceil(N/128) * CLS * D) floats; the reduction order is fixed.     */
+ *   workspaces: stats (B*CLS*2) floats, partial (B * ceil(N/64) * CLS * D) floats; the reduction order is fixed.      */
 int gfs_softmax_pool(const float* logits, const float* feat, int64_t feat_bstride, int B, int CLS, int D, int N,
                      float* stats, float* partial, float* pred_proto, void* stream);
 

@@ -84,6 +84,23 @@ def test_state_dict_contract_matches_reference_keys(golden_sd):
     assert sum(p.numel() for p in m.parameters()) == 398144
 
 
+def test_invalidate_folded_drops_every_weight_cache():
+    """the folded-weight caches are keyed on tensor._version, which `.data` edits do not bump -> explicit hook"""
+    from types import SimpleNamespace
+    from model.capl import mpti_net_Point_GeoAsWeight_v2
+    args = SimpleNamespace(edgeconv_widths=[[64, 64]] * 3, dgcnn_mlp_widths=[512, 256], pc_in_dim=9, dgcnn_k=20,
+                           base_widths=[128, 64], output_dim=64, eval_weight=1.0)
+    m = mpti_net_Point_GeoAsWeight_v2(classes=13, args=args, base_num=7, gp=torch.randn(150, 192), energy=0.9)
+    caches = [mod._folded for mod in m.modules() if hasattr(mod, "_folded")]
+    assert len(caches) >= 3                        # head, encoder, base learner
+    for c in caches:
+        c.key, c.data = ("stale",), object()
+    m.att_learner._key, m.att_learner._wp = ("stale",), object()
+    m.invalidate_folded()
+    assert all(c.key is None and c.data is None for c in caches)
+    assert m.att_learner._key is None and m.att_learner._wp is None
+
+
 def test_act_layout_roundtrip_on_cpu():
     """the documented tile formula byte(r,c) = r*128 + (((c/8) ^ (r&7)) << 4) + (c%8)*2 vs ops.act_to_dense"""
     from gfs3d import ops

@@ -168,3 +168,43 @@ def test_config5_large_blocks_end_to_end_vs_oracle(golden_sd, N, B, k):
     assert int((wrong & decidable).sum()) == 0, "a label flip on a point whose class logits are NOT a near-tie"
     assert agree >= 0.99
     assert a_agree >= 0.995 and worst_gap <= 0.1, "a GW flip that is not a near-tie of the oracle's two best words"
+
+
+def test_knn_filter_error_bound_on_all_three_layers_of_the_bench_model(golden_sd):
+    """the tensor-core filter's error bound is measured, not proven -> keep it measured where it matters: the three
+    kNN inputs of the benchmark model (raw blocks, EdgeConv-1 features, EdgeConv-2 features) at B = 32 x 2048.  For every pair
+    the filter value must stay inside HALF of the pair bound  a_i + a_j  that the exactness argument of csrc/knn_tc.cu uses,
+    no tile may need the repair pass on layers 1-2, and the indices must equal the all-fp32 kernel's bit for bit."""
+    from gfs3d import ops
+    from gfs3d.synthetic import synthetic_blocks
+    B, N, k = 32, 2048, 20
+    x = synthetic_blocks(B, N, seed=777).cuda()
+    gp = torch.randn(150, 192, generator=torch.Generator().manual_seed(7))
+    m = _model(golden_sd, gp)
+    assert m.encoder.return_edgeconvs
+    with torch.no_grad():
+        ecs, _ = m.encoder(x)
+    assert len(ecs) == 3
+    layers = [x, ecs[0].contiguous(), ecs[1].contiguous()]
+    for li, f in enumerate(layers):
+        C = f.shape[1]
+        idx, filt, flags = ops.knn_tc_diag(f, k)
+        exact = ops.knn(f, k, impl="exact")
+        worst = 0.0
+        for b in range(0, B, 8):                                   # fp64 check of four blocks per layer
+            fd = f[b].double()
+            xx = (fd * fd).sum(0)
+            d_true = 2.0 * (fd.t() @ fd) - xx[:, None] - xx[None, :]
+            f32 = f[b]
+            mu = 0.25 * ((f32[:, 0] + f32[:, N // 4]) + (f32[:, N // 2] + f32[:, 3 * (N // 4)]))
+            xc = fd - mu.double()[:, None]
+            cc = (xc * xc).sum(0)
+            a = 2.0 ** -15 * cc + (2 * C + 6) * 2.0 ** -25 * xx
+            resid = 2.0 * (filt[b, :, :N].double() - a[None, :]) - d_true
+            err = (resid - resid.median(dim=1, keepdim=True).values).abs()
+            worst = max(worst, float((err / (2.0 * (a[:, None] + a[None, :]))).max()))
+        print(f"layer {li} (C={C}): max filter error / pair bound = {worst:.4f}; tiles sent to the repair pass: {int(flags.sum())} of {flags.numel()}")
+        assert worst < 0.5
+        if li < 2:
+            assert int(flags.sum()) == 0
+        assert torch.equal(idx, exact)
