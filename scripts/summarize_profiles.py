@@ -81,6 +81,29 @@ for fn in sorted(os.listdir(G)):
                 vals.append(f"{label} {r[i]} {units[i]}".strip())
         out.append(f"* `{name}`: " + "; ".join(vals))
 
+# ---- dram traffic of the dominant entry point (the kNN graph: prep + filter + finish, three launches each per step)
+traffic = {}
+for kname in ("knn_prep_kernel", "knn_tc_kernel", "knn_finish_kernel"):
+    fn = os.path.join(G, f"{R}_raw_{kname}.csv")
+    if not os.path.exists(fn):
+        continue
+    rows = list(csv.reader(open(fn)))
+    hdr, units = rows[0], rows[1]
+
+    def to_bytes(v, u):
+        v = float(v.replace(",", ""))
+        return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+    ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    traffic[kname] = [[to_bytes(r[ir], units[ir]), to_bytes(r[iw], units[iw])] for r in rows[2:5]]
+if len(traffic) == 3 and all(len(v) == 3 for v in traffic.values()):
+    total = sum(a + b for v in traffic.values() for a, b in v)
+    json.dump({"source": f"profiles/{R}_summary.md (ncu --set full): dram__bytes_read.sum + dram__bytes_write.sum of the three launches "
+                         "(layers 1-3) of knn_prep_kernel, knn_tc_kernel and knn_finish_kernel of one step at batch 32",
+               "per_launch_bytes_read_write": traffic, "knn_bytes_per_step_b32": total},
+              open(os.path.join(P, "ncu_traffic.json"), "w"), indent=1)
+    out.append(f"\nkNN graph dram traffic per step (batch 32): {total / 1e6:.1f} MB "
+               f"(algorithmic: 51.6 MB = read the three layer inputs once + write the index lists)")
+
 # ---- SASS evidence
 so = os.path.join(ROOT, "gfs-3dseg_gws_b200", "gfs3d", "libgfs3d.so")
 if os.path.exists(so):
@@ -99,6 +122,10 @@ if os.path.exists(so):
     for k, c in counts.items():
         short = subprocess.run(["c++filt", k], capture_output=True, text=True).stdout.strip().split("(")[0]
         out.append(f"| `{short}` | {c['UTCHMMA']} | {c['LDTM']} | {c['UBLKCP']} | {c['LDGSTS']} | {c['SYNCS']} | {c['FFMA']} | {c['HMMA']} |")
+    for fn in sorted(os.listdir(G)):                      # keep the raw ncu pages next to the summary
+        if fn.startswith(f"{R}_raw_") and fn.endswith(".csv"):
+            with open(os.path.join(P, fn), "w") as f:
+                f.write(open(os.path.join(G, fn)).read())
     open(os.path.join(P, f"{R}_sass_listing.txt"), "w").write(
         "\n".join(l for l in sass.splitlines() if any(m in l for m in ("Function :", "UTCHMMA", "UTCBAR", "LDTM", "UBLKCP", "LDGSTS"))) + "\n")
 
