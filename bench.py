@@ -165,7 +165,7 @@ def run_reference(a):
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "sample": f"{sample} blocks x {max(1, a.steps)} steps"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.perf_counter() - t0}
-    print(json.dumps(line))
+    emit(line)
 
 
 SCANNET = dict(classes=21, base_num=15, G=180)
@@ -368,7 +368,27 @@ def reference_on_b200(dev, state_dict, gp, B, iters=3):
         torch.cuda.empty_cache()
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout carries ONE JSON line: keep a private handle on it and send everything else that writes to file descriptor 1 --
+    NCCL's version / debug lines, the reference constructors' prints -- to stderr"""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -585,7 +605,7 @@ def main():
                                            "stream, into a second device buffer), one forward and one D2H of the labels"},
             "gpu_launches": launches, "roofline": roof, "roofline_detail": extra, "cpu_baseline": cpu, "reference_pytorch_on_this_gpu": ref_gpu,
             "train": train, "kmeans": kmeans, "multi_gpu_check": checks, "wall_s_timed_region": wall}
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
