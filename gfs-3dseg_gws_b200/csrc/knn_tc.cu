@@ -68,7 +68,8 @@ __device__ __forceinline__ float kt_ord_val(uint32_t u) {
 // for the two norm chains, and the operand tiles / the point-major copy are written with (row, 16-byte chunk) work items
 // so that consecutive threads write consecutive bytes.
 constexpr int KP_LD = 129;   // padded row of the staged slab
-__global__ void __launch_bounds__(128)
+constexpr int KP_THREADS = 256;   // 128 points per CTA, two threads per point for the loads / stores (the kernel is latency bound)
+__global__ void __launch_bounds__(KP_THREADS)
 knn_prep_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int Npad, int Cp16, int KB, int CPT,
                 uint8_t* __restrict__ ops, float* __restrict__ xp, float* __restrict__ nh, float* __restrict__ nl,
                 uint32_t* __restrict__ tag, float* __restrict__ sqnorm) {
@@ -84,9 +85,13 @@ knn_prep_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int 
         const float* p = xb + (int64_t)t * N;
         mus[t] = t < C ? 0.25f * ((__ldg(p) + __ldg(p + N / 4)) + (__ldg(p + N / 2) + __ldg(p + 3 * (N / 4)))) : 0.0f;
     }
-    for (int c = 0; c < Cp16; ++c) xs[c * KP_LD + t] = (valid && c < C) ? __ldg(xb + (int64_t)c * N + n) : 0.0f;
+    for (int i = t; i < Cp16 * 128; i += KP_THREADS) {
+        const int c = i >> 7, r = i & 127;
+        xs[c * KP_LD + r] = (n0 + r < N && c < C) ? __ldg(xb + (int64_t)c * N + n0 + r) : 0.0f;
+    }
     __syncthreads();
 
+    if (t < 128) {
     float xx = 0.0f, cc = 0.0f;
     for (int c = 0; c < C; ++c) {
         const float v = xs[c * KP_LD + t];
@@ -105,11 +110,12 @@ knn_prep_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int 
     nl[(int64_t)b * Npad + n] = valid ? __fmaf_rd(-0.5f, cc, -a) : -INFINITY;
     tag[(int64_t)b * Npad + n] = ((uint32_t)n << 16) | (uint32_t)__bfloat16_as_ushort(dl);
     if (valid) sqnorm[(int64_t)b * N + n] = xx;
+    }
 
     // operand tiles: columns [h: 0..Cp16) [l: Cp16..2 Cp16), 8 columns per 16-byte chunk
     uint8_t* tiles = ops + ((int64_t)b * (Npad / 128) + rt) * KB * 16384;
     const int cpr = Cp16 >> 3;               // chunks per row and per part
-    for (int i = t; i < 128 * cpr; i += 128) {
+    for (int i = t; i < 128 * cpr; i += KP_THREADS) {
         const int r = i / cpr, q = i - r * cpr;
         const bool on = n0 + r < N;
         uint32_t hp[4], lp[4];
@@ -132,7 +138,7 @@ knn_prep_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int 
     // point-major fp32 copy of the ORIGINAL coordinates, rows of CPT floats (zero padded)
     float* xrows = xp + ((int64_t)b * Npad + n0) * CPT;
     const int fpr = CPT >> 2;
-    for (int i = t; i < 128 * fpr; i += 128) {
+    for (int i = t; i < 128 * fpr; i += KP_THREADS) {
         const int r = i / fpr, q = i - r * fpr;
         float4 o;
         o.x = 4 * q < Cp16 ? xs[(4 * q) * KP_LD + r] : 0.0f;
@@ -699,7 +705,7 @@ static int kt_run(const char* who, const float* x, int64_t x_bstride, int B, int
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     uint8_t* ws = static_cast<uint8_t*>(workspace);
     GFS_CUDA_OK(cudaMemsetAsync(ws + p.off_flags, 0, p.zero_bytes, st));
-    knn_prep_kernel<<<dim3(p.Npad / 128, B), 128, 0, st>>>(x, x_bstride, C, N, p.Npad, p.Cp16, p.KB, p.CPT, ws,
+    knn_prep_kernel<<<dim3(p.Npad / 128, B), KP_THREADS, 0, st>>>(x, x_bstride, C, N, p.Npad, p.Cp16, p.KB, p.CPT, ws,
                                                            reinterpret_cast<float*>(ws + p.off_xp),
                                                            reinterpret_cast<float*>(ws + p.off_nh),
                                                            reinterpret_cast<float*>(ws + p.off_nl),

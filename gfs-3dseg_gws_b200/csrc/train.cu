@@ -61,6 +61,38 @@ __global__ void bn_stats_finish_kernel(const double* __restrict__ part, int C, i
     var[c] = (float)fmax(q / (double)M - m * m, 0.0);
 }
 
+// the same finish plus what the training forward derives from the statistics (one launch instead of four elementwise ones):
+// invstd = rsqrt(var + eps), scale = gamma * invstd, shift = beta - mean * scale   (fp32, the reference's operation order)
+__global__ void bn_stats_coeffs_kernel(const double* __restrict__ part, int C, int S, int64_t M, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, float eps, float* __restrict__ mean, float* __restrict__ var,
+                                       float* __restrict__ invstd, float* __restrict__ scale, float* __restrict__ shift) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0, q = 0.0;
+    for (int i = 0; i < S; ++i) {
+        s += part[((int64_t)c * S + i) * 2 + 0];
+        q += part[((int64_t)c * S + i) * 2 + 1];
+    }
+    const double m = s / (double)M;
+    const float mf = (float)m, vf = (float)fmax(q / (double)M - m * m, 0.0);
+    const float is = rsqrtf(vf + eps), sc = gamma[c] * is;
+    mean[c] = mf;
+    var[c] = vf;
+    invstd[c] = is;
+    scale[c] = sc;
+    shift[c] = beta[c] - mf * sc;
+}
+
+// nn.BatchNorm running statistics (momentum form): r = (1 - mom) r + mom * batch, unbiased variance; ++num_batches_tracked
+__global__ void bn_update_running_kernel(const float* __restrict__ mean, const float* __restrict__ var, int C, float unbias, float mom,
+                                         float* __restrict__ rmean, float* __restrict__ rvar, long long* __restrict__ nbt) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && nbt) *nbt += 1;
+    if (c >= C) return;
+    rmean[c] = rmean[c] * (1.0f - mom) + mom * mean[c];
+    rvar[c] = rvar[c] * (1.0f - mom) + mom * (var[c] * unbias);
+}
+
 // y = act(x * scale[c] + shift[c]),  act(u) = u > 0 ? u : slope * u   (slope 0.2 LeakyReLU, 0 ReLU, 1 identity)
 __global__ void bn_act_fwd_kernel(const float* __restrict__ x, int64_t ldx, float* __restrict__ y, int64_t ldy, int64_t M,
                                   const float* __restrict__ scale, const float* __restrict__ shift, float slope) {
@@ -362,6 +394,30 @@ extern "C" int gfs_bn_stats(const float* x, int64_t ld, int C, int64_t M, double
     GFS_LAUNCH_OK("bn_stats_kernel");
     bn_stats_finish_kernel<<<(C + 127) / 128, 128, 0, st>>>(workspace, C, S, M, mean, var);
     GFS_LAUNCH_OK("bn_stats_finish_kernel");
+    return GFS_OK;
+}
+
+extern "C" int gfs_bn_stats_coeffs(const float* x, int64_t ld, int C, int64_t M, double* workspace, const float* gamma,
+                                   const float* beta, float eps, float* mean, float* var, float* invstd, float* scale, float* shift,
+                                   void* stream) {
+    GFS_REQUIRE(x && workspace && gamma && beta && mean && var && invstd && scale && shift && C > 0 && M > 0, GFS_ERR_BAD_ARG,
+                "gfs_bn_stats_coeffs: bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int S = M >= 65536 ? BN_SPLIT : 1;
+    bn_stats_kernel<<<dim3(C, S), 512, 0, st>>>(x, ld, M, workspace);
+    GFS_LAUNCH_OK("bn_stats_kernel");
+    bn_stats_coeffs_kernel<<<(C + 127) / 128, 128, 0, st>>>(workspace, C, S, M, gamma, beta, eps, mean, var, invstd, scale, shift);
+    GFS_LAUNCH_OK("bn_stats_coeffs_kernel");
+    return GFS_OK;
+}
+
+extern "C" int gfs_bn_update_running(const float* mean, const float* var, int C, int64_t n, float momentum, float* running_mean,
+                                     float* running_var, int64_t* num_batches_tracked, void* stream) {
+    GFS_REQUIRE(mean && var && running_mean && running_var && C > 0 && n > 0, GFS_ERR_BAD_ARG, "gfs_bn_update_running: bad argument");
+    const float unbias = (float)((double)n / (double)(n > 1 ? n - 1 : 1));
+    bn_update_running_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        mean, var, C, unbias, momentum, running_mean, running_var, reinterpret_cast<long long*>(num_batches_tracked));
+    GFS_LAUNCH_OK("bn_update_running_kernel");
     return GFS_OK;
 }
 

@@ -445,6 +445,24 @@ def bn_stats(x):
     return mean, var
 
 
+def bn_stats_coeffs(x, gamma, beta, eps):
+    """batch statistics of x (C, M) and the affine coefficients the training forward applies: one C call, two launches"""
+    C, M = x.shape
+    out = torch.empty(5, C, dtype=torch.float32, device=x.device)      # mean | var | invstd | scale | shift
+    ws = torch.empty(2 * 16 * C, dtype=torch.float64, device=x.device)
+    _call("gfs_bn_stats_coeffs", 2, _ptr(x), x.stride(0), C, M, _ptr(ws), _ptr(gamma), _ptr(beta), float(eps), _ptr(out[0]), _ptr(out[1]),
+          _ptr(out[2]), _ptr(out[3]), _ptr(out[4]), _stream())
+    return out[0], out[1], out[2], out[3], out[4]
+
+
+def bn_update_running(mean, var, n, momentum, running_mean, running_var, num_batches_tracked):
+    _need_cuda(mean, var, running_mean, running_var, num_batches_tracked)
+    assert running_mean.dtype == torch.float32 and running_var.dtype == torch.float32 and running_mean.is_contiguous()
+    assert num_batches_tracked is None or num_batches_tracked.dtype == torch.int64
+    _call("gfs_bn_update_running", 1, _ptr(mean), _ptr(var), mean.numel(), int(n), float(momentum), _ptr(running_mean), _ptr(running_var),
+          _ptr(num_batches_tracked), _stream())
+
+
 def bn_act_fwd(x, scale, shift, slope, out=None):
     C, M = x.shape
     y = torch.empty(C, M, dtype=torch.float32, device=x.device) if out is None else out

@@ -30,9 +30,8 @@ def from_cm(x, B, N):
 
 def _bn_coeffs(z, gamma, beta, running_mean, running_var, training):
     if training:
-        mean, var = ops.bn_stats(z)
-    else:
-        mean, var = running_mean.float(), running_var.float()
+        return ops.bn_stats_coeffs(z, gamma, beta, BN_EPS)           # mean, var, invstd, scale, shift in one call
+    mean, var = running_mean.float(), running_var.float()
     invstd = torch.rsqrt(var + BN_EPS)
     scale = (gamma * invstd).contiguous()
     shift = (beta - mean * scale).contiguous()
@@ -197,6 +196,13 @@ class AttentionTrain(torch.autograd.Function):
 def update_running_stats(bn, mean, var, n):
     """nn.BatchNorm semantics: momentum 0.1 (or cumulative when None), unbiased variance for running_var"""
     with torch.no_grad():
+        if (bn.momentum is not None and bn.running_mean.is_cuda and bn.running_mean.dtype == torch.float32
+                and bn.running_var.dtype == torch.float32 and bn.num_batches_tracked.dtype == torch.int64):
+            # one launch for both buffers.  The counter is incremented by torch: that in-place op bumps its version counter,
+            # which is what invalidates the folded-weight caches of the inference path (keyed on tensor._version)
+            ops.bn_update_running(mean, var, n, bn.momentum, bn.running_mean, bn.running_var, None)
+            bn.num_batches_tracked += 1
+            return
         bn.num_batches_tracked += 1
         mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
         bn.running_mean.mul_(1 - mom).add_(mean.to(bn.running_mean.dtype), alpha=mom)

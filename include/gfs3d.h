@@ -248,6 +248,13 @@ int gfs_gemm_tf32(const float* A, int64_t lda, int a_trans, int64_t a_bstride,
 /* BatchNorm with batch statistics (nn.BatchNorm1d/2d in training mode, model/dgcnn.py:54-55,73-74): biased variance      */
 /* workspace: 2*16*C doubles (per-channel partial sums, combined in a fixed order)                                          */
 int gfs_bn_stats(const float* x, int64_t ld, int C, int64_t M, double* workspace, float* mean, float* var, void* stream);
+/* the same statistics plus invstd = rsqrt(var + eps), scale = gamma*invstd, shift = beta - mean*scale in the same launch       */
+int gfs_bn_stats_coeffs(const float* x, int64_t ld, int C, int64_t M, double* workspace, const float* gamma, const float* beta,
+                        float eps, float* mean, float* var, float* invstd, float* scale, float* shift, void* stream);
+/* nn.BatchNorm running statistics, momentum form (model/dgcnn.py:54-55,73-74 under model.train()): r = (1-mom) r + mom * batch
+ * with the unbiased variance var * n/(n-1); ++num_batches_tracked (int64, may be NULL)                                      */
+int gfs_bn_update_running(const float* mean, const float* var, int C, int64_t n, float momentum, float* running_mean,
+                          float* running_var, int64_t* num_batches_tracked, void* stream);
 /* y = act(x*scale[c] + shift[c]);  act(u) = u > 0 ? u : slope*u  (0.2 LeakyReLU, 0 ReLU, 1 identity)                      */
 int gfs_bn_act_fwd(const float* x, int64_t ldx, float* y, int64_t ldy, int C, int64_t M,
                    const float* scale, const float* shift, float slope, void* stream);
