@@ -133,6 +133,109 @@ extern "C" int gfs_kmeans_accumulate(const float* X, int64_t n, int D, const int
     return GFS_OK;
 }
 
+namespace gfs {
+
+// ---------------------------------------------------------------------------------------------------------------
+// The rest of a Lloyd iteration as two launches (it used to be ~25 elementwise / reduction launches of the host library:
+// at the sharded size of BASELINE.json configs[3], 500 k points per GPU, those fixed costs were half of the iteration).
+//
+//   kmeans_pack_kernel    packed = [sums (K*D, written by the reduce kernel) | counts as fp64 (K) | #labels changed (1)]
+//                         -- the ONE buffer the sharded version all-reduces (get_basis.py:210)
+//   kmeans_update_kernel  sklearn _k_means_common.pyx:_average_centers + the convergence quantities of _kmeans.py:_kmeans_single_lloyd:
+//                         new = count > 0 ? sums / count : 0 (an empty cluster keeps the zero sum; the rare relocation is the
+//                         caller's), shift = sum (new - old)^2 (fp64, fixed order), #empty; also the transposed (D, Kp) copy of
+//                         the new centres that the next E-step reads.  result = [changed, shift, empty] (fp64) = one D2H read.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+kmeans_pack_kernel(const int32_t* __restrict__ labels, const int32_t* __restrict__ labels_old, int64_t n, const int64_t* __restrict__ counts,
+                   int K, int KD, double* __restrict__ packed, unsigned long long* __restrict__ scratch) {
+    // scratch[0]: mismatch counter, scratch[1]: ticket; both are left at zero for the next call
+    unsigned long long mine = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        mine += labels[i] != labels_old[i];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&scratch[0], mine);          // integer sum: order does not matter
+    __threadfence();
+    __syncthreads();
+    __shared__ bool last;
+    if (threadIdx.x == 0) last = atomicAdd(&scratch[1], 1ull) == (unsigned long long)gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    for (int c = threadIdx.x; c < K; c += blockDim.x) packed[KD + c] = (double)counts[c];
+    if (threadIdx.x == 0) {
+        packed[KD + K] = (double)atomicAdd(&scratch[0], 0ull);
+        scratch[0] = 0ull;
+        scratch[1] = 0ull;
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+kmeans_update_kernel(const double* __restrict__ packed, const float* __restrict__ centers_old, int K, int D, int Kp,
+                     float* __restrict__ centers_new, float* __restrict__ ct, double* __restrict__ result) {
+    __shared__ double red[32];
+    const int KD = K * D;
+    double shift = 0.0;
+    for (int i = threadIdx.x; i < KD; i += 1024) {
+        const int c = i / D, d = i - c * D;
+        const double cnt = rint(packed[KD + c]);
+        const float nw = cnt > 0.0 ? (float)(packed[i] / cnt) : 0.0f;
+        const double df = (double)(nw - centers_old[i]);
+        shift += df * df;
+        centers_new[i] = nw;
+        ct[(int64_t)d * Kp + c] = nw;
+    }
+    double empty = 0.0;
+    for (int c = threadIdx.x; c < K; c += 1024) empty += rint(packed[KD + c]) > 0.0 ? 0.0 : 1.0;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        shift += __shfl_xor_sync(0xffffffffu, shift, o);
+        empty += __shfl_xor_sync(0xffffffffu, empty, o);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) red[warp] = shift;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 32; ++w) t += red[w];       // fixed order: deterministic
+        result[1] = t;
+        result[0] = packed[KD + K];
+    }
+    __syncthreads();
+    if (lane == 0) red[warp] = empty;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 32; ++w) t += red[w];
+        result[2] = t;
+    }
+}
+
+}  // namespace gfs
+
+extern "C" int gfs_kmeans_pack(const int32_t* labels, const int32_t* labels_old, int64_t n, const int64_t* counts, int K, int D,
+                               double* packed, void* scratch16, void* stream) {
+    using namespace gfs;
+    GFS_REQUIRE(labels && labels_old && counts && packed && scratch16 && n > 0 && K > 0 && D > 0, GFS_ERR_BAD_ARG, "gfs_kmeans_pack: bad argument");
+    const int64_t want = (n + 256 * 8 - 1) / (256 * 8);
+    const unsigned grid = (unsigned)(want < 1 ? 1 : want > 592 ? 592 : want);
+    kmeans_pack_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(labels, labels_old, n, counts, K, K * D, packed,
+                                                                           static_cast<unsigned long long*>(scratch16));
+    GFS_LAUNCH_OK("kmeans_pack_kernel");
+    return GFS_OK;
+}
+
+extern "C" int gfs_kmeans_update(const double* packed, const float* centers_old, int K, int D, int Kp, float* centers_new, float* centers_t,
+                                 double* result3, void* stream) {
+    using namespace gfs;
+    GFS_REQUIRE(packed && centers_old && centers_new && centers_t && result3 && K > 0 && D > 0 && Kp >= K, GFS_ERR_BAD_ARG,
+                "gfs_kmeans_update: bad argument");
+    kmeans_update_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(packed, centers_old, K, D, Kp, centers_new, centers_t, result3);
+    GFS_LAUNCH_OK("kmeans_update_kernel");
+    return GFS_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // k-means++ seeding step (sklearn _kmeans.py:_kmeans_plusplus, as get_basis.py:210 reaches it through KMeans(init=
 // 'k-means++')): for T <= 8 candidate centres at once,

@@ -32,6 +32,8 @@ SIGNATURES = {
     "gfs_joint_histogram_i32": [_p, _p, _i64, _i, _i, _p, _p],
     "gfs_kmeans_assign": [_p, _i64, _i, _p, _i, _i, _p, _p, _p, _p],
     "gfs_kmeans_accumulate": [_p, _i64, _i, _p, _i, _p, _p, _p, _p, _p],
+    "gfs_kmeans_pack": [_p, _p, _i64, _p, _i, _i, _p, _p, _p],
+    "gfs_kmeans_update": [_p, _p, _i, _i, _i, _p, _p, _p, _p],
     "gfs_kmeans_pp_trial": [_p, _i64, _i64, _i, _p, _p, _i, _p, _p, _p, _p],
     # training path
     "gfs_gemm_f32": [_p, _i64, _i, _i64, _p, _i64, _i, _i64, _p, _i64, _i, _i64, _p, _i, _i, _i, _i, _i, _p, _i, _p],

@@ -172,11 +172,21 @@ class KMeans:
         else:
             raise NotImplementedError(f"init={self.init!r} is not built")
 
-        # Lloyd iterations.  Per iteration: E-step, M-step sums, ONE collective (sums | counts | labels changed) when sharded,
-        # the centre update on the device, and ONE device->host read of (labels changed, centre shift, empty clusters).
+        # Lloyd iterations.  Per iteration: E-step (4 launches), M-step sums (2), pack (1), ONE collective of the packed
+        # [sums | counts | labels changed] buffer when sharded, centre update (1) and ONE device->host read of
+        # (labels changed, centre shift, empty clusters).  All buffers are allocated once.
         Kp = (K + 3) // 4 * 4
         ct = torch.zeros(D, Kp, dtype=torch.float32, device=dev)
+        ct[:, :K] = centers.t()
+        centers = centers.contiguous()
+        centers_new = torch.empty_like(centers)
         labels_old = torch.full((npad,), -1, dtype=torch.int32, device=dev)
+        packed = torch.empty(K * D + K + 1, dtype=torch.float64, device=dev)
+        sums = packed[:K * D].view(K, D)
+        counts = torch.empty(K, dtype=torch.int64, device=dev)
+        acc_ws = ops.kmeans_accumulate_workspace(K, D, dev)
+        scratch = torch.zeros(2, dtype=torch.int64, device=dev)
+        result = torch.empty(3, dtype=torch.float64, device=dev)
         # E-step over the channel-major copy: tensor-core product when the shape allows, same labels as the fp32 kernel.  (The
         # row-major entry, ops.kmeans_assign_rows, measured slower: 32 rows per load instruction instead of one 128-byte line.)
         assign = lambda: ops.kmeans_assign(xt, ct, K)
@@ -185,23 +195,23 @@ class KMeans:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         for n_iter in range(1, self.max_iter + 1):
-            ct[:, :K] = centers.t()
-            labels = assign()
-            sums, counts = ops.kmeans_accumulate(Xc, labels, K, n_valid=n)
-            changed = (labels[:n] != labels_old[:n]).sum()
+            labels = assign()                                          # ct holds the current centres, transposed
+            ops.kmeans_accumulate(Xc, labels, K, n_valid=n, sums=sums, counts=counts, ws=acc_ws)
+            ops.kmeans_pack(labels, labels_old, n, counts, K, D, packed, scratch)
             if self.shard:
-                packed = torch.cat([sums.reshape(-1), counts.double(), changed.double().view(1)])
                 _dist().all_reduce(packed, group=self.process_group)
-                sums, counts, changed = packed[:K * D].view(K, D), packed[K * D:K * D + K].round().long(), packed[-1]
-            new = torch.where(counts[:, None] > 0, sums / counts.clamp_min(1)[:, None].double(), torch.zeros_like(sums)).float()
-            shift = ((new - centers).double() ** 2).sum()
-            n_changed, shift_h, n_empty = torch.stack([changed.double(), shift, (counts == 0).sum().double()]).tolist()
+            ops.kmeans_update(packed, centers, K, D, Kp, centers_new, ct, result)
+            n_changed, shift_h, n_empty = result.tolist()
             if n_empty > 0:           # rare: sklearn moves the empty clusters onto the points farthest from their centres
-                sums, counts = self._relocate_empty(Xc, n, labels, centers, sums.clone(), counts.clone())
+                gsums = packed[:K * D].view(K, D).clone()
+                gcounts = packed[K * D:K * D + K].round().long()
+                gsums, gcounts = self._relocate_empty(Xc, n, labels, centers, gsums, gcounts)
                 # clusters that are still empty keep the zero sum (sklearn _k_means_common.pyx:_average_centers)
-                new = torch.where(counts[:, None] > 0, sums / counts.clamp_min(1)[:, None].double(), torch.zeros_like(sums)).float()
+                new = torch.where(gcounts[:, None] > 0, gsums / gcounts.clamp_min(1)[:, None].double(), torch.zeros_like(gsums)).float()
                 shift_h = float(((new - centers).double() ** 2).sum())
-            centers = new
+                centers_new.copy_(new)
+                ct[:, :K] = new.t()
+            centers, centers_new = centers_new, centers
             if self.verbose:
                 print(f"Iteration {n_iter - 1}, center shift {shift_h:.6g}")
             if n_changed == 0:
@@ -212,8 +222,7 @@ class KMeans:
             labels_old = labels
         ev1.record()
         if not strict:
-            ct[:, :K] = centers.t()
-            labels = assign()
+            labels = assign()                                          # ct already holds the final centres
         self.labels_ = labels[:n].cpu().numpy().astype(np.int32)
         self.lloyd_ms_ = ev0.elapsed_time(ev1)          # device time of the Lloyd loop (the .cpu() above synchronised)
         self.labels_device_ = labels[:n]

@@ -362,21 +362,44 @@ def kmeans_rows_eligible(D: int, Kp: int) -> bool:
     return ROWSEL_IMPL != "fp32" and D % 64 == 0 and D <= 192 and Kp <= 192
 
 
-def kmeans_accumulate(X: torch.Tensor, labels: torch.Tensor, K: int, n_valid: Optional[int] = None):
-    """X (n, D) fp32 row-major, labels (n) int32 -> sums (K, D) fp64, counts (K) int64 (deterministic)"""
+def kmeans_accumulate(X: torch.Tensor, labels: torch.Tensor, K: int, n_valid: Optional[int] = None, sums=None, counts=None, ws=None):
+    """X (n, D) fp32 row-major, labels (n) int32 -> sums (K, D) fp64, counts (K) int64 (deterministic).
+    sums / counts / ws = (partial, pcount): optional preallocated outputs and workspaces (the Lloyd loop reuses them)"""
     _need_cuda(X, labels)
     n, D = X.shape
     if n_valid is not None:
         n = n_valid
     assert X.is_contiguous() and labels.dtype == torch.int32
-    P = lib().gfs_kmeans_partials()
-    partial = torch.empty(P * K * D, dtype=torch.float32, device=X.device)
-    pcount = torch.empty(P * K, dtype=torch.int32, device=X.device)
-    sums = torch.empty(K, D, dtype=torch.float64, device=X.device)
-    counts = torch.empty(K, dtype=torch.int64, device=X.device)
+    if ws is None:
+        ws = kmeans_accumulate_workspace(K, D, X.device)
+    partial, pcount = ws
+    if sums is None:
+        sums = torch.empty(K, D, dtype=torch.float64, device=X.device)
+    if counts is None:
+        counts = torch.empty(K, dtype=torch.int64, device=X.device)
+    assert sums.dtype == torch.float64 and sums.is_contiguous() and counts.dtype == torch.int64
     _call("gfs_kmeans_accumulate", 2, _ptr(X), n, D, _ptr(labels), K, _ptr(partial), _ptr(pcount), _ptr(sums), _ptr(counts),
                                       _stream())
     return sums, counts
+
+
+def kmeans_accumulate_workspace(K: int, D: int, device):
+    P = lib().gfs_kmeans_partials()
+    return (torch.empty(P * K * D, dtype=torch.float32, device=device), torch.empty(P * K, dtype=torch.int32, device=device))
+
+
+def kmeans_pack(labels, labels_old, n, counts, K, D, packed, scratch):
+    """packed[K*D:K*D+K] = counts, packed[-1] = #(labels != labels_old) over the first n; packed[:K*D] are the sums already"""
+    _need_cuda(labels, labels_old, counts, packed, scratch)
+    assert packed.dtype == torch.float64 and packed.numel() == K * D + K + 1 and scratch.numel() * scratch.element_size() >= 16
+    _call("gfs_kmeans_pack", 1, _ptr(labels), _ptr(labels_old), n, _ptr(counts), K, D, _ptr(packed), _ptr(scratch), _stream())
+
+
+def kmeans_update(packed, centers_old, K, D, Kp, centers_new, ct, result):
+    """new centres (K, D), their transpose ct (D, Kp) and result = [changed, shift, empty] from the (all-reduced) packed buffer"""
+    _need_cuda(packed, centers_old, centers_new, ct, result)
+    assert centers_old.is_contiguous() and centers_new.is_contiguous() and ct.is_contiguous() and result.dtype == torch.float64
+    _call("gfs_kmeans_update", 1, _ptr(packed), _ptr(centers_old), K, D, Kp, _ptr(centers_new), _ptr(ct), _ptr(result), _stream())
 
 
 # =====================================================================================================================

@@ -210,6 +210,17 @@ int gfs_kmeans_partials(void);
 int gfs_kmeans_accumulate(const float* X, int64_t n, int D, const int32_t* labels, int K,
                           float* partial, int32_t* pcount, double* sums, int64_t* counts, void* stream);
 
+/* The rest of a Lloyd iteration (sklearn _k_means_common.pyx:_average_centers, _kmeans.py:_kmeans_single_lloyd) in two launches:
+ *   gfs_kmeans_pack:   packed (K*D + K + 1 doubles) = [sums (already there: pass packed as gfs_kmeans_accumulate's sums) |
+ *                      counts as fp64 | number of i < n with labels[i] != labels_old[i]] -- the ONE buffer the sharded k-means
+ *                      all-reduces per iteration.  scratch16: 16 bytes, zero on first use (the kernel leaves them zero).
+ *   gfs_kmeans_update: centers_new (K, D) = count > 0 ? sums / count : 0, centers_t (D, Kp) its transpose for the next E-step,
+ *                      result3 = [labels changed, sum (new - old)^2 in fp64 (fixed order), empty clusters]                 */
+int gfs_kmeans_pack(const int32_t* labels, const int32_t* labels_old, int64_t n, const int64_t* counts, int K, int D,
+                    double* packed, void* scratch16, void* stream);
+int gfs_kmeans_update(const double* packed, const float* centers_old, int K, int D, int Kp, float* centers_new, float* centers_t,
+                      double* result3, void* stream);
+
 /* ---- k-means++ seeding step (sklearn _kmeans.py:_kmeans_plusplus behind get_basis.py:210) ---------------
  * For T <= 8 candidate centres:  m[t][i] = min(max(float(|x_i|^2 - 2 x_i.c_t + |c_t|^2), 0), closest[i]),  pots[t] += sum_i m[t][i]
  * The distance is accumulated in fp64 and rounded once to fp32, as sklearn's _euclidean_distances_upcast does for float32 data.

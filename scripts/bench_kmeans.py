@@ -69,7 +69,8 @@ if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0:
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
-    am, cm = prof["gfs_kmeans_assign"], prof["gfs_kmeans_accumulate"]
+    am = prof.get("gfs_kmeans_assign_tc", prof.get("gfs_kmeans_assign"))      # tensor-core E-step when the shape is eligible
+    cm = prof["gfs_kmeans_accumulate"]
     line = {"metric": "kmeans_lloyd_iteration_ms", "value": float(t[0]), "unit": "ms", "n_gpus": world, "points_total": a.n,
             "points_per_gpu": n, "centroids": K, "dim": D, "higher_is_better": False,
             "assign": {"ms": am, "fp32_tflops": 2.0 * n * D * 192 / am / 1e9, "algorithmic_gbs": (n * D * 4 + n * 4) / am / 1e6},

@@ -1,6 +1,8 @@
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -q -x --deselect tests/test_gpu_reference_callers.py 2>&1 | tail -6
-timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print('blocks/s', d['value'], 'ms/step', d['ms_per_step'], 'e2e', d['e2e']['value']); print(d['roofline_detail']['entry_point_ms_per_step']); print('knn ms', d['roofline']['ms_per_step'])"
-timeout 300 python scripts/bench_train.py --steps 10 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print('train ms/step', d['ms_per_step'], 'launches', d['gpu_launches_per_step'])"
+ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 60 --csv --log-file gpurun_out/r2_kmeans_launches.csv python scripts/bench_kmeans.py --n 500000 --iters 4 --cpu-sample 0 > /dev/null 2>&1
+python - <<'P'
+import csv
+rows=[r for r in csv.reader(open('gpurun_out/r2_kmeans_launches.csv')) if len(r)>10]
+h=rows[0]; iN=h.index("Kernel Name"); iV=h.index("Metric Value")
+for r in rows[1:45]: print(f"{float(r[iV])/1000:8.1f} {r[iN][:90]}")
+P
