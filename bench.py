@@ -31,6 +31,12 @@ UNIT = "blocks/s"
 CLASSES, BASE_NUM, G, NPTS, KNN = 13, 7, 150, 2048, 20
 
 
+def workload_name(batch):
+    """config.workload of both arms (the reference arm runs the same workload on the host cores)"""
+    return (f"BASELINE.json configs[1]: full GFS eval forward, batch={batch} S3DIS-shaped blocks/GPU, N={NPTS}, C=9, k={KNN}, "
+            f"{CLASSES} classes, {G} GWs, random-init weights")
+
+
 def model_args():
     return SimpleNamespace(edgeconv_widths=[[64, 64]] * 3, dgcnn_mlp_widths=[512, 256], pc_in_dim=9, dgcnn_k=KNN,
                            base_widths=[128, 64], output_dim=64, eval_weight=1.2)
@@ -154,14 +160,16 @@ def run_reference(a):
         return
     threads = os.cpu_count() or 1
     m, gp = build_model("cpu")
-    sample = 4
+    # each step is the workload's own batch (32 blocks, ~1.6 s on 16 cores) unless that would take more than a few minutes
+    sample = a.batch if (a.steps + a.warmup) * a.batch <= 2400 else 4
     t0 = time.perf_counter()
     v, kind = cpu_port_blocks_per_sec(m.state_dict(), gp, sample, max(1, a.steps), threads)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": 1e3 * sample / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"GFS eval forward, S3DIS-shaped blocks N={NPTS} C=9 k={KNN}, {CLASSES} classes, {G} GWs",
-                       "blocks_per_step": sample, "note": "CPU path, bounded sample of the batch=32 workload"},
+            "config": {"workload": workload_name(a.batch),
+                       "blocks_per_step": sample, "blocks_per_gpu_per_step": sample,
+                       "note": "the reference's CPU path on the host cores" + ("" if sample == a.batch else ", bounded sample of the batch=32 workload")},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "sample": f"{sample} blocks x {max(1, a.steps)} steps"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.perf_counter() - t0}
@@ -581,7 +589,7 @@ def main():
     cpu = None
     if not a.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        sample, iters = 4, 3
+        sample, iters = B, 8                                  # ~13 s of CPU work on 16 cores
         v, kind = cpu_port_blocks_per_sec(m.state_dict(), gp, sample, iters, threads)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "sample": f"{sample} blocks x {iters} iterations of the same workload"}
 
@@ -592,8 +600,7 @@ def main():
     line = {"metric": METRIC, "value": total_blocks / (dev_ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+bf16",
             "data": "synthetic",
-            "config": {"workload": f"BASELINE.json configs[1]: full GFS eval forward, batch={B} S3DIS-shaped blocks/GPU, N={NPTS}, C=9, k={KNN}, "
-                                   f"{CLASSES} classes, {G} GWs, random-init weights", "blocks_per_gpu_per_step": B,
+            "config": {"workload": workload_name(B), "blocks_per_gpu_per_step": B,
                        "l2": "flushed between steps (256 MiB write outside the per-step event pair); 4 rotating input batches",
                        "parallelism": f"block-sharded x{world}, no data-path collective",
                        "launch": "CUDA graph replay of the eager step (gfs3d/graph.py)" if used_graph else "eager",
