@@ -1,8 +1,9 @@
 mkdir -p gpurun_out
-ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 60 --csv --log-file gpurun_out/r2_kmeans_launches.csv python scripts/bench_kmeans.py --n 500000 --iters 4 --cpu-sample 0 > /dev/null 2>&1
-python - <<'P'
-import csv
-rows=[r for r in csv.reader(open('gpurun_out/r2_kmeans_launches.csv')) if len(r)>10]
-h=rows[0]; iN=h.index("Kernel Name"); iV=h.index("Metric Value")
-for r in rows[1:45]: print(f"{float(r[iV])/1000:8.1f} {r[iN][:90]}")
+timeout 600 python -m pytest tests/test_gpu_train.py -q -x 2>&1 | tail -3
+timeout 300 python scripts/bench_train.py --steps 10 2>/dev/null > gpurun_out/r2k_train.json; python - <<'P'
+import json
+d=json.loads(open('gpurun_out/r2k_train.json').read().strip().splitlines()[-1])
+e=d['entry_point_ms']
+print('step',d['ms_per_step'],'gemm',sum(v for k,v in e.items() if 'gemm' in k))
+for k,v in sorted(e.items(), key=lambda kv:-kv[1])[:8]: print(f"{v:7.3f} {d['entry_point_calls'][k]} {k}")
 P

@@ -81,6 +81,54 @@ for fn in sorted(os.listdir(G)):
                 vals.append(f"{label} {r[i]} {units[i]}".strip())
         out.append(f"* `{name}`: " + "; ".join(vals))
 
+# ---- roofline table: achieved bandwidth from the ALGORITHMIC bytes of the bench shape (B = 32, N = 2048, k = 20) and from the
+# measured dram traffic, against the measured HBM peak; tensor-pipe utilisation for the GEMM-shaped kernels
+peaks = {}
+pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+if os.path.exists(pk):
+    peaks = json.load(open(pk))
+HBM = float(peaks.get("hbm_gbs", 6547.2))
+Bn = 32 * 2048
+ALG = {   # kernel -> algorithmic bytes per launch, by the launch's position in the capture
+    "knn_prep_kernel": [Bn * (4 * 9), Bn * (4 * 64), Bn * (4 * 64)],
+    "knn_tc_kernel": [Bn * (4 * 9 + 80), Bn * (4 * 64 + 80), Bn * (4 * 64 + 80)],
+    "knn_finish_kernel": [Bn * 80, Bn * 80, Bn * 80],
+    "edgeconv_kernel": [Bn * (128 + 256 + 80 + 256 + 128)],
+    "edge_pq_kernel": [Bn * (4 * 64 + 128 + 256)],
+    "rowsel_tc_kernel": [Bn * (192 * 4 + 160 * 2 + 4)],
+    "cos_logits_kernel": [Bn * (128 * 4 + 13 * 4)],
+    "softmax_pool_kernel": [Bn * (128 * 4 + 13 * 4)],
+    "attention_kernel": [Bn * (192 * 2 + 64 * 4 + 128)],
+}
+out.append(f"\n## Roofline per kernel (bench shape; HBM peak {HBM:.0f} GB/s measured)\n")
+out.append("| kernel (launch) | duration us | algorithmic MB | algorithmic GB/s | % of HBM peak | measured dram MB | dram GB/s | tensor pipe % | issue active % |\n|---|---:|---:|---:|---:|---:|---:|---:|---:|")
+for fn in sorted(os.listdir(G)):
+    if not (fn.startswith(f"{R}_raw_") and fn.endswith(".csv")):
+        continue
+    rows = list(csv.reader(open(os.path.join(G, fn))))
+    if len(rows) < 3:
+        continue
+    hdr, units = rows[0], rows[1]
+
+    def val(r, key):
+        if key not in hdr:
+            return None
+        i = hdr.index(key)
+        v = float(r[i].replace(",", ""))
+        u = units[i]
+        return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "us": 1.0, "ms": 1e3, "ns": 1e-3}.get(u, 1.0)
+    for li, r in enumerate(rows[2:]):
+        name = r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "")
+        base = name.split("<")[0]
+        dur = val(r, "gpu__time_duration.sum")
+        dram = (val(r, "dram__bytes_read.sum") or 0) + (val(r, "dram__bytes_write.sum") or 0)
+        alg = ALG.get(base)
+        a = alg[li] if alg and li < len(alg) else None
+        tp = val(r, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")
+        ia = val(r, "smsp__issue_active.avg.pct_of_peak_sustained_active")
+        out.append(f"| `{name}` ({li}) | {dur:.1f} | " + (f"{a / 1e6:.1f} | {a / dur / 1e3:.0f} | {100 * a / dur / 1e3 / HBM:.1f} % | " if a else "- | - | - | ")
+                   + f"{dram / 1e6:.1f} | {dram / dur / 1e3:.0f} | {tp:.1f} | {ia:.1f} |")
+
 # ---- dram traffic of the dominant entry point (the kNN graph: prep + filter + finish, three launches each per step)
 traffic = {}
 for kname in ("knn_prep_kernel", "knn_tc_kernel", "knn_finish_kernel"):
