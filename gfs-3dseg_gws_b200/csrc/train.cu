@@ -310,6 +310,62 @@ edge_scatter_kernel(const float* __restrict__ dH, const int32_t* __restrict__ id
     }
 }
 
+// The same scatter with the BatchNorm + activation backward of the layer in front of it applied on the fly: the tile is
+//   dH[c, e] = gamma[c] invstd[c] (g - sum_g[c]/E - xhat sum_gx[c]/E),   g = dy[c, e] * act'(gamma xhat + beta),  xhat = (x - mean) invstd
+// computed from dy (= d h1) and x (= H) while staging, so the (64, E) tensor dH is never written or re-read.
+__global__ void __launch_bounds__(256)
+edge_scatter_bn_kernel(const float* __restrict__ dy, const float* __restrict__ x, const int32_t* __restrict__ idx, int N, int k, int64_t Mp,
+                       int64_t E, const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+                       const float* __restrict__ beta, float slope, const float* __restrict__ sum_g, const float* __restrict__ sum_gx,
+                       float* __restrict__ dpq) {
+    extern __shared__ float T[];                        // [64][EL + 1]
+    __shared__ float cf[5][64];                         // mean, invstd, gamma, beta | gamma*invstd ; a ; b  (packed below)
+    __shared__ float ca[64], cb[64];
+    const int EL = ES_PPB * k, LD = EL + 1;
+    if (threadIdx.x < 64) {
+        const int c = threadIdx.x;
+        cf[0][c] = mean[c];
+        cf[1][c] = invstd[c];
+        cf[2][c] = gamma[c];
+        cf[3][c] = beta[c];
+        cf[4][c] = gamma[c] * invstd[c];
+        ca[c] = sum_g[c] / (float)E;
+        cb[c] = sum_gx[c] / (float)E;
+    }
+    __syncthreads();
+    const int64_t i0 = (int64_t)blockIdx.x * ES_PPB;
+    const int64_t e0 = i0 * k;
+    const int np = (int)((Mp - i0) < ES_PPB ? (Mp - i0) : ES_PPB);
+    const int ne = np * k;
+    for (int t = threadIdx.x; t < 64 * EL; t += 256) {
+        const int c = t / EL, el = t - c * EL;
+        float v = 0.0f;
+        if (el < ne) {
+            const int64_t o = (int64_t)c * E + e0 + el;
+            const float xh = (__ldg(x + o) - cf[0][c]) * cf[1][c];
+            const float u = fmaf(cf[2][c], xh, cf[3][c]);
+            const float g = __ldg(dy + o) * (u > 0.0f ? 1.0f : slope);
+            v = cf[4][c] * (g - ca[c] - xh * cb[c]);      // same expression as bn_bwd_apply_kernel
+        }
+        T[c * LD + el] = v;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < 64 * np; t += 256) {
+        const int p = t >> 6, c = t & 63;
+        const float* r = T + c * LD + p * k;
+        float sum = 0.0f;
+        for (int sl = 0; sl < k; ++sl) sum += r[sl];
+        dpq[(i0 + p) * 128 + 64 + c] = sum;
+    }
+    for (int t = threadIdx.x; t < ne * 16; t += 256) {
+        const int el = t >> 4, q = t & 15;
+        const int64_t i = i0 + el / k;
+        const int64_t j = (i / N) * N + __ldg(idx + e0 + el);
+        const float* r = T + (4 * q) * LD + el;
+        red_add_v4(dpq + j * 128 + 4 * q, r[0], r[LD], r[2 * LD], r[3 * LD]);
+    }
+}
+
 // y[c, i] = max_slot a[c, i*k + slot] (first maximum), arg[c, i] = slot
 __global__ void max_over_k_fwd_kernel(const float* __restrict__ a, int64_t M, int k, float* __restrict__ y, int64_t ldy,
                                       uint8_t* __restrict__ arg) {
@@ -322,6 +378,30 @@ __global__ void max_over_k_fwd_kernel(const float* __restrict__ a, int64_t M, in
     for (int s = 1; s < k; ++s) {
         const float v = r[s];
         if (v > best) {
+            best = v;
+            bi = s;
+        }
+    }
+    y[(int64_t)c * ldy + i] = best;
+    arg[(int64_t)c * M + i] = (uint8_t)bi;
+}
+
+// BN + activation + max over k in one pass over the pre-BN tensor (model/dgcnn.py:55-58,118): the (C, M*k) activated tensor is
+// never written.  The activation is applied BEFORE the max (the folded scale may be negative).
+__global__ void bn_act_max_kernel(const float* __restrict__ z, int64_t M, int k, const float* __restrict__ scale,
+                                  const float* __restrict__ shift, float slope, float* __restrict__ y, int64_t ldy,
+                                  uint8_t* __restrict__ arg) {
+    const int c = blockIdx.y;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    const float sc = scale[c], sh = shift[c];
+    const float* r = z + (int64_t)c * M * k + i * k;
+    float best = -INFINITY;
+    int bi = 0;
+    for (int s = 0; s < k; ++s) {
+        const float u = fmaf(r[s], sc, sh);
+        const float v = u > 0.0f ? u : slope * u;
+        if (v > best) {                              // first maximum, as max_over_k_fwd_kernel
             best = v;
             bi = s;
         }
@@ -470,6 +550,44 @@ extern "C" int gfs_bn_act_bwd_argmax(const float* dy, int64_t lddy, const uint8_
         bn_bwd_apply_argmax_kernel<1><<<dim3(gx, C), 256, 0, st>>>(dy, lddy, arg, k, x, ldx, dx, lddx, Mp, mean, invstd, gamma, beta, slope,
                                                                    sum_g, sum_gx);
     GFS_LAUNCH_OK("bn_bwd_apply_argmax_kernel");
+    return GFS_OK;
+}
+
+extern "C" int gfs_bn_bwd_sums(const float* dy, int64_t lddy, const float* x, int64_t ldx, int C, int64_t M, const float* mean,
+                               const float* invstd, const float* gamma, const float* beta, float slope, double* workspace, float* sum_g,
+                               float* sum_gx, void* stream) {
+    GFS_REQUIRE(dy && x && mean && invstd && gamma && beta && workspace && sum_g && sum_gx && C > 0 && M > 0, GFS_ERR_BAD_ARG,
+                "gfs_bn_bwd_sums: bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int S = M >= 65536 ? BN_SPLIT : 1;
+    bn_bwd_reduce_kernel<<<dim3(C, S), 512, 0, st>>>(dy, lddy, x, ldx, M, mean, invstd, gamma, beta, slope, workspace);
+    GFS_LAUNCH_OK("bn_bwd_reduce_kernel");
+    bn_bwd_finish_kernel<<<(C + 127) / 128, 128, 0, st>>>(workspace, C, S, sum_g, sum_gx);
+    GFS_LAUNCH_OK("bn_bwd_finish_kernel");
+    return GFS_OK;
+}
+
+extern "C" int gfs_edge_scatter_bn(const float* dy, const float* x, const int32_t* idx, int B, int N, int k, const float* mean,
+                                   const float* invstd, const float* gamma, const float* beta, float slope, const float* sum_g,
+                                   const float* sum_gx, float* dpq, void* stream) {
+    GFS_REQUIRE(dy && x && idx && dpq && mean && invstd && gamma && beta && sum_g && sum_gx && B > 0 && N > 0 && k > 0, GFS_ERR_BAD_ARG,
+                "gfs_edge_scatter_bn: bad argument");
+    GFS_REQUIRE(k <= 64, GFS_ERR_UNSUPPORTED, "gfs_edge_scatter_bn: k <= 64");
+    const int64_t Mp = (int64_t)B * N, E = Mp * k;
+    const size_t smem = (size_t)64 * (ES_PPB * k + 1) * sizeof(float);
+    GFS_CUDA_OK(allow_smem(reinterpret_cast<const void*>(edge_scatter_bn_kernel), (size_t)64 * (ES_PPB * 64 + 1) * sizeof(float)));
+    edge_scatter_bn_kernel<<<(unsigned)((Mp + ES_PPB - 1) / ES_PPB), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+        dy, x, idx, N, k, Mp, E, mean, invstd, gamma, beta, slope, sum_g, sum_gx, dpq);
+    GFS_LAUNCH_OK("edge_scatter_bn_kernel");
+    return GFS_OK;
+}
+
+extern "C" int gfs_bn_act_max_fwd(const float* z, int C, int64_t M, int k, const float* scale, const float* shift, float slope, float* y,
+                                  int64_t ldy, uint8_t* arg, void* stream) {
+    GFS_REQUIRE(z && scale && shift && y && arg && C > 0 && M > 0 && k > 0 && k <= 255, GFS_ERR_BAD_ARG, "gfs_bn_act_max_fwd: bad argument");
+    bn_act_max_kernel<<<dim3((unsigned)((M + 255) / 256), C), 256, 0, static_cast<cudaStream_t>(stream)>>>(z, M, k, scale, shift, slope, y,
+                                                                                                          ldy, arg);
+    GFS_LAUNCH_OK("bn_act_max_kernel");
     return GFS_OK;
 }
 

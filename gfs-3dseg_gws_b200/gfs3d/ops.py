@@ -518,6 +518,36 @@ def bn_act_bwd_argmax(dy, arg, k, x, mean, invstd, gamma, beta, slope):
     return dx, sg, sgx
 
 
+def bn_act_max_fwd(z, scale, shift, slope, M, k):
+    """max over the k slots of act(BN(z)) and its arg-max, one pass over z (C, M*k) -> y (C, M), arg (C, M) uint8"""
+    C = z.shape[0]
+    assert z.is_contiguous() and z.shape[1] == M * k
+    y = torch.empty(C, M, dtype=torch.float32, device=z.device)
+    arg = torch.empty(C, M, dtype=torch.uint8, device=z.device)
+    _call("gfs_bn_act_max_fwd", 1, _ptr(z), C, M, k, _ptr(scale), _ptr(shift), float(slope), _ptr(y), M, _ptr(arg), _stream())
+    return y, arg
+
+
+def bn_bwd_sums(dy, x, mean, invstd, gamma, beta, slope):
+    """(sum_g, sum_gx) = (dbeta, dgamma) of y = act(gamma*xhat + beta) without the apply pass"""
+    C, M = x.shape
+    sg = torch.empty(C, dtype=torch.float32, device=x.device)
+    sgx = torch.empty(C, dtype=torch.float32, device=x.device)
+    ws = torch.empty(2 * 16 * C, dtype=torch.float64, device=x.device)
+    _call("gfs_bn_bwd_sums", 2, _ptr(dy), dy.stride(0), _ptr(x), x.stride(0), C, M, _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(beta),
+          float(slope), _ptr(ws), _ptr(sg), _ptr(sgx), _stream())
+    return sg, sgx
+
+
+def edge_scatter_bn(dy, x, idx, B, N, k, mean, invstd, gamma, beta, slope, sg, sgx):
+    """edge_scatter(bn_act_bwd(dy, x, ...).dx) without the (64, E) tensor in between; dy, x (64, E) contiguous"""
+    assert dy.is_contiguous() and x.is_contiguous() and dy.shape == x.shape and dy.shape[0] == 64
+    dpq = torch.zeros(B * N, 128, dtype=torch.float32, device=dy.device)
+    _call("gfs_edge_scatter_bn", 1, _ptr(dy), _ptr(x), _ptr(idx), B, N, k, _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(beta),
+          float(slope), _ptr(sg), _ptr(sgx), _ptr(dpq), _stream())
+    return dpq
+
+
 def edge_gather(pq, idx, B, N, k):
     H = torch.empty(64, B * N * k, dtype=torch.float32, device=pq.device)
     _call("gfs_edge_gather", 1, _ptr(pq), _ptr(idx), B, N, k, _ptr(H), _stream())

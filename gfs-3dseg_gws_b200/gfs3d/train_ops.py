@@ -122,9 +122,7 @@ class EdgeConvTrain(torch.autograd.Function):
         W2f = W2.detach().float().reshape(64, 64).contiguous()
         Z = ops.conv_fwd(W2f, h1)                                                   # (64, E), pre-BN2
         m2, v2, is2, sc2, sh2 = _bn_coeffs(Z, g2f, b2f, None, None, True)
-        a = ops.bn_act_fwd(Z, sc2, sh2, 0.2)
-        y, arg = ops.max_over_k_fwd(a, M, k)
-        del a
+        y, arg = ops.bn_act_max_fwd(Z, sc2, sh2, 0.2, M, k)                         # BN2 + LeakyReLU + max over k: one pass over Z
         ctx.save_for_backward(x, idx, Wpq, W2f, H, h1, Z, m1, is1, g1f, b1f, m2, is2, g2f, b2f, arg)
         ctx.dims = (B, N, k, C, M)
         ctx.mark_non_differentiable(m1, v1, m2, v2)
@@ -139,10 +137,10 @@ class EdgeConvTrain(torch.autograd.Function):
         dW2 = ops.conv_wgrad(dZ, h1)
         dh1 = ops.conv_dgrad(W2f, dZ)
         del dZ
-        dH, sg1, sgx1 = ops.bn_act_bwd(dh1, H, m1, is1, g1, b1, 0.2)
+        # BN1 / LeakyReLU backward is applied inside the scatter while its tile is staged: dH (64, E) is never built
+        sg1, sgx1 = ops.bn_bwd_sums(dh1, H, m1, is1, g1, b1, 0.2)
+        dpq = ops.edge_scatter_bn(dh1, H, idx, B, N, k, m1, is1, g1, b1, 0.2, sg1, sgx1)   # (M, 128): scatter-add over the graph
         del dh1
-        dpq = ops.edge_scatter(dH, idx, B, N, k)                                    # (M, 128): scatter-add over the graph
-        del dH
         dWpq = torch.empty(128, C, dtype=torch.float32, device=x.device)
         ops.gemm_f32(dpq, 128, False, x, M, True, 128, C, M, dWpq, C, splitk=ops._splitk(M), impl=_exact())
         dx = None

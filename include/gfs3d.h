@@ -280,6 +280,21 @@ int gfs_bn_act_bwd_argmax(const float* dy, int64_t lddy, const uint8_t* arg, int
                           int64_t lddx, int C, int64_t Mp, const float* mean, const float* invstd, const float* gamma,
                           const float* beta, float slope, double* workspace, float* sum_g, float* sum_gx, void* stream);
 
+/* Fusions of the per-edge BatchNorm passes of the training EdgeConv (model/dgcnn.py:53-58,118 under model.train()):
+ *   gfs_bn_act_max_fwd   y[c,i] = max_slot act(z[c, i*k+slot]*scale[c] + shift[c]) and its arg-max slot, in ONE pass over z:
+ *                        the (C, M*k) activated tensor of gfs_bn_act_fwd + gfs_max_over_k_fwd is never written
+ *   gfs_bn_bwd_sums      the two per-channel sums of gfs_bn_act_bwd without its apply pass
+ *   gfs_edge_scatter_bn  gfs_edge_scatter of dH = BN/activation backward of (dy = d h1, x = H), computed while the tile is staged:
+ *                        the (64, E) tensor dH is never written or re-read                                                    */
+int gfs_bn_act_max_fwd(const float* z, int C, int64_t M, int k, const float* scale, const float* shift, float slope, float* y,
+                       int64_t ldy, uint8_t* arg, void* stream);
+int gfs_bn_bwd_sums(const float* dy, int64_t lddy, const float* x, int64_t ldx, int C, int64_t M, const float* mean,
+                    const float* invstd, const float* gamma, const float* beta, float slope, double* workspace, float* sum_g,
+                    float* sum_gx, void* stream);
+int gfs_edge_scatter_bn(const float* dy, const float* x, const int32_t* idx, int B, int N, int k, const float* mean,
+                        const float* invstd, const float* gamma, const float* beta, float slope, const float* sum_g,
+                        const float* sum_gx, float* dpq, void* stream);
+
 /* edge tensor of model/dgcnn.py:35-41 after the split first conv: H[c, e] = P[j(e), c] + Q[i(e), c]  (pq point-major (M,128)) */
 int gfs_edge_gather(const float* pq, const int32_t* idx, int B, int N, int k, float* H, void* stream);
 /* its backward: dP[j] += dH[:, e], dQ[i] += dH[:, e]  (dpq (M,128) must be zeroed by the caller; fp32 atomics)            */

@@ -130,6 +130,39 @@ def test_bn_backward_through_max_over_k_without_the_sparse_tensor(Mp, k):
         assert rel_err(a, b) <= 2e-6, name
 
 
+@pytest.mark.parametrize("Mp,k", [(1000, 20), (333, 7), (70000, 20)])
+def test_bn_act_max_is_bn_act_then_max(Mp, k):
+    """gfs_bn_act_max_fwd == gfs_max_over_k_fwd(gfs_bn_act_fwd(z)) bit for bit (values and arg-max slots)"""
+    from gfs3d import ops
+    g = torch.Generator().manual_seed(Mp * k)
+    C = 64
+    z = torch.randn(C, Mp * k, generator=g).cuda()
+    sc, sh = (torch.randn(C, generator=g)).cuda(), (0.3 * torch.randn(C, generator=g)).cuda()     # negative scales included (H4)
+    want_y, want_arg = ops.max_over_k_fwd(ops.bn_act_fwd(z, sc, sh, 0.2), Mp, k)
+    y, arg = ops.bn_act_max_fwd(z, sc, sh, 0.2, Mp, k)
+    assert torch.equal(y, want_y) and torch.equal(arg, want_arg)
+
+
+@pytest.mark.parametrize("B,N,k", [(2, 128, 20), (1, 100, 7), (2, 2048, 20)])
+def test_edge_scatter_with_fused_bn_backward(B, N, k):
+    """gfs_edge_scatter_bn(dh1, H) == gfs_edge_scatter(gfs_bn_act_bwd(dh1, H).dx), sums == gfs_bn_act_bwd's"""
+    from gfs3d import ops
+    g = torch.Generator().manual_seed(B * N + k)
+    E = B * N * k
+    H = torch.randn(64, E, generator=g).cuda()
+    dh1 = torch.randn(64, E, generator=g).cuda()
+    idx = torch.randint(0, N, (B, N, k), generator=g).int().cuda()
+    ga, be = (1 + 0.3 * torch.randn(64, generator=g)).cuda(), (0.2 * torch.randn(64, generator=g)).cuda()
+    mean, var = ops.bn_stats(H)
+    invstd = torch.rsqrt(var + 1e-5)
+    dH, sg, sgx = ops.bn_act_bwd(dh1, H, mean, invstd, ga, be, 0.2)
+    want = ops.edge_scatter(dH, idx, B, N, k)
+    sg2, sgx2 = ops.bn_bwd_sums(dh1, H, mean, invstd, ga, be, 0.2)
+    assert torch.equal(sg, sg2) and torch.equal(sgx, sgx2)
+    got = ops.edge_scatter_bn(dh1, H, idx, B, N, k, mean, invstd, ga, be, 0.2, sg2, sgx2)
+    assert rel_err(got, want) <= 2e-6            # the same values, added in a different atomic order
+
+
 @pytest.mark.parametrize("B,N,k", [(2, 128, 20), (1, 100, 7), (3, 64, 40), (1, 2048, 20)])
 def test_edge_scatter_vs_index_add(B, N, k):
     """backward of the edge gather (model/dgcnn.py:35-41): dP[j] += dH[e], dQ[i] = sum over the point's k edges"""
