@@ -241,7 +241,8 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, int64_t lddy, 
 // pq: (M, 128) point-major [P | Q];  H: (64, E) channel-major.  CTA = 128 consecutive edges, transposed through smem.
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
-edge_gather_kernel(const float* __restrict__ pq, const int32_t* __restrict__ idx, int N, int k, int64_t E, float* __restrict__ H) {
+edge_gather_kernel(const float* __restrict__ pq, const int32_t* __restrict__ idx, int N, int k, int64_t E, float* __restrict__ H,
+                   float2* __restrict__ part) {
     __shared__ float T[64][129];
     const int64_t e0 = (int64_t)blockIdx.x * 128;
     const int q = threadIdx.x & 7, sub = threadIdx.x >> 3;
@@ -267,6 +268,47 @@ edge_gather_kernel(const float* __restrict__ pq, const int32_t* __restrict__ idx
     const int64_t e = e0 + threadIdx.x;
     if (e < E)
         for (int c = 0; c < 64; ++c) H[(int64_t)c * E + e] = T[c][threadIdx.x];
+    if (part) {
+        // BatchNorm statistics of H while the tile is on chip: thread (c, half) sums 64 edges of channel c (rows past E are
+        // zero); partials [c][2 * CTA + half] are combined in index order in fp64 by bn_stats_partials_kernel (deterministic)
+        const int c = threadIdx.x & 63, half = threadIdx.x >> 6;
+        float sm = 0.0f, sq = 0.0f;
+#pragma unroll 8
+        for (int el = half * 64; el < half * 64 + 64; ++el) {
+            const float v = T[c][el];
+            sm += v;
+            sq = fmaf(v, v, sq);
+        }
+        part[(int64_t)c * (2 * gridDim.x) + 2 * blockIdx.x + half] = make_float2(sm, sq);
+    }
+}
+
+// per-channel statistics and affine coefficients from the partial (sum, sum of squares) pairs of edge_gather_kernel
+__global__ void __launch_bounds__(256)
+bn_stats_partials_kernel(const float2* __restrict__ part, int P, int64_t M, const float* __restrict__ gamma, const float* __restrict__ beta,
+                         float eps, float* __restrict__ mean, float* __restrict__ var, float* __restrict__ invstd,
+                         float* __restrict__ scale, float* __restrict__ shift) {
+    __shared__ double red[16];
+    const int c = blockIdx.x;
+    const float2* row = part + (int64_t)c * P;
+    double s = 0.0, q = 0.0;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {       // fixed assignment + fixed-order tree: deterministic
+        const float2 v = row[i];
+        s += (double)v.x;
+        q += (double)v.y;
+    }
+    s = block_sum(s, red);
+    q = block_sum(q, red);
+    if (threadIdx.x == 0) {
+        const double m = s / (double)M;
+        const float mf = (float)m, vf = (float)fmax(q / (double)M - m * m, 0.0);
+        const float is = rsqrtf(vf + eps), sc = gamma[c] * is;
+        mean[c] = mf;
+        var[c] = vf;
+        invstd[c] = is;
+        scale[c] = sc;
+        shift[c] = beta[c] - mf * sc;
+    }
 }
 
 // backward of the gather: dP[j] += dH[:, e] (j = idx[e]), dQ[i] = sum_slot dH[:, i*k + slot]   (the P half of dpq must be zeroed)
@@ -594,8 +636,24 @@ extern "C" int gfs_bn_act_max_fwd(const float* z, int C, int64_t M, int k, const
 extern "C" int gfs_edge_gather(const float* pq, const int32_t* idx, int B, int N, int k, float* H, void* stream) {
     GFS_REQUIRE(pq && idx && H && B > 0 && N > 0 && k > 0, GFS_ERR_BAD_ARG, "gfs_edge_gather: bad argument");
     const int64_t E = (int64_t)B * N * k;
-    edge_gather_kernel<<<(unsigned)((E + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(pq, idx, N, k, E, H);
+    edge_gather_kernel<<<(unsigned)((E + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(pq, idx, N, k, E, H, nullptr);
     GFS_LAUNCH_OK("edge_gather_kernel");
+    return GFS_OK;
+}
+
+extern "C" int gfs_edge_gather_stats(const float* pq, const int32_t* idx, int B, int N, int k, float* H, float* partials,
+                                     const float* gamma, const float* beta, float eps, float* mean, float* var, float* invstd,
+                                     float* scale, float* shift, void* stream) {
+    GFS_REQUIRE(pq && idx && H && partials && gamma && beta && mean && var && invstd && scale && shift && B > 0 && N > 0 && k > 0,
+                GFS_ERR_BAD_ARG, "gfs_edge_gather_stats: bad argument");
+    const int64_t E = (int64_t)B * N * k;
+    const unsigned grid = (unsigned)((E + 127) / 128);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    edge_gather_kernel<<<grid, 128, 0, st>>>(pq, idx, N, k, E, H, reinterpret_cast<float2*>(partials));
+    GFS_LAUNCH_OK("edge_gather_kernel");
+    bn_stats_partials_kernel<<<64, 256, 0, st>>>(reinterpret_cast<const float2*>(partials), (int)(2 * grid), E, gamma, beta, eps, mean, var,
+                                                 invstd, scale, shift);
+    GFS_LAUNCH_OK("bn_stats_partials_kernel");
     return GFS_OK;
 }
 

@@ -48,6 +48,7 @@ SIGNATURES = {
     "gfs_bn_act_bwd": [_p, _i64, _p, _i64, _p, _i64, _i, _i64, _p, _p, _p, _p, _f, _p, _p, _p, _p],
     "gfs_bn_act_bwd_argmax": [_p, _i64, _p, _i, _p, _i64, _p, _i64, _i, _i64, _p, _p, _p, _p, _f, _p, _p, _p, _p],
     "gfs_edge_gather": [_p, _p, _i, _i, _i, _p, _p],
+    "gfs_edge_gather_stats": [_p, _p, _i, _i, _i, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p],
     "gfs_edge_scatter": [_p, _p, _i, _i, _i, _p, _p],
     "gfs_max_over_k_fwd": [_p, _i, _i64, _i, _p, _i64, _p, _p],
     "gfs_max_over_k_bwd": [_p, _i64, _p, _i, _i64, _i, _p, _p],

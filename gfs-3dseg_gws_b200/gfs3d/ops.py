@@ -554,6 +554,17 @@ def edge_gather(pq, idx, B, N, k):
     return H
 
 
+def edge_gather_stats(pq, idx, B, N, k, gamma, beta, eps):
+    """edge_gather + bn_stats_coeffs(H) in one pass: -> H (64, E), (mean, var, invstd, scale, shift)"""
+    E = B * N * k
+    H = torch.empty(64, E, dtype=torch.float32, device=pq.device)
+    part = torch.empty(64 * 2 * ((E + 127) // 128) * 2, dtype=torch.float32, device=pq.device)
+    out = torch.empty(5, 64, dtype=torch.float32, device=pq.device)
+    _call("gfs_edge_gather_stats", 2, _ptr(pq), _ptr(idx), B, N, k, _ptr(H), _ptr(part), _ptr(gamma), _ptr(beta), float(eps),
+          _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3]), _ptr(out[4]), _stream())
+    return H, (out[0], out[1], out[2], out[3], out[4])
+
+
 def edge_scatter(dH, idx, B, N, k):
     dpq = torch.zeros(B * N, 128, dtype=torch.float32, device=dH.device)
     _call("gfs_edge_scatter", 1, _ptr(dH), _ptr(idx), B, N, k, _ptr(dpq), _stream())

@@ -114,10 +114,10 @@ class EdgeConvTrain(torch.autograd.Function):
         # W_a (x_j - x_i) + W_b x_i evaluated as a DIFFERENCE of per-point terms, so an operand rounding of 2^-11 |W_a x| (plain
         # tf32) would be of the order of the neighbour differences themselves
         ops.gemm_f32(Wpq, C, True, x, M, False, 128, M, C, pq, 128, c_trans=True, impl=_exact())   # point-major rows for the gather
-        H = ops.edge_gather(pq, idx, B, N, k)                                       # (64, E), pre-BN1
-        del pq
         g1f, b1f, g2f, b2f = (t.detach().contiguous().float() for t in (g1, b1, g2, b2))
-        m1, v1, is1, sc1, sh1 = _bn_coeffs(H, g1f, b1f, None, None, True)
+        # (64, E) pre-BN1 tensor and its batch statistics / BN coefficients in one pass (the tile is summed while on chip)
+        H, (m1, v1, is1, sc1, sh1) = ops.edge_gather_stats(pq, idx, B, N, k, g1f, b1f, BN_EPS)
+        del pq
         h1 = ops.bn_act_fwd(H, sc1, sh1, 0.2)
         W2f = W2.detach().float().reshape(64, 64).contiguous()
         Z = ops.conv_fwd(W2f, h1)                                                   # (64, E), pre-BN2

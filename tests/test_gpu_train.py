@@ -130,6 +130,22 @@ def test_bn_backward_through_max_over_k_without_the_sparse_tensor(Mp, k):
         assert rel_err(a, b) <= 2e-6, name
 
 
+@pytest.mark.parametrize("B,N,k", [(2, 128, 20), (1, 100, 7), (4, 2048, 20)])
+def test_edge_gather_with_fused_statistics(B, N, k):
+    """gfs_edge_gather_stats == gfs_edge_gather + gfs_bn_stats_coeffs: same H bit for bit, statistics to fp32 rounding"""
+    from gfs3d import ops
+    g = torch.Generator().manual_seed(B * N + k)
+    pq = torch.randn(B * N, 128, generator=g).cuda()
+    idx = torch.randint(0, N, (B, N, k), generator=g).int().cuda()
+    ga, be = (1 + 0.3 * torch.randn(64, generator=g)).cuda(), (0.2 * torch.randn(64, generator=g)).cuda()
+    H0 = ops.edge_gather(pq, idx, B, N, k)
+    want = ops.bn_stats_coeffs(H0, ga, be, 1e-5)
+    H, got = ops.edge_gather_stats(pq, idx, B, N, k, ga, be, 1e-5)
+    assert torch.equal(H, H0)
+    for a, b, name in zip(got, want, ("mean", "var", "invstd", "scale", "shift")):
+        assert rel_err(a, b) <= 2e-6, name
+
+
 @pytest.mark.parametrize("Mp,k", [(1000, 20), (333, 7), (70000, 20)])
 def test_bn_act_max_is_bn_act_then_max(Mp, k):
     """gfs_bn_act_max_fwd == gfs_max_over_k_fwd(gfs_bn_act_fwd(z)) bit for bit (values and arg-max slots)"""
