@@ -467,8 +467,29 @@ __global__ void max_over_k_bwd_kernel(const float* __restrict__ dy, int64_t lddy
 // row softmax (attention, model/attention.py:45):  p = softmax(s * scale) [* mask];  one warp per row
 // backward: ds = scale * p0 * (dp*mask - sum(dp*mask*p0)),  p0 = softmax without the mask
 // ------------------------------------------------------------------------------------------------------------------
+// Dropout without a mask tensor: keep / drop of element (row r, column j) is a counter-based hash of (seed, r, j), so the
+// forward and the backward pass regenerate the same decision and the (rows x n) mask (537 MB at B = 32, N = 2048) is neither
+// drawn, stored nor read.  Returns the factor 1/keep or 0.  (The stream differs from torch's Philox: dropout is stochastic in
+// the reference too; parity tests run with p = 0 or with an explicit mask.)
+__device__ __forceinline__ float drop_factor(uint32_t seed, uint32_t r, uint32_t j, float keep, float inv_keep) {
+    uint32_t h = (r * 0x9E3779B1u) ^ (j * 0x85EBCA77u) ^ seed;
+    h ^= h >> 15;
+    h *= 0x2C1B3C6Du;
+    h ^= h >> 12;
+    h *= 0x297A2D39u;
+    h ^= h >> 15;
+    return (float)(h >> 8) * (1.0f / 16777216.0f) < keep ? inv_keep : 0.0f;
+}
+
+// the mask the hash defines, materialised (tests)
+__global__ void dropout_mask_kernel(int64_t rows, int n, uint32_t seed, float keep, float* __restrict__ mask) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * n) return;
+    mask[i] = drop_factor(seed, (uint32_t)(i / n), (uint32_t)(i % n), keep, 1.0f / keep);
+}
+
 __global__ void softmax_rows_fwd_kernel(const float* __restrict__ s, int64_t rows, int n, float scale, const float* __restrict__ mask,
-                                        float* __restrict__ p0, float* __restrict__ p) {
+                                        uint32_t seed, float keep, float* __restrict__ p0, float* __restrict__ p) {
     const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (r >= rows) return;
@@ -485,23 +506,27 @@ __global__ void softmax_rows_fwd_kernel(const float* __restrict__ s, int64_t row
     for (int j = lane; j < n; j += 32) {
         const float v = expf(sr[j] * scale - mx) * inv;
         p0[r * n + j] = v;
-        if (p != p0) p[r * n + j] = mask ? v * mask[r * n + j] : v;
+        if (p != p0) p[r * n + j] = mask ? v * mask[r * n + j] : (keep < 1.0f ? v * drop_factor(seed, (uint32_t)r, (uint32_t)j, keep, 1.0f / keep) : v);
     }
 }
 
 __global__ void softmax_rows_bwd_kernel(const float* __restrict__ p0, const float* __restrict__ dp, const float* __restrict__ mask,
-                                        int64_t rows, int n, float scale, float* __restrict__ ds) {
+                                        uint32_t seed, float keep, int64_t rows, int n, float scale, float* __restrict__ ds) {
     const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (r >= rows) return;
     const float* pr = p0 + r * n;
     const float* dr = dp + r * n;
     const float* mr = mask ? mask + r * n : nullptr;
+    const bool hashed = !mr && keep < 1.0f;
+    const float ik = 1.0f / keep;
     float dot = 0.0f;
-    for (int j = lane; j < n; j += 32) dot += pr[j] * dr[j] * (mr ? mr[j] : 1.0f);
+    for (int j = lane; j < n; j += 32)
+        dot += pr[j] * dr[j] * (mr ? mr[j] : (hashed ? drop_factor(seed, (uint32_t)r, (uint32_t)j, keep, ik) : 1.0f));
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-    for (int j = lane; j < n; j += 32) ds[r * n + j] = scale * pr[j] * (dr[j] * (mr ? mr[j] : 1.0f) - dot);
+    for (int j = lane; j < n; j += 32)
+        ds[r * n + j] = scale * pr[j] * (dr[j] * (mr ? mr[j] : (hashed ? drop_factor(seed, (uint32_t)r, (uint32_t)j, keep, ik) : 1.0f)) - dot);
 }
 
 }  // namespace gfs
@@ -682,17 +707,28 @@ extern "C" int gfs_max_over_k_bwd(const float* dy, int64_t lddy, const uint8_t* 
     return GFS_OK;
 }
 
-extern "C" int gfs_softmax_rows_fwd(const float* s, int64_t rows, int n, float scale, const float* mask, float* p0, float* p, void* stream) {
-    GFS_REQUIRE(s && p0 && p && rows > 0 && n > 0, GFS_ERR_BAD_ARG, "gfs_softmax_rows_fwd: bad argument");
-    softmax_rows_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(s, rows, n, scale, mask, p0, p);
+extern "C" int gfs_dropout_mask(int64_t rows, int n, uint32_t seed, float keep, float* mask, void* stream) {
+    GFS_REQUIRE(mask && rows > 0 && n > 0 && keep > 0.0f && keep <= 1.0f, GFS_ERR_BAD_ARG, "gfs_dropout_mask: bad argument");
+    dropout_mask_kernel<<<(unsigned)((rows * n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(rows, n, seed, keep, mask);
+    GFS_LAUNCH_OK("dropout_mask_kernel");
+    return GFS_OK;
+}
+
+extern "C" int gfs_softmax_rows_fwd(const float* s, int64_t rows, int n, float scale, const float* mask, uint32_t seed, float keep,
+                                    float* p0, float* p, void* stream) {
+    GFS_REQUIRE(s && p0 && p && rows > 0 && n > 0 && keep > 0.0f, GFS_ERR_BAD_ARG, "gfs_softmax_rows_fwd: bad argument");
+    GFS_REQUIRE(p != p0 || (!mask && keep >= 1.0f), GFS_ERR_BAD_ARG, "gfs_softmax_rows_fwd: dropout needs a separate p");
+    softmax_rows_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(s, rows, n, scale, mask, seed, keep,
+                                                                                                     p0, p);
     GFS_LAUNCH_OK("softmax_rows_fwd_kernel");
     return GFS_OK;
 }
 
-extern "C" int gfs_softmax_rows_bwd(const float* p0, const float* dp, const float* mask, int64_t rows, int n, float scale, float* ds,
-                                    void* stream) {
-    GFS_REQUIRE(p0 && dp && ds && rows > 0 && n > 0, GFS_ERR_BAD_ARG, "gfs_softmax_rows_bwd: bad argument");
-    softmax_rows_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(p0, dp, mask, rows, n, scale, ds);
+extern "C" int gfs_softmax_rows_bwd(const float* p0, const float* dp, const float* mask, uint32_t seed, float keep, int64_t rows, int n,
+                                    float scale, float* ds, void* stream) {
+    GFS_REQUIRE(p0 && dp && ds && rows > 0 && n > 0 && keep > 0.0f, GFS_ERR_BAD_ARG, "gfs_softmax_rows_bwd: bad argument");
+    softmax_rows_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(p0, dp, mask, seed, keep, rows, n,
+                                                                                                     scale, ds);
     GFS_LAUNCH_OK("softmax_rows_bwd_kernel");
     return GFS_OK;
 }

@@ -8,7 +8,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgfs3d.so")
 
-_i, _i64, _p, _f = ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_float
+_i, _i64, _p, _f, _u32 = ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_float, ctypes.c_uint32
 
 # name -> argtypes; every function returns int (gfs_status) except the three utilities
 SIGNATURES = {
@@ -52,8 +52,9 @@ SIGNATURES = {
     "gfs_edge_scatter": [_p, _p, _i, _i, _i, _p, _p],
     "gfs_max_over_k_fwd": [_p, _i, _i64, _i, _p, _i64, _p, _p],
     "gfs_max_over_k_bwd": [_p, _i64, _p, _i, _i64, _i, _p, _p],
-    "gfs_softmax_rows_fwd": [_p, _i64, _i, _f, _p, _p, _p, _p],
-    "gfs_softmax_rows_bwd": [_p, _p, _p, _i64, _i, _f, _p, _p],
+    "gfs_softmax_rows_fwd": [_p, _i64, _i, _f, _p, _u32, _f, _p, _p, _p],
+    "gfs_softmax_rows_bwd": [_p, _p, _p, _u32, _f, _i64, _i, _f, _p, _p],
+    "gfs_dropout_mask": [_i64, _i, _u32, _f, _p, _p],
 }
 UTILITIES = {"gfs_version": (_i, []), "gfs_last_error_string": (ctypes.c_char_p, []),
              "gfs_device_sm_count": (_i, []), "gfs_kmeans_partials": (_i, []),

@@ -586,16 +586,27 @@ def max_over_k_bwd(dy, arg, k):
     return da
 
 
-def softmax_rows_fwd(s, scale, mask=None):
+def softmax_rows_fwd(s, scale, mask=None, seed=0, keep=1.0):
+    """p0 = softmax(s * scale) per row; p = p0 * dropout factor.  mask: explicit (B, n, n) factors; or mask None and keep < 1: the
+    factors come from the counter-based hash of (seed, row, column) that softmax_rows_bwd regenerates (no mask tensor)"""
     rows, n = s.shape[0] * s.shape[1], s.shape[2]
     p0 = torch.empty_like(s)
-    p = torch.empty_like(s) if mask is not None else p0
-    _call("gfs_softmax_rows_fwd", 1, _ptr(s), rows, n, float(scale), _ptr(mask), _ptr(p0), _ptr(p), _stream())
+    p = torch.empty_like(s) if (mask is not None or keep < 1.0) else p0
+    _call("gfs_softmax_rows_fwd", 1, _ptr(s), rows, n, float(scale), _ptr(mask), int(seed) & 0xFFFFFFFF, float(keep), _ptr(p0), _ptr(p),
+          _stream())
     return p0, p
 
 
-def softmax_rows_bwd(p0, dp, scale, mask=None):
+def dropout_mask(rows, n, seed, keep, device):
+    """(tests) the mask the hash of softmax_rows_fwd / _bwd defines: 1/keep or 0"""
+    m = torch.empty(rows, n, dtype=torch.float32, device=device)
+    _call("gfs_dropout_mask", 1, rows, n, int(seed) & 0xFFFFFFFF, float(keep), _ptr(m), _stream())
+    return m
+
+
+def softmax_rows_bwd(p0, dp, scale, mask=None, seed=0, keep=1.0):
     rows, n = p0.shape[0] * p0.shape[1], p0.shape[2]
     ds = torch.empty_like(p0)
-    _call("gfs_softmax_rows_bwd", 1, _ptr(p0), _ptr(dp), _ptr(mask), rows, n, float(scale), _ptr(ds), _stream())
+    _call("gfs_softmax_rows_bwd", 1, _ptr(p0), _ptr(dp), _ptr(mask), int(seed) & 0xFFFFFFFF, float(keep), rows, n, float(scale), _ptr(ds),
+          _stream())
     return ds

@@ -153,27 +153,29 @@ class EdgeConvTrain(torch.autograd.Function):
 
 class AttentionTrain(torch.autograd.Function):
     """model/attention.py:43-46 in training mode: y = dropout(softmax(q^T k * scale)) v^T, per block.
-    qkv (192, M) channel-major [q | k | v]; mask: None or the (B, N, N) dropout mask already scaled by 1/(1-p)."""
+    qkv (192, M) channel-major [q | k | v]; dropout either as an explicit (B, N, N) mask already scaled by 1/(1-p) (tests) or as
+    (seed, keep): the kernels derive keep / drop from a hash of (seed, row, column), forward and backward alike, so no mask tensor
+    is drawn, stored or read."""
 
     @staticmethod
-    def forward(ctx, qkv, B, N, scale, mask):
+    def forward(ctx, qkv, B, N, scale, mask, seed=0, keep=1.0):
         qkv = qkv.contiguous()
         M = qkv.shape[1]
         q, kk, v = qkv[0:64], qkv[64:128], qkv[128:192]
         S = torch.empty(B, N, N, dtype=torch.float32, device=qkv.device)
         ops.gemm_f32(q, M, False, kk, M, False, N, N, 64, S, N, batch=B, a_bs=N, b_bs=N, c_bs=N * N)
-        p0, p = ops.softmax_rows_fwd(S, scale, mask)
+        p0, p = ops.softmax_rows_fwd(S, scale, mask, seed, keep if mask is None else 1.0)
         del S
         y = torch.empty(64, M, dtype=torch.float32, device=qkv.device)
         ops.gemm_f32(v, M, True, p, N, True, 64, N, N, y, M, batch=B, a_bs=N, b_bs=N * N, c_bs=N)
         ctx.save_for_backward(qkv, p0, p, mask if mask is not None else torch.empty(0, device=qkv.device))
-        ctx.dims = (B, N, scale, mask is not None)
+        ctx.dims = (B, N, scale, mask is not None, seed, keep if mask is None else 1.0)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         qkv, p0, p, mask = ctx.saved_tensors
-        B, N, scale, has_mask = ctx.dims
+        B, N, scale, has_mask, seed, keep = ctx.dims
         M = qkv.shape[1]
         dy = dy.contiguous()
         q, kk, v = qkv[0:64], qkv[64:128], qkv[128:192]
@@ -183,12 +185,12 @@ class AttentionTrain(torch.autograd.Function):
         # dP[q, key] = sum_c dY[c, q] v[c, key]
         dP = torch.empty(B, N, N, dtype=torch.float32, device=qkv.device)
         ops.gemm_f32(dy, M, False, v, M, False, N, N, 64, dP, N, batch=B, a_bs=N, b_bs=N, c_bs=N * N)
-        dS = ops.softmax_rows_bwd(p0, dP, scale, mask if has_mask else None)
+        dS = ops.softmax_rows_bwd(p0, dP, scale, mask if has_mask else None, seed, keep)
         del dP
         # dQ[c, q] = sum_key dS[q, key] k[c, key];   dK[c, key] = sum_q dS[q, key] q[c, q]
         ops.gemm_f32(kk, M, True, dS, N, True, 64, N, N, dqkv[0:64], M, batch=B, a_bs=N, b_bs=N * N, c_bs=N)
         ops.gemm_f32(q, M, True, dS, N, False, 64, N, N, dqkv[64:128], M, batch=B, a_bs=N, b_bs=N * N, c_bs=N)
-        return dqkv, None, None, None, None
+        return dqkv, None, None, None, None, None, None
 
 
 def update_running_stats(bn, mean, var, n):

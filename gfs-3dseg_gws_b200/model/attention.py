@@ -40,11 +40,14 @@ class SelfAttention(nn.Module):
         from gfs3d.train_ops import AttentionTrain, ConvOnly
         w = torch.cat([self.q_map.weight, self.k_map.weight, self.v_map.weight], dim=0).reshape(3 * self.out_channel, self.in_channel)
         qkv = ConvOnly.apply(x_cm, w)
-        mask = None
+        keep, seed = 1.0, 0
         if self.dropout.p > 0:
+            # dropout on the attention weights (model/attention.py:45) without a mask tensor: the kernels hash (seed, row, column);
+            # the seed advances per call from torch's seed, so torch.manual_seed makes a run repeatable (no host sync)
             keep = 1.0 - self.dropout.p
-            mask = (torch.rand(B, N, N, device=x_cm.device) < keep).float() / keep
-        return AttentionTrain.apply(qkv, B, N, 1.0 / self.temperature, mask)
+            self._drop_calls = getattr(self, "_drop_calls", 0) + 1
+            seed = (torch.initial_seed() * 0x9E3779B1 + self._drop_calls * 0x85EBCA77) & 0xFFFFFFFF
+        return AttentionTrain.apply(qkv, B, N, 1.0 / self.temperature, None, seed, keep)
 
     def forward_fused(self, x_act, B, N, y_cm=None, y_act=None, y_kb=0):
         """x_act: bf16 act tiles (B*N, in_channel).  Writes y (B, 64, N) fp32 cm and/or one bf16 act block."""

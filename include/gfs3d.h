@@ -307,9 +307,15 @@ int gfs_edge_scatter(const float* dH, const int32_t* idx, int B, int N, int k, f
 /* model/dgcnn.py:118: y[c, i] = max over the k slots of a[c, i*k + slot] (first maximum) + arg-max slot; and its backward  */
 int gfs_max_over_k_fwd(const float* a, int C, int64_t M, int k, float* y, int64_t ldy, uint8_t* arg, void* stream);
 int gfs_max_over_k_bwd(const float* dy, int64_t lddy, const uint8_t* arg, int C, int64_t M, int k, float* da, void* stream);
-/* model/attention.py:45: p0 = softmax(s*scale) per row, p = p0 * mask (dropout mask, may be NULL with p == p0); backward   */
-int gfs_softmax_rows_fwd(const float* s, int64_t rows, int n, float scale, const float* mask, float* p0, float* p, void* stream);
-int gfs_softmax_rows_bwd(const float* p0, const float* dp, const float* mask, int64_t rows, int n, float scale, float* ds, void* stream);
+/* model/attention.py:45: p0 = softmax(s*scale) per row, p = p0 * dropout; backward.  The dropout factor (1/keep or 0) comes from
+ * an explicit mask (rows x n floats), or -- mask == NULL and keep < 1 -- from a counter-based hash of (seed, row, column) that
+ * the backward regenerates, so no mask tensor exists; keep >= 1 and mask == NULL: no dropout (p may alias p0).
+ * gfs_dropout_mask materialises the hash's mask (tests).                                                                     */
+int gfs_softmax_rows_fwd(const float* s, int64_t rows, int n, float scale, const float* mask, uint32_t seed, float keep,
+                         float* p0, float* p, void* stream);
+int gfs_softmax_rows_bwd(const float* p0, const float* dp, const float* mask, uint32_t seed, float keep, int64_t rows, int n,
+                         float scale, float* ds, void* stream);
+int gfs_dropout_mask(int64_t rows, int n, uint32_t seed, float keep, float* mask, void* stream);
 
 #ifdef __cplusplus
 }

@@ -251,6 +251,29 @@ def test_attention_train_function_vs_autograd(B, N, drop, train_gemm):
     assert rel_err(tc.grad.cpu(), t.grad) <= TOL
 
 
+def test_attention_hashed_dropout_equals_its_materialised_mask(train_gemm):
+    """dropout without a mask tensor: forward and backward derive keep / drop from a hash of (seed, row, column).  The result must
+    equal the explicit-mask path fed with the mask the same hash defines (gfs_dropout_mask), and the keep rate must be right."""
+    from gfs3d import ops
+    from gfs3d.train_ops import AttentionTrain, from_cm, to_cm
+    B, N, keep, seed = 2, 256, 0.9, 12345
+    g = torch.Generator().manual_seed(3)
+    qkv = torch.randn(B, 192, N, generator=g)
+    dy = torch.randn(B, 64, N, generator=g).cuda()
+    mask = ops.dropout_mask(B * N, N, seed, keep, torch.device("cuda")).view(B, N, N)
+    vals = mask.unique().tolist()
+    assert len(vals) == 2 and vals[0] == 0.0 and abs(vals[1] - 1.0 / keep) < 1e-6
+    assert abs(float((mask > 0).float().mean()) - keep) < 5e-3
+    assert not torch.equal(mask[0], mask[1]) and not torch.equal(mask, ops.dropout_mask(B * N, N, seed + 1, keep, mask.device).view(B, N, N))
+    outs = []
+    for m_, s_, k_ in ((mask, 0, 1.0), (None, seed, keep)):
+        t = qkv.clone().cuda().requires_grad_(True)
+        y = AttentionTrain.apply(to_cm(t), B, N, 1.0 / 8.0, m_, s_, k_)
+        from_cm(y, B, N).backward(dy)
+        outs.append((y.detach(), t.grad))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
 def _train_model(golden, golden_sd, name="train_s3dis_b4_n128", wname="gfs_s3dis_weights"):
     import random
     from types import SimpleNamespace
