@@ -34,5 +34,5 @@ rows = sorted(((e.key, e.count, e.device_time_total / 1e3) for e in prof.key_ave
 tot = sum(r[2] for r in rows)
 ours = sum(r[2] for r in rows if "gfs::" in r[0])
 print(f"device kernels: total {tot:.2f} ms, gfs:: {ours:.2f} ms, others {tot - ours:.2f} ms")
-for k, c, t in rows[:45]:
+for k, c, t in [r for r in rows if 'gfs::' not in r[0]][:40]:
     print(f"{t:8.3f} ms {c:4d}  {k[:150]}")
