@@ -193,6 +193,27 @@ class AttentionTrain(torch.autograd.Function):
         return dqkv, None, None, None, None, None, None
 
 
+class ClassSums(torch.autograd.Function):
+    """sums[c, :] = sum of the rows of X (n, D) whose label is c, and the label counts -- the per-class masked sums of
+    model/capl.py:398-401 (generate_fake_proto) for ALL classes in one deterministic pass (gfs_kmeans_accumulate: per-CTA fp32
+    partials, fp64 reduction in a fixed order) instead of one (mask, multiply, two reductions) chain per class.
+    Backward: dX[row] = dSums[label[row]]."""
+
+    @staticmethod
+    def forward(ctx, X, labels, K):
+        X = X.contiguous()
+        labels = labels.to(torch.int32).contiguous()
+        sums, counts = ops.kmeans_accumulate(X, labels, K)
+        ctx.save_for_backward(labels)
+        ctx.mark_non_differentiable(counts)
+        return sums.float(), counts
+
+    @staticmethod
+    def backward(ctx, dsums, _dcounts):
+        (labels,) = ctx.saved_tensors
+        return dsums.index_select(0, labels.long()), None, None
+
+
 def update_running_stats(bn, mean, var, n):
     """nn.BatchNorm semantics: momentum 0.1 (or cumulative when None), unbiased variance for running_var"""
     with torch.no_grad():

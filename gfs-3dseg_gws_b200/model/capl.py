@@ -161,8 +161,9 @@ class mpti_net_Point_GeoAsWeight_v2(nn.Module):
         return fg_feat.transpose(1, 0), fg_gp_feat.transpose(1, 0)
 
     # ------------------------------------------------------------------ logits / prototypes
-    def get_pred(self, x, proto, use_bg_proto=False):
-        """10 * cos(proto, x): x (b, c, n); proto (cls, c) or (b, cls, c); optional bg_proto row first -> (b, cls, n)"""
+    def get_pred(self, x, proto, use_bg_proto=False, xn=None):
+        """10 * cos(proto, x): x (b, c, n); proto (cls, c) or (b, cls, c); optional bg_proto row first -> (b, cls, n).
+        xn: F.normalize(x, dim=1) if the caller already has it (the training forward normalises the point features once)"""
         if proto.dim() == 3:
             if use_bg_proto:
                 proto = torch.cat([self.bg_proto.unsqueeze(0).repeat(proto.shape[0], 1, 1), proto], dim=1)
@@ -173,12 +174,12 @@ class mpti_net_Point_GeoAsWeight_v2(nn.Module):
             pn = F.normalize(proto, p=2, dim=1)
         if torch.is_grad_enabled() and (x.requires_grad or pn.requires_grad):
             # training branch: O(B * cls * N) prototype algebra stays in differentiable torch ops
-            return torch.matmul(pn if pn.dim() == 3 else pn.unsqueeze(0), F.normalize(x, p=2, dim=1)) * 10
+            return torch.matmul(pn if pn.dim() == 3 else pn.unsqueeze(0), xn if xn is not None else F.normalize(x, p=2, dim=1)) * 10
         return ops.cos_logits(_cm(x), pn.detach())
 
-    def post_refine_proto_v2(self, proto, x, point_feat, use_bg_proto=False):
+    def post_refine_proto_v2(self, proto, x, point_feat, use_bg_proto=False, xn=None):
         """query-adaptive prototype refinement (eqn. 6) -> (b, classes, c)"""
-        pred = self.get_pred(x, proto, use_bg_proto)
+        pred = self.get_pred(x, proto, use_bg_proto, xn=xn)
         if pred.requires_grad or point_feat.requires_grad:
             pred_proto = torch.softmax(pred, dim=2) @ point_feat.permute(0, 2, 1)
         else:
@@ -243,20 +244,26 @@ class mpti_net_Point_GeoAsWeight_v2(nn.Module):
         base_num = self.base_num
         point_feat, _, _ = self._features(x)
         fake_num = x.size(0) // 2
-        ori_proto, fake_novel = self.generate_fake_proto(x=point_feat[fake_num:], y=y[fake_num:], main_proto=self.main_proto.clone())
-        x_pre_1 = self.get_pred(x=point_feat, proto=ori_proto, use_bg_proto=True)
+        # the L2-normalised point features are needed three times (support prototypes, both logit evaluations): once is enough
+        xn = F.normalize(point_feat, p=2, dim=1)
+        ori_proto, fake_novel = self.generate_fake_proto(x=point_feat[fake_num:], y=y[fake_num:], main_proto=self.main_proto.clone(),
+                                                         xn=xn[fake_num:])
+        x_pre_1 = self.get_pred(x=point_feat, proto=ori_proto, use_bg_proto=True, xn=xn)
         loss_ce_1 = self.criterion(x_pre_1, y)
-        refine_proto = self.post_refine_proto_v2(proto=self.main_proto.clone(), x=point_feat, point_feat=point_feat, use_bg_proto=True)
+        refine_proto = self.post_refine_proto_v2(proto=self.main_proto.clone(), x=point_feat, point_feat=point_feat, use_bg_proto=True, xn=xn)
         post_refine_proto = refine_proto.clone()
         post_refine_proto[:, :base_num] = post_refine_proto[:, :base_num] + ori_proto[:base_num].unsqueeze(0)
         post_refine_proto[:, base_num:] = post_refine_proto[:, base_num:] * 0 + ori_proto[base_num:].unsqueeze(0)
-        x_pre_2 = self.get_pred(x=point_feat, proto=post_refine_proto, use_bg_proto=True)
+        x_pre_2 = self.get_pred(x=point_feat, proto=post_refine_proto, use_bg_proto=True, xn=xn)
         loss_ce_2 = self.criterion(x_pre_2, y)
         return x_pre_2.max(1)[1], 0.5 * loss_ce_2 + 0.5 * loss_ce_1
 
-    def generate_fake_proto(self, x, y, main_proto, fake_novel=None, post_processing=False):
+    def generate_fake_proto(self, x, y, main_proto, fake_novel=None, post_processing=False, xn=None):
         """model/capl.py:364-411 (training only): half of the classes present in the support half-batch are declared
-        'fake novel'; their classifier rows are replaced by the masked mean of the L2-normalised support features."""
+        'fake novel'; their classifier rows are replaced by the masked mean of the L2-normalised support features.
+        xn: the normalised support features if the caller has them (x / (|x| + 1e-12) and F.normalize agree in fp32 unless
+        |x| < 1e-5).  On CUDA the masked sums of ALL classes come from one deterministic segmented-sum kernel
+        (gfs3d.train_ops.ClassSums) instead of one mask / multiply / reduce chain per class."""
         tmp_y = y.unsqueeze(1)
         unique_y = list(tmp_y.unique())
         if fake_novel is None:
@@ -265,10 +272,21 @@ class mpti_net_Point_GeoAsWeight_v2(nn.Module):
             novel_num = len(unique_y) // 2
             fake_novel = random.sample(unique_y, novel_num)
         new_proto = main_proto / (torch.norm(main_proto, 2, 1, True) + 1e-12)
-        x = x / (torch.norm(x, 2, 1, True) + 1e-12)
+        x = xn if xn is not None else x / (torch.norm(x, 2, 1, True) + 1e-12)
+        class_sums = None
+        if x.is_cuda and len(fake_novel) > 0 and x.shape[1] % 4 == 0:
+            from gfs3d.train_ops import ClassSums
+            rows = x.permute(0, 2, 1).reshape(-1, x.shape[1])                      # (b*n, c) point-major
+            ncls = main_proto.size(0)                                              # labels 0 (background) .. ncls; anything else
+            lab = y.reshape(-1)                                                    # (ignore_index 255) goes to a spare bin
+            lab = torch.where((lab < 0) | (lab > ncls), torch.full_like(lab, ncls + 1), lab)
+            class_sums, class_counts = ClassSums.apply(rows, lab, ncls + 2)
         for fn in fake_novel:
-            tmp_mask = (tmp_y == fn).float()
-            tmp_feat = (x * tmp_mask).sum(0).sum(-1) / (tmp_mask.sum(0).sum(-1) + 1e-12)
+            if class_sums is not None:
+                tmp_feat = class_sums[fn.long()] / (class_counts[fn.long()].float() + 1e-12)
+            else:
+                tmp_mask = (tmp_y == fn).float()
+                tmp_feat = (x * tmp_mask).sum(0).sum(-1) / (tmp_mask.sum(0).sum(-1) + 1e-12)
             if post_processing:
                 tmp_feat = self.post_processing_hard_coding(tmp_feat)
             fake_vec = torch.zeros(new_proto.size(0), 1, device=new_proto.device)
