@@ -89,6 +89,7 @@ class mpti_net_Point_GeoAsWeight_v2(nn.Module):
                 f.key = f.data = None
             if hasattr(mod, "_key") and hasattr(mod, "_wp"):
                 mod._key = mod._wp = None
+        self._mp_key = self._coding_key = None
 
     # ------------------------------------------------------------------ fused feature extraction
     def _features(self, x, need_semantic=False):
@@ -177,6 +178,16 @@ class mpti_net_Point_GeoAsWeight_v2(nn.Module):
             return torch.matmul(pn if pn.dim() == 3 else pn.unsqueeze(0), xn if xn is not None else F.normalize(x, p=2, dim=1)) * 10
         return ops.cos_logits(_cm(x), pn.detach())
 
+    def _main_proto_l2(self):
+        """F.normalize(main_proto) for the eval forward, cached on the parameter's version (three tiny launches per call otherwise)"""
+        p = self.main_proto
+        key = (id(p), p._version, str(p.device))
+        if getattr(self, "_mp_key", None) != key:
+            with torch.no_grad():
+                self._mp_l2 = F.normalize(p.detach(), p=2, dim=1)
+            self._mp_key = key
+        return self._mp_l2
+
     def post_refine_proto_v2(self, proto, x, point_feat, use_bg_proto=False, xn=None):
         """query-adaptive prototype refinement (eqn. 6) -> (b, classes, c)"""
         pred = self.get_pred(x, proto, use_bg_proto, xn=xn)
@@ -223,10 +234,14 @@ class mpti_net_Point_GeoAsWeight_v2(nn.Module):
         with torch.no_grad():
             # post_refine_proto_v2 (eqn. 6), the base/novel prototype update of model/capl.py:117-120 and the normalisation
             # of get_pred as one kernel (gfs_refine_proto) instead of ~25 small tensor ops on (B, classes, 128)
-            pred = self.get_pred(point_feat, self.main_proto)
+            pred = ops.cos_logits(_cm(point_feat), self._main_proto_l2())          # get_pred(point_feat, main_proto)
             pred_proto = ops.softmax_pool(pred, _cm(point_feat))
             refine_l2 = ops.refine_proto(pred_proto, self.main_proto.detach(), gened_proto, base_num)
-            gp_coding = torch.cat([base_class_coding, novel_class_coding], dim=0).float()
+            ck = (id(base_class_coding), base_class_coding._version, id(novel_class_coding), novel_class_coding._version)
+            if getattr(self, "_coding_key", None) != ck:                           # the codings change once per evaluation, not per batch
+                self._coding_cat, self._coding_key = torch.cat([base_class_coding, novel_class_coding], dim=0).float(), ck
+                self._coding_refs = (base_class_coding, novel_class_coding)       # keeps the ids of the key alive
+            gp_coding = self._coding_cat
             x_pre = ops.cos_logits(point_feat, refine_l2, gp_coding, assignment, float(self.args.eval_weight))
             # diagnostics of model/capl.py:104-114: mean of coding[gt, assignment] over all / novel points
             if y is not None:

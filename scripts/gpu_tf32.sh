@@ -1,8 +1,5 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_train.py -q -x 2>&1 | tail -3
-timeout 300 python scripts/bench_train.py --steps 10 2>/dev/null > gpurun_out/r2k_train.json; python - <<'P'
-import json
-d=json.loads(open('gpurun_out/r2k_train.json').read().strip().splitlines()[-1])
-e=d['entry_point_ms']
-print('step',d['ms_per_step'],'gemm',sum(v for k,v in e.items() if 'gemm' in k), 'mem', d['peak_mem_gb'], 'launches', d['gpu_launches_per_step'])
-P
+timeout 900 python -m pytest tests/test_gpu_model.py tests/test_gpu_fullsize.py tests/test_gpu_callers.py tests/test_gpu_train.py -q -x 2>&1 | tail -3
+timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --skip-train --skip-kmeans 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('blocks/s', d['value'], 'ms/step', d['ms_per_step'], 'e2e', d['e2e']['value'], 'launches', d['gpu_launches'])"
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
