@@ -577,7 +577,18 @@ def main():
             "binding_roof": "per-row top-k selection out of TMEM (dependent-issue latency), not HBM or the tensor pipe",
             "distance_tflops_algorithmic": knn_flops / 1e12 / (knn_ms / 1e3) if knn_ms else None,
             "timing": "CUDA events around every C-ABI call on the launch stream, instrumented replay of the same K steps"}
+    # the same entry point against the tensor roof: algorithmic flops = 2 C N^2 per block and layer (the distance matrix); the
+    # filter EXECUTES 12 C' N^2 (three bf16 products of the hi/lo split, candidates streamed twice, C' = C padded to 16)
+    bf16_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1405.0)))
+    knn_exec_flops = 12.0 * (16 + 64 + 64) * NPTS * NPTS * B
+    knn_tensor = {"bound": "tensor", "achieved": knn_flops / 1e12 / (knn_ms / 1e3) if knn_ms else None, "peak": bf16_peak, "unit": "TFLOP/s",
+                  "frac": (knn_flops / 1e12 / (knn_ms / 1e3) / bf16_peak) if knn_ms else None,
+                  "executed_tflops": knn_exec_flops / 1e12 / (knn_ms / 1e3) if knn_ms else None,
+                  "executed_frac": (knn_exec_flops / 1e12 / (knn_ms / 1e3) / bf16_peak) if knn_ms else None,
+                  "note": "over the whole kNN entry point (preparation + filter + exact finish); the filter kernel alone runs the "
+                          "tensor pipe at 43-46 % (ncu, profiles/r2_summary.md)"}
     extra = {
+        "knn_graph_tensor": knn_tensor,
         "edgeconv_given_graph": {"bound": "hbm", "achieved": gbs(ec_bytes, ec_ms), "peak": hbm_peak, "unit": "GB/s",
                                  "frac": (gbs(ec_bytes, ec_ms) or 0) / hbm_peak, "ms_per_step": ec_ms},
         "edgeconv123_fused_knn": {"bound": "hbm", "achieved": gbs(ec123_bytes, ec123_ms), "peak": hbm_peak, "unit": "GB/s",
