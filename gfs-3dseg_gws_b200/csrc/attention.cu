@@ -175,20 +175,23 @@ attention_kernel(const uint8_t* __restrict__ qkv, int kblocks, int kb_q, int til
                 mbar_wait(&s.s_full[sb], ph);
                 tc_fence_after();
                 // pass 1: row max of the raw scores
-                float mx = -INFINITY;
+                // (four independent chains: this warp is alone on its scheduler, a single 128-long dependent max / add chain
+                // would cost 4 cycles per element)
+                float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
                 for (int c0 = 0; c0 < 128; c0 += 32) {
                     uint32_t r[32];
                     tmem_ld32(tmem + tlane + TM_S + sb * 128 + c0, r);
                     tmem_ld_wait32(r);
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(r[c]));
+                    for (int c = 0; c < 32; ++c) mx4[c & 3] = fmaxf(mx4[c & 3], __uint_as_float(r[c]));
                 }
+                const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
                 const float m_new = fmaxf(m_run, mx * scale_log2);
                 const float alpha = ex2(m_run - m_new);           // 0 on the first tile (m_run = -inf)
                 // pass 2: p = 2^(s*scale - m), written as the bf16 A operand of P.V
                 mbar_wait(&s.p_empty[sb], ph ^ 1);
-                float sum = 0.0f;
+                float sum4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
                 for (int c0 = 0; c0 < 128; c0 += 32) {
                     uint32_t r[32];
@@ -201,7 +204,7 @@ attention_kernel(const uint8_t* __restrict__ qkv, int kblocks, int kb_q, int til
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
                             pv[e] = ex2(fmaf(__uint_as_float(r[qq * 8 + e]), scale_log2, -m_new));
-                            sum += pv[e];
+                            sum4[e & 3] += pv[e];
                         }
                         uint4 pk;
                         pk.x = pack_bf16x2(pv[0], pv[1]);
@@ -231,7 +234,7 @@ attention_kernel(const uint8_t* __restrict__ qkv, int kblocks, int kb_q, int til
                     tc_fence_before();
                     mbar_arrive(&s.o_empty[ob]);
                 }
-                l_run = l_run * alpha + sum;
+                l_run = l_run * alpha + ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
                 m_run = m_new;
                 (void)alpha_prev;
             }

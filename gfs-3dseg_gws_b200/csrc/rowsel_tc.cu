@@ -83,6 +83,12 @@ __global__ void rowsel_cmax_kernel(const float* __restrict__ cnorm, int G, float
     }
 }
 
+__device__ __forceinline__ float rt_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // best, second best and the FIRST index of the best among 32 scores held in registers.  MAXM: larger is better.
 // A tournament tree (a pair keeps its best and its runner-up; merging two pairs is three independent min/max), not a
 // running update: the epilogue thread is alone on its scheduler slot and would otherwise crawl along one dependent chain.
@@ -305,21 +311,35 @@ rowsel_tc_kernel(const float* __restrict__ x, int64_t bstride, int64_t cstride, 
                         b2 = fmaxf(b2, cb);
                     }
                 }
-                float sum = 0.0f;
+                // softmax over the words: exp(10 cos - max) as ONE fma and ONE ex2.approx per element (the library expf carries a
+                // range fix-up: two predicated multiplies and a compare per element, and this single-warp-per-scheduler epilogue is
+                // what the kernel waits for -- ncu source page, r2); chunks entirely inside G run without the column predicate
+                const float inv2 = inv * 1.4426950408889634f, nb2 = -b1 * 1.4426950408889634f;
+                float sum4[4] = {0.0f, 0.0f, 0.0f, 0.0f};           // four independent add chains instead of one 150 long
                 for (int ch = 0; ch * 32 < G; ++ch) {
                     tmem_ld32(t0 + ch * 32, rr);
                     tmem_ld_wait32(rr);
+                    if (ch * 32 + 32 <= G) {
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) sum += ch * 32 + c < G ? __expf(__uint_as_float(rr[c]) * inv - b1) : 0.0f;
+                        for (int c = 0; c < 32; ++c) sum4[c & 3] += rt_ex2(fmaf(__uint_as_float(rr[c]), inv2, nb2));
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) sum4[c & 3] += ch * 32 + c < G ? rt_ex2(fmaf(__uint_as_float(rr[c]), inv2, nb2)) : 0.0f;
+                    }
                 }
-                const float rs = 1.0f / sum;
+                const float rs = 1.0f / ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
                 for (int ch = 0; ch * 32 < Gp; ++ch) {
                     tmem_ld32(t0 + ch * 32, rr);
                     tmem_ld_wait32(rr);
                     if (valid) {
                         float e[32];
+                        if (ch * 32 + 32 <= G) {
 #pragma unroll
-                        for (int c = 0; c < 32; ++c) e[c] = ch * 32 + c < G ? __expf(__uint_as_float(rr[c]) * inv - b1) * rs : 0.0f;
+                            for (int c = 0; c < 32; ++c) e[c] = rt_ex2(fmaf(__uint_as_float(rr[c]), inv2, nb2)) * rs;
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < 32; ++c) e[c] = ch * 32 + c < G ? rt_ex2(fmaf(__uint_as_float(rr[c]), inv2, nb2)) * rs : 0.0f;
+                        }
                         if (cos_act) {
                             uint8_t* tl = cos_act + (((m >> 7) * kblocks + kb0 + (ch >> 1)) * 16384);
                             const uint32_t rw = (uint32_t)(m & 127);
