@@ -174,36 +174,38 @@ attention_kernel(const uint8_t* __restrict__ qkv, int kblocks, int kb_q, int til
                 const int sb = g & 1, ph = (g >> 1) & 1;
                 mbar_wait(&s.s_full[sb], ph);
                 tc_fence_after();
-                // pass 1: row max of the raw scores
-                // (four independent chains: this warp is alone on its scheduler, a single 128-long dependent max / add chain
-                // would cost 4 cycles per element)
+                // The score tile is read out of TMEM ONCE, into 128 registers (TMEM reads are 64 B/clk per SM: at two passes over
+                // S plus the O fold they were 71 us of this kernel's 89), and its buffer goes back to the MMA warp right away.
+                uint32_t sr[4][32];
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) tmem_ld32(tmem + tlane + TM_S + sb * 128 + q4 * 32, sr[q4]);
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) tmem_ld_wait32(sr[q4]);
+                tc_fence_before();
+                mbar_arrive(&s.s_empty[sb]);
+                // row max of the raw scores (four independent chains: this warp is alone on its scheduler, a single 128-long
+                // dependent max / add chain would cost 4 cycles per element)
                 float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-                for (int c0 = 0; c0 < 128; c0 += 32) {
-                    uint32_t r[32];
-                    tmem_ld32(tmem + tlane + TM_S + sb * 128 + c0, r);
-                    tmem_ld_wait32(r);
+                for (int q4 = 0; q4 < 4; ++q4)
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) mx4[c & 3] = fmaxf(mx4[c & 3], __uint_as_float(r[c]));
-                }
+                    for (int c = 0; c < 32; ++c) mx4[c & 3] = fmaxf(mx4[c & 3], __uint_as_float(sr[q4][c]));
                 const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
                 const float m_new = fmaxf(m_run, mx * scale_log2);
                 const float alpha = ex2(m_run - m_new);           // 0 on the first tile (m_run = -inf)
-                // pass 2: p = 2^(s*scale - m), written as the bf16 A operand of P.V
+                // p = 2^(s*scale - m), written as the bf16 A operand of P.V
                 mbar_wait(&s.p_empty[sb], ph ^ 1);
                 float sum4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-                for (int c0 = 0; c0 < 128; c0 += 32) {
-                    uint32_t r[32];
-                    tmem_ld32(tmem + tlane + TM_S + sb * 128 + c0, r);
-                    tmem_ld_wait32(r);
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const int c0 = q4 * 32;
                     uint8_t* Pt = s.P[sb] + (c0 >> 6) * 16384;
 #pragma unroll
                     for (int qq = 0; qq < 4; ++qq) {
                         float pv[8];
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
-                            pv[e] = ex2(fmaf(__uint_as_float(r[qq * 8 + e]), scale_log2, -m_new));
+                            pv[e] = ex2(fmaf(__uint_as_float(sr[q4][qq * 8 + e]), scale_log2, -m_new));
                             sum4[e & 3] += pv[e];
                         }
                         uint4 pk;
@@ -214,8 +216,6 @@ attention_kernel(const uint8_t* __restrict__ qkv, int kblocks, int kb_q, int til
                         *reinterpret_cast<uint4*>(Pt + sw128(row, ((c0 & 63) >> 3) + qq)) = pk;
                     }
                 }
-                tc_fence_before();
-                mbar_arrive(&s.s_empty[sb]);
                 fence_proxy_async();
                 mbar_arrive(&s.p_full[sb]);
                 // fold O_{j-1} (relative to the previous max) and rescale to the new max
