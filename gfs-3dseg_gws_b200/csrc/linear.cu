@@ -22,14 +22,14 @@ struct LnSmem {
     uint8_t X[LN_NST][16384];
     uint8_t W[LN_NST][32768];
     float shift[2][256];
-    uint64_t full[LN_NST], empty[LN_NST], accf[2], acce[2];
+    uint64_t full[LN_NST], empty[LN_NST], accf[2], acce[2], wfull;
     uint32_t tmem_base;
 };
 
 __global__ void __launch_bounds__(LN_THREADS, 1)
 linear_kernel(const uint8_t* __restrict__ x_act, int x_kblocks, int x_kb0, int kb_count, const uint8_t* __restrict__ wp,
               const float* __restrict__ shift, int Nout, int NT, int act, int N, int64_t M, int n_mtiles,
-              uint8_t* __restrict__ y_act, int y_kblocks, int y_kb0, float* __restrict__ y_cm, int64_t y_bstride) {
+              uint8_t* __restrict__ y_act, int y_kblocks, int y_kb0, float* __restrict__ y_cm, int64_t y_bstride, int resident) {
     extern __shared__ unsigned char smem_raw[];
     // align inside the shared window with pointer arithmetic on smem_raw (keeps the .shared address space: LDS/STS, not generic LD/ST)
     LnSmem& s = *reinterpret_cast<LnSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
@@ -37,6 +37,12 @@ linear_kernel(const uint8_t* __restrict__ x_act, int x_kblocks, int x_kb0, int k
     const int n_ntiles = Nout / NT;
     const int n_items = n_mtiles * n_ntiles;
     const uint32_t w_bytes = (uint32_t)NT * 128u;
+    // resident mode (the layer's weight slice of one N tile fits the W area: kb_count * NT * 128 B <= 128 KiB): a CTA keeps ONE
+    // N tile's weights in shared memory for its whole life and streams only X tiles; its items are (mt, nt fixed).  The
+    // streaming mode re-reads the weights with every M tile -- 100 of the 147 MB of L2 traffic of the 192 -> 512 layer.
+    const int nt_res = blockIdx.x % n_ntiles, it_first = resident ? blockIdx.x / n_ntiles : blockIdx.x;
+    const int it_step = resident ? gridDim.x / n_ntiles : gridDim.x, it_end = resident ? n_mtiles : n_items;
+    uint8_t* const Wres = s.W[0];
 
     if (warp == 1) {
         if (lane == 0) {
@@ -48,6 +54,7 @@ linear_kernel(const uint8_t* __restrict__ x_act, int x_kblocks, int x_kb0, int k
                 mbar_init(&s.accf[i], 1);
                 mbar_init(&s.acce[i], 128);
             }
+            mbar_init(&s.wfull, 1);
             mbar_fence_init();
         }
         __syncwarp();
@@ -62,13 +69,19 @@ linear_kernel(const uint8_t* __restrict__ x_act, int x_kblocks, int x_kb0, int k
         // =============================== TMA producer ===============================
         if (lane == 0) {
             int stage = 0, phase = 0;
-            for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-                const int mt = it / n_ntiles, nt = it - mt * n_ntiles;
+            if (resident && it_first < it_end) {
+                mbar_arrive_expect_tx(&s.wfull, w_bytes * (uint32_t)kb_count);
+                for (int kb = 0; kb < kb_count; ++kb)
+                    tma_load_1d(Wres + (size_t)kb * w_bytes, wp + ((int64_t)kb * Nout + (int64_t)nt_res * NT) * 128, w_bytes, &s.wfull);
+            }
+            for (int it = it_first; it < it_end; it += it_step) {
+                const int mt = resident ? it : it / n_ntiles, nt = resident ? nt_res : it - mt * n_ntiles;
                 for (int kb = 0; kb < kb_count; ++kb) {
                     mbar_wait(&s.empty[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&s.full[stage], 16384u + w_bytes);
+                    mbar_arrive_expect_tx(&s.full[stage], resident ? 16384u : 16384u + w_bytes);
                     tma_load_1d(s.X[stage], x_act + ((int64_t)mt * x_kblocks + x_kb0 + kb) * 16384, 16384u, &s.full[stage]);
-                    tma_load_1d(s.W[stage], wp + ((int64_t)kb * Nout + (int64_t)nt * NT) * 128, w_bytes, &s.full[stage]);
+                    if (!resident)
+                        tma_load_1d(s.W[stage], wp + ((int64_t)kb * Nout + (int64_t)nt * NT) * 128, w_bytes, &s.full[stage]);
                     if (++stage == LN_NST) {
                         stage = 0;
                         phase ^= 1;
@@ -82,14 +95,15 @@ linear_kernel(const uint8_t* __restrict__ x_act, int x_kblocks, int x_kb0, int k
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_bf16(128, (uint32_t)NT);
             int stage = 0, phase = 0, acc = 0, aphase = 0;
-            for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+            if (resident && it_first < it_end) mbar_wait(&s.wfull, 0);
+            for (int it = it_first; it < it_end; it += it_step) {
                 mbar_wait(&s.acce[acc], aphase ^ 1);
                 tc_fence_after();
                 for (int kb = 0; kb < kb_count; ++kb) {
                     mbar_wait(&s.full[stage], phase);
                     tc_fence_after();
                     const uint64_t adesc = umma_desc_sw128(smem_u32(s.X[stage]));
-                    const uint64_t bdesc = umma_desc_sw128(smem_u32(s.W[stage]));
+                    const uint64_t bdesc = umma_desc_sw128(smem_u32(resident ? Wres + (size_t)kb * w_bytes : s.W[stage]));
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks)
                         umma_bf16(tmem + acc * 256, adesc + ks * 2, bdesc + ks * 2, idesc, (kb | ks) ? 1u : 0u);
@@ -114,8 +128,8 @@ linear_kernel(const uint8_t* __restrict__ x_act, int x_kblocks, int x_kb0, int k
         const int et = tid - 64;   // 0..127
         const uint32_t tlane = (uint32_t)(quarter * 32) << 16;
         int acc = 0, aphase = 0;
-        for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-            const int mt = it / n_ntiles, nt = it - mt * n_ntiles;
+        for (int it = it_first; it < it_end; it += it_step) {
+            const int mt = resident ? it : it / n_ntiles, nt = resident ? nt_res : it - mt * n_ntiles;
             for (int c = et; c < NT; c += 128) s.shift[acc][c] = shift ? shift[nt * NT + c] : 0.0f;
             named_bar_sync(1, 128);
             mbar_wait(&s.accf[acc], aphase);
@@ -202,9 +216,14 @@ extern "C" int gfs_linear_bf16(const void* x_act, int x_kblocks, int x_kb0, int 
     GFS_REQUIRE(sms > 0, GFS_ERR_CUDA, "gfs_linear_bf16: cannot query the device");
     const size_t smem = sizeof(LnSmem) + 1024;
     GFS_CUDA_OK(allow_smem(reinterpret_cast<const void*>(linear_kernel), smem));
-    linear_kernel<<<items < sms ? items : sms, LN_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
+    const int n_ntiles = Nout / NT;
+    int grid = items < sms ? items : sms;
+    // resident weights: the N tile's slice must fit the 128 KiB W area; the grid is a multiple of the N tiles so that a CTA's tile is fixed
+    const int resident = ((size_t)kb_count * NT * 128 <= sizeof(LnSmem::W)) && grid >= n_ntiles;
+    if (resident) grid -= grid % n_ntiles;
+    linear_kernel<<<grid, LN_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const uint8_t*>(x_act), x_kblocks, x_kb0, kb_count, static_cast<const uint8_t*>(w_packed), shift, Nout, NT,
-        act, N, M, n_mtiles, static_cast<uint8_t*>(y_act), y_kblocks, y_kb0, y_cm, y_bstride);
+        act, N, M, n_mtiles, static_cast<uint8_t*>(y_act), y_kblocks, y_kb0, y_cm, y_bstride, resident);
     GFS_LAUNCH_OK("linear_kernel");
     return GFS_OK;
 }
