@@ -128,18 +128,22 @@ linear_kernel(const uint8_t* __restrict__ x_act, int x_kblocks, int x_kb0, int k
         const int et = tid - 64;   // 0..127
         const uint32_t tlane = (uint32_t)(quarter * 32) << 16;
         int acc = 0, aphase = 0;
+        if (resident) {                                      // the N tile is fixed: its shifts are loaded once, not once per item
+            for (int c = et; c < NT; c += 128) s.shift[0][c] = s.shift[1][c] = shift ? shift[nt_res * NT + c] : 0.0f;
+            named_bar_sync(1, 128);
+        }
         for (int it = it_first; it < it_end; it += it_step) {
             const int mt = resident ? it : it / n_ntiles, nt = resident ? nt_res : it - mt * n_ntiles;
-            for (int c = et; c < NT; c += 128) s.shift[acc][c] = shift ? shift[nt * NT + c] : 0.0f;
-            named_bar_sync(1, 128);
+            if (!resident) {
+                for (int c = et; c < NT; c += 128) s.shift[acc][c] = shift ? shift[nt * NT + c] : 0.0f;
+                named_bar_sync(1, 128);
+            }
             mbar_wait(&s.accf[acc], aphase);
             tc_fence_after();
             const int64_t m = (int64_t)mt * 128 + row;
             const int64_t b = m / N, n = m - b * N;
-            for (int c0 = 0; c0 < NT; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld32(tmem + tlane + acc * 256 + c0, r);
-                tmem_ld_wait32(r);
+            // one 32-column chunk of the accumulator: + shift, activation, fp32 channel-major and / or bf16 act-tile stores
+            auto emit = [&](int c0, const uint32_t (&r)[32]) {
                 float v[32];
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
@@ -168,6 +172,21 @@ linear_kernel(const uint8_t* __restrict__ x_act, int x_kblocks, int x_kb0, int k
                             *reinterpret_cast<uint4*>(t + sw128(row, q0 + qq)) = pk;
                         }
                     }
+                }
+            };
+            // the TMEM read of chunk i+1 is in flight while chunk i is converted and stored (two register buffers taking turns:
+            // the ncu source page showed the first use after every tcgen05.wait::ld as the epilogue's largest stall)
+            const uint32_t tacc = tmem + tlane + acc * 256;
+            uint32_t ra[32], rb[32];
+            tmem_ld32(tacc, ra);
+            for (int c0 = 0; c0 < NT; c0 += 64) {
+                tmem_ld_wait32(ra);
+                if (c0 + 32 < NT) tmem_ld32(tacc + c0 + 32, rb);
+                emit(c0, ra);
+                if (c0 + 32 < NT) {
+                    tmem_ld_wait32(rb);
+                    if (c0 + 64 < NT) tmem_ld32(tacc + c0 + 64, ra);
+                    emit(c0 + 32, rb);
                 }
             }
             tc_fence_before();
