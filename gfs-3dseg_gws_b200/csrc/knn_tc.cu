@@ -38,6 +38,10 @@
 //   A row-half that collects more than KT_CAP candidates inside the bound (floods of exact ties; feature spaces so
 //   collapsed that the pinned chain's own rounding exceeds the neighbour spacing) raises a flag for its 64-row tile, and
 //   knn.cu's exact kernel redoes just those tiles inside the same call.
+#include <cstdlib>
+#include <map>
+#include <mutex>
+
 #include "common.cuh"
 
 namespace gfs {
@@ -680,9 +684,87 @@ static int kt_launch_finish(const KtPlan& p, uint8_t* ws, const float* sqnorm, i
 
 }  // namespace gfs
 
+namespace gfs {
+
+// One chain of the four launches over `B` consecutive blocks, scratch at `ws` (kt_plan(B, C, N) bytes).
+static int kt_chain(const float* x, int64_t x_bstride, int B, int C, int N, int k, float* sqnorm, uint8_t* ws, int32_t* idx_out,
+                    float* dist_out, float* dbg, bool set_only, cudaStream_t st) {
+    const KtPlan p = kt_plan(B, C, N);
+    GFS_CUDA_OK(cudaMemsetAsync(ws + p.off_flags, 0, p.zero_bytes, st));
+    knn_prep_kernel<<<dim3(p.Npad / 128, B), KP_THREADS, 0, st>>>(x, x_bstride, C, N, p.Npad, p.Cp16, p.KB, p.CPT, ws,
+                                                           reinterpret_cast<float*>(ws + p.off_xp),
+                                                           reinterpret_cast<float*>(ws + p.off_nh),
+                                                           reinterpret_cast<float*>(ws + p.off_nl),
+                                                           reinterpret_cast<uint32_t*>(ws + p.off_tag), sqnorm);
+    GFS_LAUNCH_OK("knn_prep_kernel");
+    int rc = kt_launch_filter<32>(p, ws, B, N, k, dbg, st);
+    if (rc != GFS_OK) return rc;
+    rc = set_only ? kt_launch_finish<true>(p, ws, sqnorm, B, N, k, idx_out, nullptr, st)
+                  : kt_launch_finish<false>(p, ws, sqnorm, B, N, k, idx_out, dist_out, st);
+    if (rc != GFS_OK) return rc;
+    return knn_exact_flagged(x, x_bstride, B, C, N, k, sqnorm, reinterpret_cast<const int*>(ws + p.off_flags), idx_out, dist_out, st);
+}
+
+// Two chains side by side.  The filter kernel holds one CTA per SM (all 512 TMEM columns, ~200 KB of shared memory), so a
+// call whose CTA count is not a multiple of the SM count ends in a partly empty wave (32 blocks x 2048 points: 256 CTAs on
+// 148 SMs, 40 SMs idle for the second half of the kernel).  Splitting the blocks into two independent chains on two
+// streams lets the first chain's finish kernel (and the second chain's preparation) run on the SMs the second chain's
+// filter leaves idle.  The side stream is forked from and joined back into the caller's stream with events, so the call
+// keeps its stream semantics and can be captured into a CUDA graph (the graph gets two parallel branches).
+struct KtSide {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+static std::mutex g_kt_mu;
+static std::map<int, KtSide> g_kt_side;
+static int g_kt_split = -2;            // -2: read GFS3D_KNN_SPLIT on first use; -1: automatic; 0: never; n > 0: blocks in the first chain
+
+// blocks that go to the first chain (0 = one chain)
+static int kt_first_chain(int B, int N) {
+    if (g_kt_split == -2) {
+        const char* e = getenv("GFS3D_KNN_SPLIT");
+        g_kt_split = e ? atoi(e) : -1;
+        if (g_kt_split < -1) g_kt_split = -1;
+    }
+    if (B < 2 || g_kt_split == 0) return 0;
+    if (g_kt_split > 0) return g_kt_split < B ? g_kt_split : B - 1;
+    const int sms = sm_count();
+    const int per_block = (N + KT_ROWS - 1) / KT_ROWS;
+    const int ctas = B * per_block;
+    if (sms <= 0 || ctas <= sms || ctas % sms == 0) return 0;      // one wave, or no tail to fill
+    return B / 2;
+}
+
+static int kt_side_for_device(KtSide*& out) {
+    int dev = 0;
+    GFS_CUDA_OK(cudaGetDevice(&dev));
+    KtSide& s = g_kt_side[dev];
+    if (!s.stream) {
+        GFS_CUDA_OK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        GFS_CUDA_OK(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
+        GFS_CUDA_OK(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
+    }
+    out = &s;
+    return GFS_OK;
+}
+
+}  // namespace gfs
+
 extern "C" int64_t gfs_knn_tc_workspace_bytes(int B, int C, int N) {
     if (B <= 0 || C <= 0 || N <= 0 || C > 64) return 0;
-    return (int64_t)gfs::kt_plan(B, C, N).total;
+    return (int64_t)gfs::kt_plan(B, C, N).total + 512;     // + the rounding slack of two chains' separate plans
+}
+
+extern "C" int gfs_knn_tc_chains(int B, int C, int N) {
+    if (B <= 0 || C <= 0 || N <= 0) return 0;
+    std::lock_guard<std::mutex> lk(gfs::g_kt_mu);
+    return gfs::kt_first_chain(B, N) > 0 ? 2 : 1;
+}
+
+extern "C" int gfs_knn_tc_set_split(int blocks_in_first_chain) {
+    std::lock_guard<std::mutex> lk(gfs::g_kt_mu);
+    gfs::g_kt_split = blocks_in_first_chain < -1 ? -1 : blocks_in_first_chain;
+    return GFS_OK;
 }
 
 static int kt_run(const char* who, const float* x, int64_t x_bstride, int B, int C, int N, int k, float* sqnorm, void* workspace,
@@ -698,25 +780,33 @@ static int kt_run(const char* who, const float* x, int64_t x_bstride, int B, int
                 (long long)B * N);
     GFS_REQUIRE(N % 4 == 0 && x_bstride % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, GFS_ERR_UNSUPPORTED,
                 "%s: needs N %% 4 == 0 and 16-byte aligned rows (N=%d)", who, N);
-    const KtPlan p = kt_plan(B, C, N);
-    GFS_REQUIRE(workspace_bytes >= (int64_t)p.total && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, GFS_ERR_BAD_ARG,
-                "%s: workspace of %lld bytes (256-byte aligned) needed, got %lld", who, (long long)p.total,
-                (long long)workspace_bytes);
+    const int64_t need = gfs_knn_tc_workspace_bytes(B, C, N);
+    GFS_REQUIRE(workspace_bytes >= need && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, GFS_ERR_BAD_ARG,
+                "%s: workspace of %lld bytes (256-byte aligned) needed, got %lld", who, (long long)need, (long long)workspace_bytes);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     uint8_t* ws = static_cast<uint8_t*>(workspace);
-    GFS_CUDA_OK(cudaMemsetAsync(ws + p.off_flags, 0, p.zero_bytes, st));
-    knn_prep_kernel<<<dim3(p.Npad / 128, B), KP_THREADS, 0, st>>>(x, x_bstride, C, N, p.Npad, p.Cp16, p.KB, p.CPT, ws,
-                                                           reinterpret_cast<float*>(ws + p.off_xp),
-                                                           reinterpret_cast<float*>(ws + p.off_nh),
-                                                           reinterpret_cast<float*>(ws + p.off_nl),
-                                                           reinterpret_cast<uint32_t*>(ws + p.off_tag), sqnorm);
-    GFS_LAUNCH_OK("knn_prep_kernel");
-    int rc = kt_launch_filter<32>(p, ws, B, N, k, dbg, st);
+    std::lock_guard<std::mutex> lk(g_kt_mu);           // the side stream's events are shared by the callers of one device
+    const int b1 = dbg ? 0 : kt_first_chain(B, N);     // the diagnostic entry reads one plan's flags: one chain
+    if (b1 == 0) return kt_chain(x, x_bstride, B, C, N, k, sqnorm, ws, idx_out, dist_out, dbg, set_only, st);
+
+    KtSide* side = nullptr;
+    int rc = kt_side_for_device(side);
     if (rc != GFS_OK) return rc;
-    rc = set_only ? kt_launch_finish<true>(p, ws, sqnorm, B, N, k, idx_out, nullptr, st)
-                  : kt_launch_finish<false>(p, ws, sqnorm, B, N, k, idx_out, dist_out, st);
+    const int b2 = B - b1;
+    GFS_CUDA_OK(cudaEventRecord(side->fork, st));
+    GFS_CUDA_OK(cudaStreamWaitEvent(side->stream, side->fork, 0));
+    rc = kt_chain(x, x_bstride, b1, C, N, k, sqnorm, ws, idx_out, dist_out, nullptr, set_only, st);
+    const int rc2 = kt_chain(x + (int64_t)b1 * x_bstride, x_bstride, b2, C, N, k, sqnorm + (int64_t)b1 * N, ws + kt_plan(b1, C, N).total,
+                             idx_out + (int64_t)b1 * N * k, dist_out ? dist_out + (int64_t)b1 * N * k : nullptr, nullptr, set_only,
+                             side->stream);
+    // join even after a failed launch: a stream left forked would break an enclosing graph capture
+    const cudaError_t e1 = cudaEventRecord(side->join, side->stream);
+    const cudaError_t e2 = cudaStreamWaitEvent(st, side->join, 0);
     if (rc != GFS_OK) return rc;
-    return knn_exact_flagged(x, x_bstride, B, C, N, k, sqnorm, reinterpret_cast<const int*>(ws + p.off_flags), idx_out, dist_out, st);
+    if (rc2 != GFS_OK) return rc2;
+    GFS_CUDA_OK(e1);
+    GFS_CUDA_OK(e2);
+    return GFS_OK;
 }
 
 extern "C" int gfs_knn_tc_f32(const float* x, int64_t x_bstride, int B, int C, int N, int k, float* sqnorm, void* workspace,

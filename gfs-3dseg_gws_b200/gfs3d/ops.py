@@ -114,11 +114,13 @@ def knn(x: torch.Tensor, k: int, return_dist: bool = False, impl: Optional[str] 
     if impl == "tc" or (impl == "auto" and knn_tc_eligible(C, N, k)):
         nbytes = int(lib().gfs_knn_tc_workspace_bytes(B, C, N))
         ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        with torch.cuda.device(x.device):
+            nk = 4 * int(lib().gfs_knn_tc_chains(B, C, N))     # prepare, filter, finish, repair per chain (one or two chains)
         if ordered or return_dist:
-            _call("gfs_knn_tc_f32", 4, _ptr(x), x.stride(0), B, C, N, k, _ptr(sq), _ptr(ws), nbytes, _ptr(idx), _ptr(dist),
+            _call("gfs_knn_tc_f32", nk, _ptr(x), x.stride(0), B, C, N, k, _ptr(sq), _ptr(ws), nbytes, _ptr(idx), _ptr(dist),
                   _stream())
         else:
-            _call("gfs_knn_tc_set_f32", 4, _ptr(x), x.stride(0), B, C, N, k, _ptr(sq), _ptr(ws), nbytes, _ptr(idx), _stream())
+            _call("gfs_knn_tc_set_f32", nk, _ptr(x), x.stride(0), B, C, N, k, _ptr(sq), _ptr(ws), nbytes, _ptr(idx), _stream())
     else:
         _call("gfs_knn_f32", 2, _ptr(x), x.stride(0), B, C, N, k, _ptr(sq), _ptr(idx), _ptr(dist), _stream())
     return (idx, dist) if return_dist else idx

@@ -64,8 +64,15 @@ int gfs_knn_f32(const float* x, int64_t x_bstride, int B, int C, int N, int k,
  * `workspace` is scratch of gfs_knn_tc_workspace_bytes(B, C, N) bytes, 256-byte aligned (operand tiles, point-major copy,
  * per-point filter terms, up to 2 x 128 survivor records per row, repair flags); rows with more survivors than that
  * (floods of exact ties) are redone by the all-fp32 kernel inside the same call.  Four launches (prepare, filter,
- * finish, repair), no host synchronisation.                                                                          */
+ * finish, repair), no host synchronisation.  When the filter's CTA count leaves a partly empty last wave on this device
+ * the blocks are processed as TWO such chains side by side (the second on an internal stream forked from and joined back
+ * into `stream` with events: same stream semantics, capturable into a CUDA graph), so that one chain's finish fills the
+ * SMs the other chain's filter leaves idle.  gfs_knn_tc_chains tells how many chains a call of that shape runs (1 or 2);
+ * gfs_knn_tc_set_split overrides the choice: -1 automatic (default; also the GFS3D_KNN_SPLIT environment variable),
+ * 0 always one chain, n > 0 the first n blocks form the first chain.  The results do not depend on it.               */
 int64_t gfs_knn_tc_workspace_bytes(int B, int C, int N);
+int gfs_knn_tc_chains(int B, int C, int N);
+int gfs_knn_tc_set_split(int blocks_in_first_chain);
 int gfs_knn_tc_f32(const float* x, int64_t x_bstride, int B, int C, int N, int k,
                    float* sqnorm, void* workspace, int64_t workspace_bytes,
                    int32_t* idx_out, float* dist_out, void* stream);

@@ -204,3 +204,46 @@ def test_tc_large_common_offset_c64():
     (ia, da), (ib, db) = _both(x.cuda(), 20)
     assert torch.equal(ia, ib) and torch.equal(da, db)
     assert torch.equal(ib[:1].cpu(), O.knn_exact(x[:1], 20))
+
+
+@pytest.mark.parametrize("B,C,N,k,first", [(5, 64, 1024, 20, 2), (3, 9, 516, 16, 1), (4, 33, 2048, 40, 3), (2, 64, 260, 20, 5)])
+def test_two_chains_equal_one_chain(B, C, N, k, first):
+    """gfs_knn_tc_set_split: the blocks processed as two chains side by side (second chain on the library's side stream)
+    give the bits of the single chain -- ordered output with distances, set output, tie-flood repair included -- and the
+    call can be captured into a CUDA graph with the fork / join inside."""
+    from gfs3d._lib import lib
+    ops = _ops()
+    g = torch.Generator().manual_seed(B * 77 + N)
+    x = torch.randn(B, C, N, generator=g)
+    x[B - 1, :, : N // 2] = 0.25                      # a tie flood in the last block: repair pass inside the second chain
+    x = x.cuda()
+    try:
+        assert lib().gfs_knn_tc_set_split(0) == 0
+        assert lib().gfs_knn_tc_chains(B, C, N) == 1
+        i1, d1 = ops.knn(x, k, return_dist=True, impl="tc")
+        s1 = ops.knn(x, k, impl="tc", ordered=False)
+        assert lib().gfs_knn_tc_set_split(first) == 0
+        assert lib().gfs_knn_tc_chains(B, C, N) == 2
+        n0 = ops.LAUNCHES
+        i2, d2 = ops.knn(x, k, return_dist=True, impl="tc")
+        assert ops.LAUNCHES - n0 == 8
+        s2 = ops.knn(x, k, impl="tc", ordered=False)
+        torch.cuda.synchronize()
+        assert torch.equal(i1, i2) and torch.equal(d1, d2)
+        assert torch.equal(s1.sort(dim=2).values, s2.sort(dim=2).values)
+        assert torch.equal(s2.sort(dim=2).values, i1.sort(dim=2).values)
+        # graph capture: the side stream is forked from and joined back into the capturing stream
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            ops.knn(x, k, impl="tc", ordered=False)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            s3 = ops.knn(x, k, impl="tc", ordered=False)
+        s3.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(s3.sort(dim=2).values, s1.sort(dim=2).values)
+    finally:
+        lib().gfs_knn_tc_set_split(-1)
