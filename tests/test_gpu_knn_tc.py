@@ -94,7 +94,7 @@ def test_tc_adversarial_inputs(case):
                                               (33, 512, 1e-3, 0.0), (64, 2048, 1.0, 5.0), (9, 1024, 0.05, 3.0)])
 def test_filter_error_is_inside_the_margin(C, N, scale, offset):
     """The proof of exactness in knn_tc.cu needs |v(i,j) - D(i,j)| <= a_i + a_j for the tensor-core value v, with
-    a = 2^-15 |x~|^2 + (2C+6) 2^-25 |x|^2 per point.  The diagnostic entry dumps u = v + a_j; in units of d = 2 D + const_i the
+    a = 2^-15 |x~|^2 + 2^-24 sum_c (C-c) x_c^2 + 6 2^-25 |x|^2 per point.  The diagnostic entry dumps u = v + a_j; in units of d = 2 D + const_i the
     requirement reads |2 (u - a_j) - d - const_i| <= 2 (a_i + a_j).  Measure it: it must stay below HALF of that."""
     ops = _ops()
     g = torch.Generator().manual_seed(C + N)
@@ -108,7 +108,8 @@ def test_filter_error_is_inside_the_margin(C, N, scale, offset):
     mu = 0.25 * ((x32[:, 0] + x32[:, N // 4]) + (x32[:, N // 2] + x32[:, 3 * (N // 4)]))       # the kernel's shift
     xc = xd - mu.double()[:, None]
     cc = (xc * xc).sum(0)
-    a = 2.0 ** -15 * cc + (2 * C + 6) * 2.0 ** -25 * xx
+    aw = (torch.arange(C, 0, -1, dtype=torch.float64, device=xd.device)[:, None] * xd * xd).sum(0)
+    a = 2.0 ** -15 * cc + 2.0 ** -24 * aw + 6 * 2.0 ** -25 * xx
     resid = 2.0 * (filt[0, :, :N].double() - a[None, :]) - d_true        # = |x~_i|^2 + error
     err = (resid - resid.median(dim=1, keepdim=True).values).abs()
     ratio = float((err / (2.0 * (a[:, None] + a[None, :]))).max())
