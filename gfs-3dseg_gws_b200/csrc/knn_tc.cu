@@ -23,15 +23,17 @@
 //                records {u, tag} in global memory with predicated stores: about 1.2 % of the candidates at NG = 32
 //                (N = 2048, k = 20: ~25 per row), independent of the data's order.
 //      Error bound (per PAIR, so that one far-away point does not loosen the filter for every row):
-//        |v(i,j) - D(i,j)| <= a_i + a_j,   a = 2^-15 |x~|^2 + 2^-24 A + 6 2^-25 |x|^2,  A = sum_c (C - c) x_c^2   per point
+//        |v(i,j) - D(i,j)| <= a_i + a_j,   a = 2^-15 |x~|^2 + 2^-25 A + 6 2^-25 |x|^2,  A = sum_c (C - c) x_c^2   per point
 //      (bf16 split residual <= 3 * 2^-18 |x~_i||x~_j|, <= 192 fp32 accumulations in the tensor core, one fp32 addition,
 //      |x~_i||x~_j| <= (|x~_i|^2+|x~_j|^2)/2, plus the rounding of the pinned fp32 chain on the original coordinates.
 //      The chain rounds every partial sum s_c = fl(s_{c-1} + x_ic x_jc) once, |error_c| <= 2^-24 sum_{c'<=c} |x_ic' x_jc'|:
 //      channel c' enters C - c' partial sums, so the dot product is off by at most 2^-24 sum_c (C - c) |x_ic x_jc|
-//      <= 2^-25 (A_i + A_j), and |x_j|^2 (the same chain on one point) by at most 2^-24 A_j.  On the filter's scale
-//      v ~ D / 2 that is 2^-25 A per point for the dot product plus 2^-25 A for the point's own square norm; the fmaf /
-//      subtraction that finish d and the (1 + 2^-24)^C growth of the partial sums are inside 6 2^-25 |x|^2.  A <= C |x|^2,
-//      about half of it for evenly spread channels: the worst case "C roundings of the full product" is twice as wide.
+//      <= 2^-25 (A_i + A_j): on the filter's scale v ~ D / 2 that is 2^-25 A per point.  The square norms the pinned
+//      formula subtracts are COMPUTED numbers, known per point when the operands are prepared: the filter constant of
+//      candidate j carries dj = (|x_j|^2 - xx_j) / 2 (|x_j|^2 from an fp64 chain), so their rounding is not an uncertainty
+//      at all.  The fmaf / subtraction that finish d, the (1 + 2^-24)^C growth of the partial sums and the 2^-53 of the
+//      fp64 chain are inside 6 2^-25 |x|^2.  A <= C |x|^2, about half of it for evenly spread channels: the plain worst
+//      case "C roundings of the full product, twice" ((2C+6) 2^-25 |x|^2) is four times as wide.
 //      tests/test_gpu_knn_tc.py measures the observed error against the bound).  u is an UPPER bound of D up to the row constant
 //      a_i, w a LOWER bound.  The k-th largest lower bound minus 2 a_i cannot exceed the exact k-th best D, hence a
 //      candidate with u below T - 2 a_i cannot be among the exact top k.
@@ -102,23 +104,29 @@ knn_prep_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int 
 
     if (t < 128) {
     float xx = 0.0f, cc = 0.0f, aw = 0.0f;
+    double xd = 0.0;
     for (int c = 0; c < C; ++c) {
         const float v = xs[c * KP_LD + t];
         const float u = v - mus[c];
         xx = fmaf(v, v, xx);                 // same chain as sqnorm_kernel
         cc = fmaf(u, u, cc);
         aw = __fmaf_ru(__fmul_ru(v, v), (float)(C - c), aw);   // A = sum_c (C - c) x_c^2, rounded up
+        xd = fma((double)v, (double)v, xd);  // |x|^2 to 2^-53: what the fp32 chain above SHOULD have given
     }
     if (!valid) cc = 0.0f;                   // padding rows: all-zero operands (their v - mu would not be zero)
+    // The pinned distance subtracts the COMPUTED square norm xx, not |x_j|^2: its rounding error is a known number per
+    // point, not an uncertainty.  dj = (|x_j|^2 - xx_j) / 2 moves the candidate's filter constant to where the pinned
+    // arithmetic will put it (the row's own term is the same for all its candidates and does not matter).
+    const float dj = (float)(0.5 * (xd - (double)xx));
     // a = the point's share of the pair error bound  |v(i,j) - D(i,j)| <= a_i + a_j  (see the header):
     //   2^-15 |x~|^2  covers the bf16 split residual, the tensor core's fp32 accumulation and the fp32 addition of the constant
-    //   2^-24 A + 6 2^-25 |x|^2  the rounding of the pinned fp32 chain on the original coordinates, A = sum_c (C - c) x_c^2:
+    //   2^-25 A + 6 2^-25 |x|^2  the rounding of the pinned fp32 dot product on the original coordinates, A = sum_c (C - c) x_c^2:
     //   channel c's product sits in C - c of the chain's partial sums, each of which is rounded once.
     // nh carries +a_j (-> an upper bound of D), nl carries -a_j (-> a lower bound), the tag 2 a_j rounded UP to bf16.
-    const float a = __fmaf_ru(0x1p-15f, cc, __fmaf_ru(0x1p-24f, aw, __fmul_ru(6.0f * 0x1p-25f, xx)));
+    const float a = __fmaf_ru(0x1p-15f, cc, __fmaf_ru(0x1p-25f, aw, __fmul_ru(6.0f * 0x1p-25f, xx)));
     const __nv_bfloat16 dl = __float2bfloat16_ru(2.0f * a);
-    nh[(int64_t)b * Npad + n] = valid ? __fmaf_ru(-0.5f, cc, a) : -INFINITY;
-    nl[(int64_t)b * Npad + n] = valid ? __fmaf_rd(-0.5f, cc, -a) : -INFINITY;
+    nh[(int64_t)b * Npad + n] = valid ? __fadd_ru(__fmaf_ru(-0.5f, cc, a), dj) : -INFINITY;
+    nl[(int64_t)b * Npad + n] = valid ? __fadd_rd(__fmaf_rd(-0.5f, cc, -a), dj) : -INFINITY;
     tag[(int64_t)b * Npad + n] = ((uint32_t)n << 16) | (uint32_t)__bfloat16_as_ushort(dl);
     if (valid) sqnorm[(int64_t)b * N + n] = xx;
     }

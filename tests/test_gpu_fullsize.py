@@ -194,13 +194,16 @@ def test_knn_filter_error_bound_on_all_three_layers_of_the_bench_model(golden_sd
         for b in range(0, B, 8):                                   # fp64 check of four blocks per layer
             fd = f[b].double()
             xx = (fd * fd).sum(0)
-            d_true = 2.0 * (fd.t() @ fd) - xx[:, None] - xx[None, :]
+            xx_fl = torch.zeros(N, dtype=torch.float32, device=f.device)      # the pinned fp32 chain's |x_j|^2 (fma = fp64 sum rounded)
+            for c in range(C):
+                xx_fl = (xx_fl.double() + fd[c] * fd[c]).float()
+            d_true = 2.0 * (fd.t() @ fd) - xx[:, None] - xx_fl.double()[None, :]
             f32 = f[b]
             mu = 0.25 * ((f32[:, 0] + f32[:, N // 4]) + (f32[:, N // 2] + f32[:, 3 * (N // 4)]))
             xc = fd - mu.double()[:, None]
             cc = (xc * xc).sum(0)
             aw = (torch.arange(C, 0, -1, dtype=torch.float64, device=fd.device)[:, None] * fd * fd).sum(0)
-            a = 2.0 ** -15 * cc + 2.0 ** -24 * aw + 6 * 2.0 ** -25 * xx
+            a = 2.0 ** -15 * cc + 2.0 ** -25 * aw + 6 * 2.0 ** -25 * xx
             resid = 2.0 * (filt[b, :, :N].double() - a[None, :]) - d_true
             err = (resid - resid.median(dim=1, keepdim=True).values).abs()
             worst = max(worst, float((err / (2.0 * (a[:, None] + a[None, :]))).max()))
