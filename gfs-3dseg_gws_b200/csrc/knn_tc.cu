@@ -61,6 +61,8 @@ constexpr int KT_SELW = 16;           // selection warps: (row tile, lane quarte
 constexpr int KT_THREADS = 64 + 32 * KT_SELW;   // warp 0 TMA, warp 1 MMA, warps 2-17 selection
 constexpr int KT_CAP = 128;           // survivor records per (row, column half)
 constexpr int KT_SURV = 2 * KT_CAP;   // survivors per row the finish kernel can take (32 per round, one per lane)
+constexpr int KF_RMAX = 20;           // SET finish: rows with up to k + KF_RMAX survivors are classified by their bounds
+constexpr int KF_GL = 4;              // finish: row-gather load instructions in flight per group
 
 typedef unsigned long long u64;
 
@@ -379,13 +381,14 @@ knn_tc_kernel(const uint8_t* __restrict__ ops, const float* __restrict__ nh, con
         // the chunk are staged in the thread's own shared-memory slot (the exchange area of the threshold step, now free)
         // because a hit's value has to be fetched by a run-time index.
         // 32-bit record offsets from the (uniform) base pointer: one IMAD.WIDE per store instead of 64-bit pointer chains
+        // (records are {u, tag} pairs, the two half lists of a row lie side by side: [half 0: KT_CAP x 8 B][half 1: KT_CAP x 8 B])
         const int64_t g = (int64_t)b * N + (valid ? n : 0);
-        const uint32_t off0 = (uint32_t)(g * 2 + half) * (uint32_t)(2 * KT_CAP);     // [u: KT_CAP floats][tag: KT_CAP words]
+        const uint32_t off0 = (uint32_t)(g * 2 + half) * (uint32_t)KT_CAP;           // KT_CAP records {u, tag} of 8 bytes
         uint32_t off = off0;
         const uint32_t olim = off0 + (KT_CAP - 32);
         // the base comes from shared memory, not from the parameter bank: it then lives in a register pair instead of being
         // re-loaded from the constant bank for every record
-        uint32_t* const survw = reinterpret_cast<uint32_t*>(s.surv_base);
+        uint2* const survw = reinterpret_cast<uint2*>(s.surv_base);
         bool ovf = false;
         named_bar_sync(1, 32 * KT_SELW);                          // every thread has read the other half's maxima: xch is free
         float4* const stg = xch + (tid - 64);                     // float4 q of this thread's chunk lives at stg[q * 512]
@@ -423,9 +426,7 @@ knn_tc_kernel(const uint8_t* __restrict__ ops, const float* __restrict__ nh, con
             while (mask) {                                        // ascending column order
                 const int c = __ffs(mask) - 1;
                 mask &= mask - 1;
-                uint32_t* const rec = survw + off;                // one IMAD.WIDE.U32, two stores with immediate offsets
-                rec[0] = __float_as_uint(stgf[(c >> 2) * (128 * KT_SELW) + (c & 3)]);
-                rec[KT_CAP] = tgs[c];
+                survw[off] = make_uint2(__float_as_uint(stgf[(c >> 2) * (128 * KT_SELW) + (c & 3)]), tgs[c]);   // one 8-byte store
                 ++off;
             }
             tc_fence_before();
@@ -474,11 +475,42 @@ knn_finish_kernel(const float* __restrict__ xp, const float* __restrict__ sqnorm
     float* stg = stg_all[warp];
     const int sub = lane % LPR, grp = lane / LPR;
     const int64_t gstep = (int64_t)gridDim.x * KF_WARPS;
-    for (int64_t g = (int64_t)blockIdx.x * KF_WARPS + warp; g < rows; g += gstep) {
-        const int c0 = __ldg(surv_cnt + 2 * g), c1 = __ldg(surv_cnt + 2 * g + 1);
+    const uint2* const recs = reinterpret_cast<const uint2*>(surv);      // [row][half][KT_CAP] records {u, tag}
+    int64_t g = (int64_t)blockIdx.x * KF_WARPS + warp;
+    // SET mode keeps the NEXT row's counters and the first 32 records of either half list in registers: one round of loads
+    // issued a whole row ahead, instead of two dependent rounds (counters, then records) at the head of every row -- the
+    // kernel spends its time waiting for exactly these loads.  Slots beyond a list's count hold whatever the workspace
+    // held; they are masked by the counters.
+    int2 pc = make_int2(0, 0);
+    uint2 pr0 = make_uint2(0u, 0u), pr1 = make_uint2(0u, 0u);
+    uint32_t pm = 0u;
+    if (SET && g < rows) {
+        pc = __ldg(reinterpret_cast<const int2*>(surv_cnt) + g);
+        pr0 = __ldg(recs + g * (2 * KT_CAP) + lane);
+        pr1 = __ldg(recs + g * (2 * KT_CAP) + KT_CAP + lane);
+        pm = __ldg(tag + (g / N) * Npad + g % N);
+    }
+    for (; g < rows; g += gstep) {
+        int c0, c1;
+        uint2 r0 = pr0, r1 = pr1;
+        uint32_t mtag = pm;
+        if (SET) {
+            c0 = pc.x;
+            c1 = pc.y;
+            const int64_t gn = g + gstep;
+            if (gn < rows) {
+                pc = __ldg(reinterpret_cast<const int2*>(surv_cnt) + gn);
+                pr0 = __ldg(recs + gn * (2 * KT_CAP) + lane);
+                pr1 = __ldg(recs + gn * (2 * KT_CAP) + KT_CAP + lane);
+                pm = __ldg(tag + (gn / N) * Npad + gn % N);
+            }
+        } else {
+            c0 = __ldg(surv_cnt + 2 * g);
+            c1 = __ldg(surv_cnt + 2 * g + 1);
+        }
         if (c0 < 0 || c1 < 0) continue;              // flagged for the exact repair pass
         const int ns = c0 + c1;
-        const float* su = surv + g * (4 * KT_CAP);   // [half 0: u | tag][half 1: u | tag]
+        const uint2* su = recs + g * (2 * KT_CAP);   // [half 0][half 1]
         const int64_t b = g / N;
         const float* xpb = xp + b * Npad * CPT;
         u64* keys = reinterpret_cast<u64*>(kbuf[warp]);
@@ -487,21 +519,22 @@ knn_finish_kernel(const float* __restrict__ xp, const float* __restrict__ sqnorm
         int kneed = k;                               // ... of which this many complete the set
         int nout = 0;                                // (SET) indices already written
         if (SET) {
-            // ---- classify by the bounds.  Slots: lane, lane + 32 over the concatenation of the two half lists ----
+            // ---- classify by the bounds.  Slots: lane of half list 0, lane of half list 1 ----
             const int r = ns - k;                    // survivors that have to go
-            if (ns <= 64 && r <= 12) {
+            if (c0 <= 32 && c1 <= 32 && r <= KF_RMAX) {
                 float u[2], w[2];
                 uint32_t tg[2], ku[2];
                 float amax = 0.0f;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int e = h * 32 + lane;
+                    const bool live = lane < (h ? c1 : c0);
+                    const uint2 rec = h ? r1 : r0;
                     u[h] = w[h] = INFINITY;
                     tg[h] = 0u;
-                    if (e < ns) {
-                        const float* p = e < c0 ? su + e : su + 2 * KT_CAP + (e - c0);
-                        u[h] = __ldg(p);
-                        tg[h] = __ldg(reinterpret_cast<const uint32_t*>(p) + KT_CAP);
+                    if (live) {
+                        u[h] = __uint_as_float(rec.x);
+                        tg[h] = rec.y;
                         const float a2 = __uint_as_float(tg[h] << 16);
                         w[h] = __fsub_rd(u[h], a2);
                         amax = fmaxf(amax, a2);
@@ -525,14 +558,13 @@ knn_finish_kernel(const float* __restrict__ xp, const float* __restrict__ sqnorm
                 const float U = r > 0 ? kt_ord_val(k1 | 63u) : -INFINITY;
                 amax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(amax)));     // non-negative floats order as integers
                 const float W = __fsub_rd(kt_ord_val(k0 & ~63u), amax);
-                const float m = __uint_as_float(__ldg(tag + b * Npad + (g - b * N)) << 16);
+                const float m = __uint_as_float(mtag << 16);
                 const float Uin = __fadd_ru(U, m), Wout = __fsub_rd(W, m);
                 int nin = 0;
                 nb = 0;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const int e = h * 32 + lane;
-                    const bool live = e < ns;
+                    const bool live = lane < (h ? c1 : c0);
                     const bool in = live && w[h] > Uin;                       // at most k - 1 others can reach it
                     const bool out = live && !in && u[h] < Wout;              // k others certainly beat it
                     const bool band = live && !in && !out;
@@ -547,18 +579,12 @@ knn_finish_kernel(const float* __restrict__ xp, const float* __restrict__ sqnorm
                 kneed = k - nin;
                 __syncwarp();
             } else {
-                for (int e = lane; e < ns; e += 32) {
-                    const float* p = e < c0 ? su + e : su + 2 * KT_CAP + (e - c0);
-                    js[e] = (uint16_t)(__ldg(reinterpret_cast<const uint32_t*>(p) + KT_CAP) >> 16);
-                }
+                for (int e = lane; e < ns; e += 32) js[e] = (uint16_t)(__ldg(&(e < c0 ? su + e : su + KT_CAP + (e - c0))->y) >> 16);
                 __syncwarp();
             }
             if (kneed == 0) continue;
         } else {
-            for (int e = lane; e < ns; e += 32) {
-                const float* p = e < c0 ? su + e : su + 2 * KT_CAP + (e - c0);
-                js[e] = (uint16_t)(__ldg(reinterpret_cast<const uint32_t*>(p) + KT_CAP) >> 16);
-            }
+            for (int e = lane; e < ns; e += 32) js[e] = (uint16_t)(__ldg(&(e < c0 ? su + e : su + KT_CAP + (e - c0))->y) >> 16);
             __syncwarp();
         }
         // the query row itself goes to shared memory (broadcast reads in the chain): holding it in 64 registers per lane
@@ -568,17 +594,25 @@ knn_finish_kernel(const float* __restrict__ xp, const float* __restrict__ sqnorm
         const float xxi = __ldg(sqnorm + g);
         for (int half = 0; half * 32 < nb; ++half) {   // further rounds only for rows with more than 32 candidates
             const int e = half * 32 + lane;
+            const int nbr = nb - half * 32;            // candidates of this round: the first nbr lanes
             const uint32_t j = e < nb ? (uint32_t)js[e] : 0u;
-            float4 t[32 / RPI];
-#pragma unroll
-            for (int it = 0; it < 32 / RPI; ++it) {
-                const uint32_t jj = __shfl_sync(0xffffffffu, j, it * RPI + grp);
-                t[it] = __ldg(reinterpret_cast<const float4*>(xpb + (int64_t)jj * CPT + sub * 4));
-            }
             const float xxj = __ldg(sqnorm + b * N + j);
             __syncwarp();                            // the previous chains are done with the staging tile
+            // gather in groups of KF_GL load instructions (uniform test: groups beyond the round's candidates are skipped;
+            // the band is a handful of candidates for most rows)
 #pragma unroll
-            for (int it = 0; it < 32 / RPI; ++it) *reinterpret_cast<float4*>(stg + (it * RPI + grp) * RS + sub * 4) = t[it];
+            for (int g0 = 0; g0 < 32 / RPI; g0 += KF_GL) {
+                if (g0 * RPI < nbr) {
+                    float4 t[KF_GL];
+#pragma unroll
+                    for (int it = 0; it < KF_GL; ++it) {
+                        const uint32_t jj = __shfl_sync(0xffffffffu, j, (g0 + it) * RPI + grp);
+                        t[it] = __ldg(reinterpret_cast<const float4*>(xpb + (int64_t)jj * CPT + sub * 4));
+                    }
+#pragma unroll
+                    for (int it = 0; it < KF_GL; ++it) *reinterpret_cast<float4*>(stg + ((g0 + it) * RPI + grp) * RS + sub * 4) = t[it];
+                }
+            }
             __syncwarp();
             float dot = 0.0f;
 #pragma unroll
