@@ -460,14 +460,17 @@ knn_tc_kernel(const uint8_t* __restrict__ ops, const float* __restrict__ nh, con
 // arithmetic, and the best (k - #certain) of the band complete the set.  The k indices are written in no particular order.
 // ---------------------------------------------------------------------------------------------------------------
 template <int CPT, int KF_WARPS, bool SET>
-__global__ void __launch_bounds__(KF_WARPS * 32)
+__global__ void __launch_bounds__(KF_WARPS * 32, CPT == 16 ? 5 : (SET ? 7 : 4))
 knn_finish_kernel(const float* __restrict__ xp, const float* __restrict__ sqnorm, const float* __restrict__ surv,
                   const int* __restrict__ surv_cnt, const uint32_t* __restrict__ tag, int N, int Npad, int k, int64_t rows,
                   int32_t* __restrict__ idx_out, float* __restrict__ dist_out) {
     constexpr int RS = CPT + 4;            // padded staging row: conflict-free LDS.128 across lanes
     constexpr int LPR = CPT / 4;           // lanes that fetch one row
     constexpr int RPI = 32 / LPR;          // rows per load instruction
-    __shared__ __align__(16) float stg_all[KF_WARPS][32 * RS];
+    // candidates per round of exact arithmetic (one lane each).  SET mode leaves a handful per row (and none at all for most
+    // rows), so its staging tile is half as high: the kernel waits for loads and lives on the number of resident warps.
+    constexpr int RND = (SET && CPT == 64) ? 16 : 32;
+    __shared__ __align__(16) float stg_all[KF_WARPS][RND * RS];
     __shared__ __align__(16) unsigned long long kbuf[KF_WARPS][KT_SURV];
     __shared__ __align__(16) float xi_all[KF_WARPS][CPT];
     __shared__ uint16_t jbuf[KF_WARPS][KT_SURV];
@@ -592,16 +595,17 @@ knn_finish_kernel(const float* __restrict__ xp, const float* __restrict__ sqnorm
         float* xis = xi_all[warp];
         if (lane < LPR) *reinterpret_cast<float4*>(xis + lane * 4) = __ldg(reinterpret_cast<const float4*>(xpb + (g - b * N) * CPT + lane * 4));
         const float xxi = __ldg(sqnorm + g);
-        for (int half = 0; half * 32 < nb; ++half) {   // further rounds only for rows with more than 32 candidates
-            const int e = half * 32 + lane;
-            const int nbr = nb - half * 32;            // candidates of this round: the first nbr lanes
-            const uint32_t j = e < nb ? (uint32_t)js[e] : 0u;
+        for (int base = 0; base < nb; base += RND) {   // further rounds only for rows with more than RND candidates
+            const int e = base + lane;
+            const int nbr = nb - base;                 // candidates of this round: the first min(nbr, RND) lanes
+            const bool act = lane < RND && e < nb;
+            const uint32_t j = act ? (uint32_t)js[e] : 0u;
             const float xxj = __ldg(sqnorm + b * N + j);
             __syncwarp();                            // the previous chains are done with the staging tile
             // gather in groups of KF_GL load instructions (uniform test: groups beyond the round's candidates are skipped;
             // the band is a handful of candidates for most rows)
 #pragma unroll
-            for (int g0 = 0; g0 < 32 / RPI; g0 += KF_GL) {
+            for (int g0 = 0; g0 < RND / RPI; g0 += KF_GL) {
                 if (g0 * RPI < nbr) {
                     float4 t[KF_GL];
 #pragma unroll
@@ -617,7 +621,7 @@ knn_finish_kernel(const float* __restrict__ xp, const float* __restrict__ sqnorm
             float dot = 0.0f;
 #pragma unroll
             for (int c = 0; c < CPT; c += 4) {
-                const float4 q = *reinterpret_cast<const float4*>(stg + lane * RS + c);
+                const float4 q = *reinterpret_cast<const float4*>(stg + (lane & (RND - 1)) * RS + c);
                 const float4 a = *reinterpret_cast<const float4*>(xis + c);
                 dot = fmaf(a.x, q.x, dot);
                 dot = fmaf(a.y, q.y, dot);
@@ -626,13 +630,13 @@ knn_finish_kernel(const float* __restrict__ xp, const float* __restrict__ sqnorm
             }
             const float d = fmaf(2.0f, dot, -xxi) - xxj;
             // 64-bit key: larger = nearer, equal distances -> smaller index first; 0 = empty slot (below every real key)
-            keys[e] = e < nb ? (((u64)kt_ord_key(d) << 32) | (u64)(~j)) : 0ull;
+            if (lane < RND) keys[e] = act ? (((u64)kt_ord_key(d) << 32) | (u64)(~j)) : 0ull;
         }
         __syncwarp();
         // rank by counting (independent broadcast reads: no dependent shuffle network), keys are all distinct
-        const int nk = (nb + 3) & ~3;                  // slots up to the next multiple of 32 hold 0 = never greater
+        const int nk = (nb + 3) & ~3;                  // slots up to the next multiple of RND hold 0 = never greater
         for (int half = 0; half * 32 < nb; ++half) {
-            const u64 mine = keys[half * 32 + lane];
+            const u64 mine = half * 32 + lane < nb ? keys[half * 32 + lane] : 0ull;
             int rank = 0;
 #pragma unroll 2
             for (int f = 0; f < nk; f += 4) {            // two 16-byte broadcast loads = four keys
@@ -720,11 +724,12 @@ static int kt_launch_finish(const KtPlan& p, uint8_t* ws, const float* sqnorm, i
     const uint32_t* tag = reinterpret_cast<const uint32_t*>(ws + p.off_tag);
     if (p.CPT == 16) {
         const int64_t want = (rows + 7) / 8;
-        const int grid = (int)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
+        const int grid = (int)(want < (int64_t)sms * 5 ? want : (int64_t)sms * 5);        // the resident CTAs, each strides over the rows
         knn_finish_kernel<16, 8, SET><<<grid, 256, 0, st>>>(xp, sqnorm, surv, cnt, tag, N, p.Npad, k, rows, idx_out, dist_out);
     } else {
         const int64_t want = (rows + 3) / 4;
-        const int grid = (int)(want < (int64_t)sms * 16 ? want : (int64_t)sms * 16);
+        const int per_sm = SET ? 7 : 4;
+        const int grid = (int)(want < (int64_t)sms * per_sm ? want : (int64_t)sms * per_sm);
         knn_finish_kernel<64, 4, SET><<<grid, 128, 0, st>>>(xp, sqnorm, surv, cnt, tag, N, p.Npad, k, rows, idx_out, dist_out);
     }
     GFS_LAUNCH_OK("knn_finish_kernel");
