@@ -57,6 +57,7 @@ constexpr int KT_ROWS = 256;          // query rows per CTA
 constexpr int KT_COLS = 64;           // candidates per stage
 constexpr int KT_TST = 4;             // TMEM stages: 2 row tiles x 4 stages x 64 fp32 columns = 512 columns
 constexpr int KT_BST = 4;             // shared-memory stages of the candidate operand
+constexpr int KT_CST = KT_BST + KT_TST;   // slots of the per-candidate constants: loaded with the operand, read after the MMA
 constexpr int KT_SELW = 16;           // selection warps: (row tile, lane quarter, column half)
 constexpr int KT_THREADS = 64 + 32 * KT_SELW;   // warp 0 TMA, warp 1 MMA, warps 2-17 selection
 constexpr int KT_CAP = 128;           // survivor records per (row, column half)
@@ -174,8 +175,8 @@ knn_prep_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int 
 // main kernel
 // ---------------------------------------------------------------------------------------------------------------
 struct KtCtl {
-    float cst[KT_TST][KT_COLS];       // the stage's per-candidate constant: nl_j in pass A, nh_j in pass B
-    uint32_t tag[KT_TST][KT_COLS];    // (j << 16) | bf16(2 a_j)   (pass B only)
+    float cst[KT_CST][KT_COLS];       // the stage's per-candidate constant: nl_j in pass A, nh_j in pass B
+    uint32_t tag[KT_CST][KT_COLS];    // (j << 16) | bf16(2 a_j)   (pass B only)
     uint64_t a_full, b_full[KT_BST], b_empty[KT_BST], d_full[KT_TST], d_empty[KT_TST];
     float* surv_base;
     uint32_t tmem_base;
@@ -257,16 +258,19 @@ knn_tc_kernel(const uint8_t* __restrict__ ops, const float* __restrict__ nh, con
             for (int st = 0; st < 2 * nst; ++st) {
                 const bool passB = st >= nst;
                 const int cs = passB ? st - nst : st;                 // candidate stage
-                const int buf = st % KT_BST, ts = st % KT_TST;
+                const int buf = st % KT_BST, slot = st % KT_CST;
+                // The operand buffer is free once the MMAs of stage st - KT_BST have read it.  Those MMAs had to wait for the
+                // selection warps to hand back the accumulator of stage st - KT_BST - KT_TST, so the constants' slot
+                // (st mod KT_CST, last used by that stage) is free as well: the loads never wait for the selection warps
+                // themselves, only the MMAs do, and the operand is in shared memory by the time an accumulator frees up.
                 mbar_wait(&s.b_empty[buf], ((st / KT_BST) & 1) ^ 1);
-                mbar_wait(&s.d_empty[ts], ((st / KT_TST) & 1) ^ 1);   // the constants' slot is read by the selection warps
                 mbar_arrive_expect_tx(&s.b_full[buf], b_bytes + KT_COLS * (passB ? 8u : 4u));
                 // candidates [cs*64, cs*64+64): half of row tile cs/2, every k-block
                 const uint8_t* src = blk + (int64_t)(cs >> 1) * a_bytes + (cs & 1) * 8192;
                 for (int kb = 0; kb < KB; ++kb)
                     tma_load_1d(sB0 + buf * b_bytes + kb * 8192, src + (int64_t)kb * 16384, 8192u, &s.b_full[buf]);
-                tma_load_1d(s.cst[ts], (passB ? nh : nl) + (int64_t)b * Npad + cs * KT_COLS, KT_COLS * 4u, &s.b_full[buf]);
-                if (passB) tma_load_1d(s.tag[ts], tag + (int64_t)b * Npad + cs * KT_COLS, KT_COLS * 4u, &s.b_full[buf]);
+                tma_load_1d(s.cst[slot], (passB ? nh : nl) + (int64_t)b * Npad + cs * KT_COLS, KT_COLS * 4u, &s.b_full[buf]);
+                if (passB) tma_load_1d(s.tag[slot], tag + (int64_t)b * Npad + cs * KT_COLS, KT_COLS * 4u, &s.b_full[buf]);
             }
         }
         __syncwarp();
@@ -330,7 +334,7 @@ knn_tc_kernel(const uint8_t* __restrict__ ops, const float* __restrict__ nh, con
             tc_fence_after();
             tmem_ld32(tbase + ts * KT_COLS, r);
             tmem_ld_wait32(r);
-            const float* cst = s.cst[ts] + half * 32;
+            const float* cst = s.cst[st % KT_CST] + half * 32;
 #pragma unroll
             for (int c = 0; c < 32; c += 4) {
                 const float4 l4 = *reinterpret_cast<const float4*>(cst + c);
@@ -403,8 +407,8 @@ knn_tc_kernel(const uint8_t* __restrict__ ops, const float* __restrict__ nh, con
                 ovf = true;
                 thr = INFINITY;
             }
-            const float* cst = s.cst[ts] + half * 32;
-            const uint32_t* tgs = s.tag[ts] + half * 32;
+            const float* cst = s.cst[st % KT_CST] + half * 32;
+            const uint32_t* tgs = s.tag[st % KT_CST] + half * 32;
             uint32_t m0 = 0u, m1 = 0u;                            // two chains: even / odd pairs
 #pragma unroll
             for (int c = 0; c < 32; c += 4) {
