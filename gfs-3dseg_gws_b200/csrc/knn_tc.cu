@@ -57,6 +57,7 @@ constexpr int KT_ROWS = 256;          // query rows per CTA
 constexpr int KT_COLS = 64;           // candidates per stage
 constexpr int KT_TST = 4;             // TMEM stages: 2 row tiles x 4 stages x 64 fp32 columns = 512 columns
 constexpr int KT_BST = 4;             // shared-memory stages of the candidate operand
+constexpr int KT_ATMEM_DEFAULT = 1;   // query operand of the filter MMAs: 0 = shared memory, 1 = tensor memory
 constexpr int KT_CST = KT_BST + KT_TST;   // slots of the per-candidate constants: loaded with the operand, read after the MMA
 constexpr int KT_SELW = 16;           // selection warps: (row tile, lane quarter, column half)
 constexpr int KT_THREADS = 64 + 32 * KT_SELW;   // warp 0 TMA, warp 1 MMA, warps 2-17 selection
@@ -208,7 +209,11 @@ __device__ __forceinline__ void kt_sort_desc(float (&a)[NG]) {
     }
 }
 
-template <int NG, int KS>
+// ATM: the query operand is copied into tensor memory once per CTA (tcgen05.cp, 64 columns per row tile) and every MMA
+// reads it from there: the shared-memory pipe then carries only the candidate operand (2 KB per MMA instead of 6 KB).  At
+// C = 64 that pipe is what the kernel runs out of (ncu: tensor-core wavefronts 56 % + LSU wavefronts 29 % of its peak).
+// The accumulators keep 384 of the 512 columns: three stages per row tile instead of four.
+template <int NG, int KS, bool ATM>
 __global__ void __launch_bounds__(KT_THREADS, 1)
 knn_tc_kernel(const uint8_t* __restrict__ ops, const float* __restrict__ nh, const float* __restrict__ nl,
               const uint32_t* __restrict__ tag, int* __restrict__ flags, int N, int Npad, int Cp16, int KB, int k,
@@ -223,6 +228,9 @@ knn_tc_kernel(const uint8_t* __restrict__ ops, const float* __restrict__ nh, con
     float4* xch = reinterpret_cast<float4*>(sB0 + KT_BST * b_bytes);
     KtCtl& s = *reinterpret_cast<KtCtl*>(reinterpret_cast<unsigned char*>(xch) + 2 * (NG / 4) * KT_ROWS * 16);
 
+    constexpr int TST = ATM ? 3 : KT_TST;             // accumulator stages per row tile
+    constexpr uint32_t D0 = ATM ? 128u : 0u;          // first accumulator column (ATM: [A tile 0: 64][A tile 1: 64][D ...])
+    constexpr uint32_t DT = TST * KT_COLS;            // accumulator columns per row tile
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.y, q0 = blockIdx.x * KT_ROWS;
     const int nst = Npad / KT_COLS;
@@ -285,9 +293,23 @@ knn_tc_kernel(const uint8_t* __restrict__ ops, const float* __restrict__ nh, con
         const uint64_t a0 = umma_desc_sw128(smem_u32(sA));
         const uint64_t b0 = umma_desc_sw128(smem_u32(sB0));
         const uint32_t a_step = a_bytes >> 4, b_step = b_bytes >> 4;     // descriptor address units (16 bytes)
+        if (ATM) {
+            // the query operand [h | l] of both row tiles -> tensor memory, 16 columns (8 TMEM columns) per copy
+            if (elect_one()) {
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int q = 0; q < 2 * KS; ++q) {
+                        const int c16 = q * 16;
+                        const uint32_t oa = (uint32_t)((c16 >> 6) * 16384 + (c16 & 63) * 2) >> 4;
+                        tmem_cp_128x256b(tmem + mt * 64 + q * 8, a0 + (uint64_t)(mt * a_step) + oa);
+                    }
+            }
+            __syncwarp();
+        }
         for (int st = 0; st < 2 * nst; ++st) {
-            const int buf = st % KT_BST, ts = st % KT_TST;
-            mbar_wait(&s.d_empty[ts], ((st / KT_TST) & 1) ^ 1);
+            const int buf = st % KT_BST, ts = st % TST;
+            mbar_wait(&s.d_empty[ts], ((st / TST) & 1) ^ 1);
             mbar_wait(&s.b_full[buf], (st / KT_BST) & 1);
             tc_fence_after();
             if (elect_one()) {
@@ -295,16 +317,23 @@ knn_tc_kernel(const uint8_t* __restrict__ ops, const float* __restrict__ nh, con
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt) {
                     const uint64_t aB = a0 + (uint64_t)(mt * a_step);
-                    const uint32_t d = tmem + mt * 256 + ts * KT_COLS;
+                    const uint32_t d = tmem + D0 + mt * DT + ts * KT_COLS;
 #pragma unroll
                     for (int ks = 0; ks < KS; ++ks) {
                         const int ch = ks * 16, cl = CP16 + ks * 16;
                         // offset of a 16-column slice inside the operand: k-block (16 KiB / 8 KiB apart) + 32 bytes per k-step
                         const uint32_t oah = (uint32_t)((ch >> 6) * 16384 + (ch & 63) * 2) >> 4, oal = (uint32_t)((cl >> 6) * 16384 + (cl & 63) * 2) >> 4;
                         const uint32_t obh = (uint32_t)((ch >> 6) * 8192 + (ch & 63) * 2) >> 4, obl = (uint32_t)((cl >> 6) * 8192 + (cl & 63) * 2) >> 4;
-                        umma_bf16(d, aB + oah, bB + obh, idesc, ks ? 1u : 0u);
-                        umma_bf16(d, aB + oah, bB + obl, idesc, 1u);
-                        umma_bf16(d, aB + oal, bB + obh, idesc, 1u);
+                        if (ATM) {
+                            const uint32_t ah = tmem + mt * 64 + ks * 8, al = tmem + mt * 64 + (KS + ks) * 8;
+                            umma_bf16_ts(d, ah, bB + obh, idesc, ks ? 1u : 0u);
+                            umma_bf16_ts(d, ah, bB + obl, idesc, 1u);
+                            umma_bf16_ts(d, al, bB + obh, idesc, 1u);
+                        } else {
+                            umma_bf16(d, aB + oah, bB + obh, idesc, ks ? 1u : 0u);
+                            umma_bf16(d, aB + oah, bB + obl, idesc, 1u);
+                            umma_bf16(d, aB + oal, bB + obh, idesc, 1u);
+                        }
                     }
                 }
                 umma_commit(&s.b_empty[buf]);
@@ -321,7 +350,7 @@ knn_tc_kernel(const uint8_t* __restrict__ ops, const float* __restrict__ nh, con
         const int row = mt * 128 + quarter * 32 + lane;
         const int n = q0 + row;
         const bool valid = n < N;
-        const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16) + mt * 256 + half * 32;
+        const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16) + D0 + mt * DT + half * 32;
         uint32_t r[32];
 
         // ---------------- pass A: running maxima of the lower bounds, one group per column position ----------------
@@ -329,8 +358,8 @@ knn_tc_kernel(const uint8_t* __restrict__ ops, const float* __restrict__ nh, con
 #pragma unroll
         for (int i = 0; i < NG; ++i) gm[i] = -INFINITY;
         for (int st = 0; st < nst; ++st) {
-            const int ts = st % KT_TST;
-            mbar_wait(&s.d_full[ts], (st / KT_TST) & 1);
+            const int ts = st % TST;
+            mbar_wait(&s.d_full[ts], (st / TST) & 1);
             tc_fence_after();
             tmem_ld32(tbase + ts * KT_COLS, r);
             tmem_ld_wait32(r);
@@ -398,8 +427,8 @@ knn_tc_kernel(const uint8_t* __restrict__ ops, const float* __restrict__ nh, con
         float4* const stg = xch + (tid - 64);                     // float4 q of this thread's chunk lives at stg[q * 512]
         const float* const stgf = reinterpret_cast<const float*>(stg);
         for (int st = nst; st < 2 * nst; ++st) {
-            const int ts = st % KT_TST;
-            mbar_wait(&s.d_full[ts], (st / KT_TST) & 1);
+            const int ts = st % TST;
+            mbar_wait(&s.d_full[ts], (st / TST) & 1);
             tc_fence_after();
             tmem_ld32(tbase + ts * KT_COLS, r);
             tmem_ld_wait32(r);
@@ -695,11 +724,20 @@ static KtPlan kt_plan(int B, int C, int N) {
 int knn_exact_flagged(const float* x, int64_t x_bstride, int B, int C, int N, int k, const float* sqnorm, const int* flags,
                       int32_t* idx_out, float* dist_out, cudaStream_t st);
 
-template <int NG, int KS>
+static int g_kt_atmem = -1;            // -1: read GFS3D_KNN_ATMEM on first use; 0 / 1: query operand in shared / tensor memory
+static bool kt_atmem() {
+    if (g_kt_atmem < 0) {
+        const char* e = getenv("GFS3D_KNN_ATMEM");
+        g_kt_atmem = e ? (atoi(e) != 0) : KT_ATMEM_DEFAULT;
+    }
+    return g_kt_atmem != 0;
+}
+
+template <int NG, int KS, bool ATM>
 static int kt_launch_filter_ks(const KtPlan& p, uint8_t* ws, int B, int N, int k, float* dbg, cudaStream_t st) {
     const size_t smem = (size_t)2 * p.KB * 16384 + (size_t)KT_BST * p.KB * 8192 + (size_t)2 * (NG / 4) * KT_ROWS * 16 + sizeof(KtCtl) + 1024;
-    GFS_CUDA_OK(allow_smem(reinterpret_cast<const void*>(knn_tc_kernel<NG, KS>), smem));
-    knn_tc_kernel<NG, KS><<<dim3(p.Npad / KT_ROWS, B), KT_THREADS, smem, st>>>(
+    GFS_CUDA_OK(allow_smem(reinterpret_cast<const void*>(knn_tc_kernel<NG, KS, ATM>), smem));
+    knn_tc_kernel<NG, KS, ATM><<<dim3(p.Npad / KT_ROWS, B), KT_THREADS, smem, st>>>(
         ws, reinterpret_cast<const float*>(ws + p.off_nh), reinterpret_cast<const float*>(ws + p.off_nl),
         reinterpret_cast<const uint32_t*>(ws + p.off_tag), reinterpret_cast<int*>(ws + p.off_flags), N, p.Npad, p.Cp16, p.KB, k,
         reinterpret_cast<float*>(ws + p.off_surv), reinterpret_cast<int*>(ws + p.off_cnt), dbg);
@@ -708,11 +746,19 @@ static int kt_launch_filter_ks(const KtPlan& p, uint8_t* ws, int B, int N, int k
 }
 template <int NG>
 static int kt_launch_filter(const KtPlan& p, uint8_t* ws, int B, int N, int k, float* dbg, cudaStream_t st) {
+    if (kt_atmem()) {
+        switch (p.Cp16 >> 4) {
+            case 1: return kt_launch_filter_ks<NG, 1, true>(p, ws, B, N, k, dbg, st);
+            case 2: return kt_launch_filter_ks<NG, 2, true>(p, ws, B, N, k, dbg, st);
+            case 3: return kt_launch_filter_ks<NG, 3, true>(p, ws, B, N, k, dbg, st);
+            default: return kt_launch_filter_ks<NG, 4, true>(p, ws, B, N, k, dbg, st);
+        }
+    }
     switch (p.Cp16 >> 4) {
-        case 1: return kt_launch_filter_ks<NG, 1>(p, ws, B, N, k, dbg, st);
-        case 2: return kt_launch_filter_ks<NG, 2>(p, ws, B, N, k, dbg, st);
-        case 3: return kt_launch_filter_ks<NG, 3>(p, ws, B, N, k, dbg, st);
-        default: return kt_launch_filter_ks<NG, 4>(p, ws, B, N, k, dbg, st);
+        case 1: return kt_launch_filter_ks<NG, 1, false>(p, ws, B, N, k, dbg, st);
+        case 2: return kt_launch_filter_ks<NG, 2, false>(p, ws, B, N, k, dbg, st);
+        case 3: return kt_launch_filter_ks<NG, 3, false>(p, ws, B, N, k, dbg, st);
+        default: return kt_launch_filter_ks<NG, 4, false>(p, ws, B, N, k, dbg, st);
     }
 }
 
