@@ -79,20 +79,24 @@ __device__ __forceinline__ float kt_ord_val(uint32_t u) {
 // ---------------------------------------------------------------------------------------------------------------
 // operand preparation
 // ---------------------------------------------------------------------------------------------------------------
-// One CTA per 128 points.  The (C x 128) slab is staged in shared memory with coalesced loads; thread t then owns point t
-// for the two norm chains, and the operand tiles / the point-major copy are written with (row, 16-byte chunk) work items
-// so that consecutive threads write consecutive bytes.
-constexpr int KP_LD = 129;   // padded row of the staged slab
-constexpr int KP_THREADS = 256;   // 128 points per CTA, two threads per point for the loads / stores (the kernel is latency bound)
+// One CTA per 64 points (half a 128-row operand tile): 16 CTAs of 128 threads per block of 1024 points keep far more loads
+// in flight than one CTA per tile did (the kernel is latency bound: it reads C x N floats per block once and writes the
+// operand tiles, the point-major copy and four small per-point arrays).  The (C x 64) slab is staged in shared memory with
+// coalesced loads; thread t < 64 then owns point t for the norm chains, and the operand tiles / the point-major copy are
+// written with (row, 16-byte chunk) work items so that consecutive threads write consecutive bytes.
+constexpr int KP_PTS = 64;        // points per CTA
+constexpr int KP_LD = 65;         // padded row of the staged slab
+constexpr int KP_THREADS = 128;
 __global__ void __launch_bounds__(KP_THREADS)
 knn_prep_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int Npad, int Cp16, int KB, int CPT,
                 uint8_t* __restrict__ ops, float* __restrict__ xp, float* __restrict__ nh, float* __restrict__ nl,
                 uint32_t* __restrict__ tag, float* __restrict__ sqnorm) {
     __shared__ float xs[64 * KP_LD];
     __shared__ float mus[64];
-    const int t = threadIdx.x, rt = blockIdx.x, b = blockIdx.y;
-    const int n0 = rt * 128, n = n0 + t;
-    const bool valid = n < N;
+    const int t = threadIdx.x, b = blockIdx.y;
+    const int rt = blockIdx.x >> 1, roff = (blockIdx.x & 1) * KP_PTS;      // operand tile, first row inside it
+    const int n0 = blockIdx.x * KP_PTS, n = n0 + t;
+    const bool valid = t < KP_PTS && n < N;
     const float* xb = x + (int64_t)b * bstride;
     // the shift: any vector is valid (distances are translation invariant), it only has to be the SAME for every point of
     // the block and close to the data.  The mean of four spread-out points costs four loads and no extra kernel.
@@ -100,13 +104,13 @@ knn_prep_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int 
         const float* p = xb + (int64_t)t * N;
         mus[t] = t < C ? 0.25f * ((__ldg(p) + __ldg(p + N / 4)) + (__ldg(p + N / 2) + __ldg(p + 3 * (N / 4)))) : 0.0f;
     }
-    for (int i = t; i < Cp16 * 128; i += KP_THREADS) {
-        const int c = i >> 7, r = i & 127;
+    for (int i = t; i < Cp16 * KP_PTS; i += KP_THREADS) {
+        const int c = i >> 6, r = i & 63;
         xs[c * KP_LD + r] = (n0 + r < N && c < C) ? __ldg(xb + (int64_t)c * N + n0 + r) : 0.0f;
     }
     __syncthreads();
 
-    if (t < 128) {
+    if (t < KP_PTS) {
     float xx = 0.0f, cc = 0.0f, aw = 0.0f;
     double xd = 0.0;
     for (int c = 0; c < C; ++c) {
@@ -138,7 +142,7 @@ knn_prep_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int 
     // operand tiles: columns [h: 0..Cp16) [l: Cp16..2 Cp16), 8 columns per 16-byte chunk
     uint8_t* tiles = ops + ((int64_t)b * (Npad / 128) + rt) * KB * 16384;
     const int cpr = Cp16 >> 3;               // chunks per row and per part
-    for (int i = t; i < 128 * cpr; i += KP_THREADS) {
+    for (int i = t; i < KP_PTS * cpr; i += KP_THREADS) {
         const int r = i / cpr, q = i - r * cpr;
         const bool on = n0 + r < N;
         uint32_t hp[4], lp[4];
@@ -155,13 +159,13 @@ knn_prep_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int 
             lp[e] = pack_bf16x2(u0 - __bfloat162float(h0), u1 - __bfloat162float(h1));
         }
         const int ch = q * 8, cl = Cp16 + q * 8;
-        *reinterpret_cast<uint4*>(tiles + (ch >> 6) * 16384 + sw128(r, (ch & 63) >> 3)) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-        *reinterpret_cast<uint4*>(tiles + (cl >> 6) * 16384 + sw128(r, (cl & 63) >> 3)) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+        *reinterpret_cast<uint4*>(tiles + (ch >> 6) * 16384 + sw128(roff + r, (ch & 63) >> 3)) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+        *reinterpret_cast<uint4*>(tiles + (cl >> 6) * 16384 + sw128(roff + r, (cl & 63) >> 3)) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
     }
     // point-major fp32 copy of the ORIGINAL coordinates, rows of CPT floats (zero padded)
     float* xrows = xp + ((int64_t)b * Npad + n0) * CPT;
     const int fpr = CPT >> 2;
-    for (int i = t; i < 128 * fpr; i += KP_THREADS) {
+    for (int i = t; i < KP_PTS * fpr; i += KP_THREADS) {
         const int r = i / fpr, q = i - r * fpr;
         float4 o;
         o.x = 4 * q < Cp16 ? xs[(4 * q) * KP_LD + r] : 0.0f;
@@ -795,7 +799,7 @@ static int kt_chain(const float* x, int64_t x_bstride, int B, int C, int N, int 
                     float* dist_out, float* dbg, bool set_only, cudaStream_t st) {
     const KtPlan p = kt_plan(B, C, N);
     GFS_CUDA_OK(cudaMemsetAsync(ws + p.off_flags, 0, p.zero_bytes, st));
-    knn_prep_kernel<<<dim3(p.Npad / 128, B), KP_THREADS, 0, st>>>(x, x_bstride, C, N, p.Npad, p.Cp16, p.KB, p.CPT, ws,
+    knn_prep_kernel<<<dim3(p.Npad / KP_PTS, B), KP_THREADS, 0, st>>>(x, x_bstride, C, N, p.Npad, p.Cp16, p.KB, p.CPT, ws,
                                                            reinterpret_cast<float*>(ws + p.off_xp),
                                                            reinterpret_cast<float*>(ws + p.off_nh),
                                                            reinterpret_cast<float*>(ws + p.off_nl),

@@ -33,9 +33,12 @@ if os.path.exists(fn):
     hdr, data = rows[0], rows[1:]
     iN, iV = hdr.index("Kernel Name"), hdr.index("Metric Value")
     seq = [(r[iN], float(r[iV]) / 1000.0) for r in data]
-    starts = [i for i, (n, _) in enumerate(seq) if "sqnorm_kernel" in n or "knn_prep_kernel" in n]
-    if len(starts) >= 4:
-        step = seq[starts[0]:starts[3]]
+    # a step starts with the first kNN preparation launch that follows the head's last kernel (the second cos_logits launch)
+    # and runs up to the next such launch; a kNN call is one chain of launches or two (gfs_knn_tc_chains)
+    starts = [i for i, (n, _) in enumerate(seq)
+              if ("sqnorm_kernel" in n or "knn_prep_kernel" in n) and i > 0 and not any(t in seq[i - 1][0] for t in ("knn_", "edgeconv", "edge_pq", "sqnorm"))]
+    if len(starts) >= 2:
+        step = seq[starts[0]:starts[1]]
         tot = sum(t for _, t in step)
         agg = collections.OrderedDict()
         for n, t in step:
@@ -142,11 +145,11 @@ for kname in ("knn_prep_kernel", "knn_tc_kernel", "knn_finish_kernel"):
         v = float(v.replace(",", ""))
         return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
     ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
-    traffic[kname] = [[to_bytes(r[ir], units[ir]), to_bytes(r[iw], units[iw])] for r in rows[2:5]]
-if len(traffic) == 3 and all(len(v) == 3 for v in traffic.values()):
+    traffic[kname] = [[to_bytes(r[ir], units[ir]), to_bytes(r[iw], units[iw])] for r in rows[2:] if len(r) > max(ir, iw)]
+if len(traffic) == 3 and all(len(v) in (3, 6) for v in traffic.values()):
     total = sum(a + b for v in traffic.values() for a, b in v)
     json.dump({"source": f"profiles/{R}_summary.md (ncu --set full): dram__bytes_read.sum + dram__bytes_write.sum of the three launches "
-                         "(layers 1-3) of knn_prep_kernel, knn_tc_kernel and knn_finish_kernel of one step at batch 32",
+                         "(layers 1-3, one or two chains per layer) of knn_prep_kernel, knn_tc_kernel and knn_finish_kernel of one step at batch 32",
                "per_launch_bytes_read_write": traffic, "knn_bytes_per_step_b32": total},
               open(os.path.join(P, "ncu_traffic.json"), "w"), indent=1)
     out.append(f"\nkNN graph dram traffic per step (batch 32): {total / 1e6:.1f} MB "
