@@ -1,6 +1,7 @@
 // api.cu -- error plumbing and small utilities of the C ABI (include/gfs3d.h).
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <map>
 #include <set>
@@ -32,6 +33,23 @@ int sm_count() {
     return cached[dev];
 }
 
+static int g_pdl = -1;   // -1: read GFS3D_PDL on first use
+bool pdl_enabled(int cls) {
+    if (g_pdl < 0) {
+        const char* e = getenv("GFS3D_PDL");
+        g_pdl = e ? (atoi(e) & 3) : 3;
+    }
+    return (g_pdl & cls) != 0;
+}
+
+static thread_local bool g_pdl_break = false;
+void pdl_break() { g_pdl_break = true; }
+bool pdl_take_break() {
+    const bool b = g_pdl_break;
+    g_pdl_break = false;
+    return b;
+}
+
 cudaError_t allow_smem(const void* func, size_t bytes) {
     static std::mutex mu;
     static std::map<std::pair<int, const void*>, size_t> done;   // largest size granted so far
@@ -51,3 +69,7 @@ cudaError_t allow_smem(const void* func, size_t bytes) {
 extern "C" int gfs_version(void) { return 100; }
 extern "C" const char* gfs_last_error_string(void) { return gfs::g_err; }
 extern "C" int gfs_device_sm_count(void) { return gfs::sm_count(); }
+extern "C" int gfs_set_pdl(int on) {
+    gfs::g_pdl = on & 3;
+    return GFS_OK;
+}

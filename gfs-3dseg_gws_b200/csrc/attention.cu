@@ -51,6 +51,7 @@ __device__ __forceinline__ float ex2(float x) {
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attention_kernel(const uint8_t* __restrict__ qkv, int kblocks, int kb_q, int tiles_per_block, int n_items, float scale_log2,
                  int N, float* __restrict__ y_cm, int64_t y_bstride, uint8_t* __restrict__ y_act, int y_kblocks, int y_kb) {
+    pdl_enter();
     extern __shared__ unsigned char smem_raw[];
     // align inside the shared window with pointer arithmetic on smem_raw (keeps the .shared address space: LDS/STS, not generic LD/ST)
     AtSmem& s = *reinterpret_cast<AtSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
@@ -301,7 +302,7 @@ extern "C" int gfs_attention_fwd(const void* qkv_act, int kblocks, int kb_q, int
     GFS_REQUIRE(sms > 0, GFS_ERR_CUDA, "gfs_attention_fwd: cannot query the device");
     const size_t smem = sizeof(AtSmem) + 1024;
     GFS_CUDA_OK(allow_smem(reinterpret_cast<const void*>(attention_kernel), smem));
-    attention_kernel<<<items < sms ? items : sms, AT_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
+    launch_pdl(attention_kernel, dim3((unsigned)(items < sms ? items : sms)), dim3(AT_THREADS), smem, static_cast<cudaStream_t>(stream),
         static_cast<const uint8_t*>(qkv_act), kblocks, kb_q, T, items, scale * 1.4426950408889634f, N, y_cm, y_bstride,
         static_cast<uint8_t*>(y_act), y_kblocks, y_kb);
     GFS_LAUNCH_OK("attention_kernel");

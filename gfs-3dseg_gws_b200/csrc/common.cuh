@@ -31,6 +31,36 @@ int fail(int code, const char* fmt, ...);   // records the thread-local error st
     } while (0)
 
 int sm_count();
+
+// Programmatic dependent launch.  A kernel launched through launch_pdl may be scheduled while the kernel before it on the
+// stream is still draining: its CTAs become resident as the predecessor's CTAs retire and block in pdl_enter() -- the first
+// statement of every such kernel -- until the predecessor has completed and its writes are visible.  What overlaps is the
+// launch latency and the CTA ramp-up, not any work (pdl_enter comes before every allocation of tensor memory, so a waiting
+// CTA never holds a resource a predecessor CTA on the same SM still needs).  Without the launch attribute pdl_enter is a
+// no-op.  Kernels of the kNN chains (class 2) run two chains side by side on two streams and are sized to fill each other's
+// idle SMs: there only the short preparation kernel releases its dependents early (pdl_enter); the filter and the finish
+// just wait (pdl_wait), so their dependents are launched when their last CTA exits and never sit on SMs the other chain
+// could use.  GFS3D_PDL / gfs_set_pdl: bit 0 = the single-stream kernels, bit 1 = the kNN chains (default 3, 0 = off).
+bool pdl_enabled(int cls);
+// The next launch_pdl of this host thread is an ordinary launch: called after a cross-stream join (cudaStreamWaitEvent), so
+// that a kernel whose predecessors are a kernel of this stream AND an event of another stream keeps full dependencies only.
+void pdl_break();
+bool pdl_take_break();
+template <int CLS = 1, typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    const bool brk = pdl_take_break();
+    cfg.numAttrs = (pdl_enabled(CLS) && !brk) ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // a failure is picked up by GFS_LAUNCH_OK
+}
 // opt a kernel in to > 48 KB dynamic shared memory (cached per device)
 cudaError_t allow_smem(const void* func, size_t bytes);
 
@@ -45,6 +75,15 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 __host__ __device__ __forceinline__ uint32_t sw128(uint32_t r, uint32_t q) {
     return r * 128u + (((q ^ (r & 7u)) & 7u) << 4);
 }
+
+// first statement of a kernel launched with launch_pdl (see there)
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
+}
+
+// same without releasing the dependents early: they are launched when this grid's last CTA exits
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
 
 // ---- cp.async (LDGSTS) ----
 __device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_bytes) {

@@ -44,6 +44,7 @@ edgeconv_kernel(const uint8_t* __restrict__ pb, const float* __restrict__ qv, co
                 const float* __restrict__ shift2, int N, int k, int64_t M, int ntiles, float* __restrict__ y_cm,
                 int64_t y_bstride, uint8_t* __restrict__ y_act, int act_kblocks, int act_kb, uint8_t* __restrict__ y_act2,
                 int act2_kblocks, int act2_kb, uint8_t* __restrict__ argmax) {
+    pdl_enter();
     extern __shared__ unsigned char smem_raw[];
     // align inside the shared window with pointer arithmetic on smem_raw (keeps the .shared address space: LDS/STS, not generic LD/ST)
     EcSmem& s = *reinterpret_cast<EcSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
@@ -304,14 +305,14 @@ extern "C" int gfs_edgeconv_fwd(const void* pb, const float* q, const int32_t* i
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (argmax) {
         GFS_CUDA_OK(allow_smem(reinterpret_cast<const void*>(edgeconv_kernel<true>), EC_MAX_SMEM));
-        edgeconv_kernel<true><<<grid, EC_THREADS, smem, st>>>(
-            static_cast<const uint8_t*>(pb), q, idx, static_cast<const uint8_t*>(w2_packed), shift2, N, k, M, ntiles, y_cm, y_bstride,
+        launch_pdl(edgeconv_kernel<true>, grid, dim3(EC_THREADS), smem, st,
+        static_cast<const uint8_t*>(pb), q, idx, static_cast<const uint8_t*>(w2_packed), shift2, N, k, M, ntiles, y_cm, y_bstride,
             static_cast<uint8_t*>(y_act), y_act_kblocks, y_act_kb, static_cast<uint8_t*>(y_act2), y_act2_kblocks, y_act2_kb,
             argmax);
     } else {
         GFS_CUDA_OK(allow_smem(reinterpret_cast<const void*>(edgeconv_kernel<false>), EC_MAX_SMEM));
-        edgeconv_kernel<false><<<grid, EC_THREADS, smem, st>>>(
-            static_cast<const uint8_t*>(pb), q, idx, static_cast<const uint8_t*>(w2_packed), shift2, N, k, M, ntiles, y_cm, y_bstride,
+        launch_pdl(edgeconv_kernel<false>, grid, dim3(EC_THREADS), smem, st,
+        static_cast<const uint8_t*>(pb), q, idx, static_cast<const uint8_t*>(w2_packed), shift2, N, k, M, ntiles, y_cm, y_bstride,
             static_cast<uint8_t*>(y_act), y_act_kblocks, y_act_kb, static_cast<uint8_t*>(y_act2), y_act2_kblocks, y_act2_kb,
             nullptr);
     }

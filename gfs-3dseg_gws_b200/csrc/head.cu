@@ -22,6 +22,7 @@ __global__ void __launch_bounds__(128)
 cos_logits_kernel(const float* __restrict__ feat, int64_t bstride, int D, int N, const float* __restrict__ proto, int PB, int CLS,
                   const float* __restrict__ coding, int G, const int32_t* __restrict__ assignment, float th,
                   float* __restrict__ logits) {
+    pdl_enter();
     extern __shared__ __align__(16) float sp[];   // [D][CP]: the CLS prototype values of one channel are CP/4 broadcast LDS.128
     const int b = blockIdx.y;
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -86,6 +87,7 @@ cos_logits_kernel(const float* __restrict__ feat, int64_t bstride, int D, int N,
 // max and sum-exp over the points of one (block, class) row
 __global__ void __launch_bounds__(256)
 softmax_stats_kernel(const float* __restrict__ logits, int N, float* __restrict__ stats) {
+    pdl_enter();
     __shared__ float red[8];
     const float* row = logits + (int64_t)blockIdx.x * N;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -120,6 +122,7 @@ template <int CP>                    // classes padded to 16 / 24 / 32 (see cos_
 __global__ void __launch_bounds__(128)
 softmax_pool_kernel(const float* __restrict__ logits, const float* __restrict__ stats, const float* __restrict__ feat,
                     int64_t bstride, int CLS, int D, int N, int nchunks, float* __restrict__ partial) {
+    pdl_enter();
     extern __shared__ __align__(16) float sm[];
     float* P = sm;                       // [SP_CH][CP]: the CLS probabilities of one point are CP/4 broadcast LDS.128
     float* F = sm + CP * SP_CH;          // [D][SP_LD]
@@ -181,6 +184,7 @@ softmax_pool_kernel(const float* __restrict__ logits, const float* __restrict__ 
 
 __global__ void softmax_pool_reduce_kernel(const float* __restrict__ partial, int nchunks, int CD, int64_t total,
                                            float* __restrict__ out) {
+    pdl_enter();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int64_t b = i / CD, r = i - b * CD;
@@ -196,6 +200,7 @@ __global__ void softmax_pool_reduce_kernel(const float* __restrict__ partial, in
 __global__ void __launch_bounds__(128)
 refine_proto_kernel(const float* __restrict__ pred_proto, const float* __restrict__ proto, const float* __restrict__ gened,
                     int rows, int CLS, int D, int base_num, float* __restrict__ out) {
+    pdl_enter();
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -251,11 +256,14 @@ extern "C" int gfs_cos_logits(const float* feat, int64_t feat_bstride, int B, in
     const dim3 grid((N + 127) / 128, B);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (CP == 16)
-        cos_logits_kernel<16><<<grid, 128, smem, st>>>(feat, feat_bstride, D, N, proto_l2, PB, CLS, coding, G, assignment, th, logits);
+        launch_pdl(cos_logits_kernel<16>, grid, dim3(128), smem, st,
+        feat, feat_bstride, D, N, proto_l2, PB, CLS, coding, G, assignment, th, logits);
     else if (CP == 24)
-        cos_logits_kernel<24><<<grid, 128, smem, st>>>(feat, feat_bstride, D, N, proto_l2, PB, CLS, coding, G, assignment, th, logits);
+        launch_pdl(cos_logits_kernel<24>, grid, dim3(128), smem, st,
+        feat, feat_bstride, D, N, proto_l2, PB, CLS, coding, G, assignment, th, logits);
     else
-        cos_logits_kernel<32><<<grid, 128, smem, st>>>(feat, feat_bstride, D, N, proto_l2, PB, CLS, coding, G, assignment, th, logits);
+        launch_pdl(cos_logits_kernel<32>, grid, dim3(128), smem, st,
+        feat, feat_bstride, D, N, proto_l2, PB, CLS, coding, G, assignment, th, logits);
     GFS_LAUNCH_OK("cos_logits_kernel");
     return GFS_OK;
 }
@@ -271,22 +279,27 @@ extern "C" int gfs_softmax_pool(const float* logits, const float* feat, int64_t 
     GFS_REQUIRE(smem <= 200 * 1024, GFS_ERR_UNSUPPORTED, "gfs_softmax_pool: D=%d too large", D);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int nchunks = (N + SP_CH - 1) / SP_CH;
-    softmax_stats_kernel<<<B * CLS, 256, 0, st>>>(logits, N, stats);
+    launch_pdl(softmax_stats_kernel, dim3((unsigned)(B * CLS)), dim3(256), 0, st,
+        logits, N, stats);
     GFS_LAUNCH_OK("softmax_stats_kernel");
     const dim3 grid(nchunks, B);
     if (CP == 16) {
         GFS_CUDA_OK(allow_smem(reinterpret_cast<const void*>(softmax_pool_kernel<16>), 200 * 1024));
-        softmax_pool_kernel<16><<<grid, 128, smem, st>>>(logits, stats, feat, feat_bstride, CLS, D, N, nchunks, partial);
+        launch_pdl(softmax_pool_kernel<16>, grid, dim3(128), smem, st,
+        logits, stats, feat, feat_bstride, CLS, D, N, nchunks, partial);
     } else if (CP == 24) {
         GFS_CUDA_OK(allow_smem(reinterpret_cast<const void*>(softmax_pool_kernel<24>), 200 * 1024));
-        softmax_pool_kernel<24><<<grid, 128, smem, st>>>(logits, stats, feat, feat_bstride, CLS, D, N, nchunks, partial);
+        launch_pdl(softmax_pool_kernel<24>, grid, dim3(128), smem, st,
+        logits, stats, feat, feat_bstride, CLS, D, N, nchunks, partial);
     } else {
         GFS_CUDA_OK(allow_smem(reinterpret_cast<const void*>(softmax_pool_kernel<32>), 200 * 1024));
-        softmax_pool_kernel<32><<<grid, 128, smem, st>>>(logits, stats, feat, feat_bstride, CLS, D, N, nchunks, partial);
+        launch_pdl(softmax_pool_kernel<32>, grid, dim3(128), smem, st,
+        logits, stats, feat, feat_bstride, CLS, D, N, nchunks, partial);
     }
     GFS_LAUNCH_OK("softmax_pool_kernel");
     const int64_t total = (int64_t)B * CLS * D;
-    softmax_pool_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(partial, nchunks, CLS * D, total, pred_proto);
+    launch_pdl(softmax_pool_reduce_kernel, dim3((unsigned)((unsigned)((total + 255) / 256))), dim3(256), 0, st,
+        partial, nchunks, CLS * D, total, pred_proto);
     GFS_LAUNCH_OK("softmax_pool_reduce_kernel");
     return GFS_OK;
 }
@@ -298,7 +311,8 @@ extern "C" int gfs_refine_proto(const float* pred_proto, const float* proto, con
     GFS_REQUIRE(B > 0 && CLS > 0 && D > 0 && base_num >= 0 && base_num <= CLS, GFS_ERR_BAD_ARG,
                 "gfs_refine_proto: bad sizes (B=%d CLS=%d D=%d base_num=%d)", B, CLS, D, base_num);
     const int rows = B * CLS;
-    refine_proto_kernel<<<(rows + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(pred_proto, proto, gened_proto, rows, CLS, D,
+    launch_pdl(refine_proto_kernel, dim3((unsigned)((rows + 3) / 4)), dim3(128), 0, static_cast<cudaStream_t>(stream),
+        pred_proto, proto, gened_proto, rows, CLS, D,
                                                                                       base_num, refine_l2);
     GFS_LAUNCH_OK("refine_proto_kernel");
     return GFS_OK;

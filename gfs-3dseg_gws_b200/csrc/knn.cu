@@ -104,6 +104,7 @@ template <int LR>
 __global__ void __launch_bounds__(KNN_THREADS, 1)
 knn_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int k, const float* __restrict__ sqnorm,
            int32_t* __restrict__ idx_out, float* __restrict__ dist_out, const int* __restrict__ tile_flags) {
+    pdl_wait();
     // repair pass of knn_tc.cu: only the flagged 64-row tiles are redone
     if (tile_flags && tile_flags[blockIdx.y * gridDim.x + blockIdx.x] == 0) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -328,10 +329,12 @@ static int knn_exact_launch(const float* x, int64_t x_bstride, int B, int C, int
     const dim3 grid((N + T_ROWS - 1) / T_ROWS, B);
     if (k <= 32) {
         GFS_CUDA_OK(allow_smem(reinterpret_cast<const void*>(knn_kernel<1>), sizeof(KnnSmem) + 64 * T_ROWS * sizeof(float)));
-        knn_kernel<1><<<grid, KNN_THREADS, smem, st>>>(x, x_bstride, C, N, k, sqnorm, idx_out, dist_out, flags);
+        launch_pdl<2>(knn_kernel<1>, grid, dim3(KNN_THREADS), smem, st,
+        x, x_bstride, C, N, k, sqnorm, idx_out, dist_out, flags);
     } else {
         GFS_CUDA_OK(allow_smem(reinterpret_cast<const void*>(knn_kernel<2>), sizeof(KnnSmem) + 64 * T_ROWS * sizeof(float)));
-        knn_kernel<2><<<grid, KNN_THREADS, smem, st>>>(x, x_bstride, C, N, k, sqnorm, idx_out, dist_out, flags);
+        launch_pdl<2>(knn_kernel<2>, grid, dim3(KNN_THREADS), smem, st,
+        x, x_bstride, C, N, k, sqnorm, idx_out, dist_out, flags);
     }
     GFS_LAUNCH_OK("knn_kernel");
     return GFS_OK;

@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(KP_THREADS)
 knn_prep_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, int Npad, int Cp16, int KB, int CPT,
                 uint8_t* __restrict__ ops, float* __restrict__ xp, float* __restrict__ nh, float* __restrict__ nl,
                 uint32_t* __restrict__ tag, float* __restrict__ sqnorm) {
+    pdl_enter();
     __shared__ float xs[64 * KP_LD];
     __shared__ float mus[64];
     const int t = threadIdx.x, b = blockIdx.y;
@@ -222,6 +223,7 @@ __global__ void __launch_bounds__(KT_THREADS, 1)
 knn_tc_kernel(const uint8_t* __restrict__ ops, const float* __restrict__ nh, const float* __restrict__ nl,
               const uint32_t* __restrict__ tag, int* __restrict__ flags, int N, int Npad, int Cp16, int KB, int k,
               float* __restrict__ surv, int* __restrict__ surv_cnt, float* __restrict__ dbg) {
+    pdl_wait();
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     // [A: 2 row tiles x KB k-blocks x 16 KiB][B: KT_BST stages x KB x 8 KiB (64 candidate rows)][xch: 2 x NG/4 x 256 float4][ctl]
@@ -501,6 +503,7 @@ __global__ void __launch_bounds__(KF_WARPS * 32, CPT == 16 ? 5 : (SET ? 7 : 4))
 knn_finish_kernel(const float* __restrict__ xp, const float* __restrict__ sqnorm, const float* __restrict__ surv,
                   const int* __restrict__ surv_cnt, const uint32_t* __restrict__ tag, int N, int Npad, int k, int64_t rows,
                   int32_t* __restrict__ idx_out, float* __restrict__ dist_out) {
+    pdl_wait();
     constexpr int RS = CPT + 4;            // padded staging row: conflict-free LDS.128 across lanes
     constexpr int LPR = CPT / 4;           // lanes that fetch one row
     constexpr int RPI = 32 / LPR;          // rows per load instruction
@@ -741,7 +744,7 @@ template <int NG, int KS, bool ATM>
 static int kt_launch_filter_ks(const KtPlan& p, uint8_t* ws, int B, int N, int k, float* dbg, cudaStream_t st) {
     const size_t smem = (size_t)2 * p.KB * 16384 + (size_t)KT_BST * p.KB * 8192 + (size_t)2 * (NG / 4) * KT_ROWS * 16 + sizeof(KtCtl) + 1024;
     GFS_CUDA_OK(allow_smem(reinterpret_cast<const void*>(knn_tc_kernel<NG, KS, ATM>), smem));
-    knn_tc_kernel<NG, KS, ATM><<<dim3(p.Npad / KT_ROWS, B), KT_THREADS, smem, st>>>(
+    launch_pdl<2>(knn_tc_kernel<NG, KS, ATM>, dim3(p.Npad / KT_ROWS, B), dim3(KT_THREADS), smem, st,
         ws, reinterpret_cast<const float*>(ws + p.off_nh), reinterpret_cast<const float*>(ws + p.off_nl),
         reinterpret_cast<const uint32_t*>(ws + p.off_tag), reinterpret_cast<int*>(ws + p.off_flags), N, p.Npad, p.Cp16, p.KB, k,
         reinterpret_cast<float*>(ws + p.off_surv), reinterpret_cast<int*>(ws + p.off_cnt), dbg);
@@ -779,12 +782,14 @@ static int kt_launch_finish(const KtPlan& p, uint8_t* ws, const float* sqnorm, i
     if (p.CPT == 16) {
         const int64_t want = (rows + 7) / 8;
         const int grid = (int)(want < (int64_t)sms * 5 ? want : (int64_t)sms * 5);        // the resident CTAs, each strides over the rows
-        knn_finish_kernel<16, 8, SET><<<grid, 256, 0, st>>>(xp, sqnorm, surv, cnt, tag, N, p.Npad, k, rows, idx_out, dist_out);
+        launch_pdl<2>(knn_finish_kernel<16, 8, SET>, grid, dim3(256), 0, st,
+        xp, sqnorm, surv, cnt, tag, N, p.Npad, k, rows, idx_out, dist_out);
     } else {
         const int64_t want = (rows + 3) / 4;
         const int per_sm = SET ? 7 : 4;
         const int grid = (int)(want < (int64_t)sms * per_sm ? want : (int64_t)sms * per_sm);
-        knn_finish_kernel<64, 4, SET><<<grid, 128, 0, st>>>(xp, sqnorm, surv, cnt, tag, N, p.Npad, k, rows, idx_out, dist_out);
+        launch_pdl<2>(knn_finish_kernel<64, 4, SET>, grid, dim3(128), 0, st,
+        xp, sqnorm, surv, cnt, tag, N, p.Npad, k, rows, idx_out, dist_out);
     }
     GFS_LAUNCH_OK("knn_finish_kernel");
     return GFS_OK;
@@ -799,7 +804,8 @@ static int kt_chain(const float* x, int64_t x_bstride, int B, int C, int N, int 
                     float* dist_out, float* dbg, bool set_only, cudaStream_t st) {
     const KtPlan p = kt_plan(B, C, N);
     GFS_CUDA_OK(cudaMemsetAsync(ws + p.off_flags, 0, p.zero_bytes, st));
-    knn_prep_kernel<<<dim3(p.Npad / KP_PTS, B), KP_THREADS, 0, st>>>(x, x_bstride, C, N, p.Npad, p.Cp16, p.KB, p.CPT, ws,
+    launch_pdl<2>(knn_prep_kernel, dim3(p.Npad / KP_PTS, B), dim3(KP_THREADS), 0, st,
+        x, x_bstride, C, N, p.Npad, p.Cp16, p.KB, p.CPT, ws,
                                                            reinterpret_cast<float*>(ws + p.off_xp),
                                                            reinterpret_cast<float*>(ws + p.off_nh),
                                                            reinterpret_cast<float*>(ws + p.off_nl),
@@ -910,6 +916,7 @@ static int kt_run(const char* who, const float* x, int64_t x_bstride, int B, int
     // join even after a failed launch: a stream left forked would break an enclosing graph capture
     const cudaError_t e1 = cudaEventRecord(side->join, side->stream);
     const cudaError_t e2 = cudaStreamWaitEvent(st, side->join, 0);
+    pdl_break();
     if (rc != GFS_OK) return rc;
     if (rc2 != GFS_OK) return rc2;
     GFS_CUDA_OK(e1);

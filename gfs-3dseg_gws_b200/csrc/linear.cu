@@ -9,14 +9,16 @@
 // pipeline stage is two plain TMA bulk copies (cp.async.bulk, 16 KiB of X and NT*128 B of W) that land ready to be
 // consumed by tcgen05.mma -- no tensor maps, no software swizzle on the load side.
 //
-// Persistent CTA, 6 warps:  warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner), warps 2-5 = epilogue.
-// TMEM holds two accumulator stages of NT <= 256 fp32 columns, so the epilogue of work item i overlaps the MMAs of i+1.
+// Persistent CTA, 10 warps:  warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner), warps 2-5 and 6-9 = two epilogue
+// groups.  TMEM holds two accumulator stages of NT <= 256 fp32 columns; group g drains stage g (the CTA's even / odd work
+// items), so two items are in their epilogue at once (two warps per scheduler hide the TMEM-read and store latencies of
+// each other: one group left the issue slots 86 % idle) while the MMAs of the next item run.
 #include "common.cuh"
 
 namespace gfs {
 
 constexpr int LN_NST = 4;
-constexpr int LN_THREADS = 192;
+constexpr int LN_THREADS = 320;
 
 struct LnSmem {
     uint8_t X[LN_NST][16384];
@@ -30,6 +32,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1)
 linear_kernel(const uint8_t* __restrict__ x_act, int x_kblocks, int x_kb0, int kb_count, const uint8_t* __restrict__ wp,
               const float* __restrict__ shift, int Nout, int NT, int act, int N, int64_t M, int n_mtiles,
               uint8_t* __restrict__ y_act, int y_kblocks, int y_kb0, float* __restrict__ y_cm, int64_t y_bstride, int resident) {
+    pdl_enter();
     extern __shared__ unsigned char smem_raw[];
     // align inside the shared window with pointer arithmetic on smem_raw (keeps the .shared address space: LDS/STS, not generic LD/ST)
     LnSmem& s = *reinterpret_cast<LnSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
@@ -125,18 +128,20 @@ linear_kernel(const uint8_t* __restrict__ x_act, int x_kblocks, int x_kb0, int k
         // =============================== epilogue ===============================
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
-        const int et = tid - 64;   // 0..127
+        const int et = (tid - 64) & 127;   // 0..127 inside the group
         const uint32_t tlane = (uint32_t)(quarter * 32) << 16;
-        int acc = 0, aphase = 0;
+        const int acc = (warp - 2) >> 2;   // the group's accumulator stage
+        int aphase = 0;
         if (resident) {                                      // the N tile is fixed: its shifts are loaded once, not once per item
-            for (int c = et; c < NT; c += 128) s.shift[0][c] = s.shift[1][c] = shift ? shift[nt_res * NT + c] : 0.0f;
-            named_bar_sync(1, 128);
+            for (int c = et; c < NT; c += 128) s.shift[acc][c] = shift ? shift[nt_res * NT + c] : 0.0f;
+            named_bar_sync(1 + acc, 128);
         }
-        for (int it = it_first; it < it_end; it += it_step) {
+        for (int it = it_first + acc * it_step; it < it_end; it += 2 * it_step) {
             const int mt = resident ? it : it / n_ntiles, nt = resident ? nt_res : it - mt * n_ntiles;
             if (!resident) {
+                named_bar_sync(1 + acc, 128);          // the group's previous item has been read out before its shifts are replaced
                 for (int c = et; c < NT; c += 128) s.shift[acc][c] = shift ? shift[nt * NT + c] : 0.0f;
-                named_bar_sync(1, 128);
+                named_bar_sync(1 + acc, 128);
             }
             mbar_wait(&s.accf[acc], aphase);
             tc_fence_after();
@@ -191,10 +196,7 @@ linear_kernel(const uint8_t* __restrict__ x_act, int x_kblocks, int x_kb0, int k
             }
             tc_fence_before();
             mbar_arrive(&s.acce[acc]);
-            if (++acc == 2) {
-                acc = 0;
-                aphase ^= 1;
-            }
+            aphase ^= 1;
         }
     }
 
@@ -240,7 +242,7 @@ extern "C" int gfs_linear_bf16(const void* x_act, int x_kblocks, int x_kb0, int 
     // resident weights: the N tile's slice must fit the 128 KiB W area; the grid is a multiple of the N tiles so that a CTA's tile is fixed
     const int resident = ((size_t)kb_count * NT * 128 <= sizeof(LnSmem::W)) && grid >= n_ntiles;
     if (resident) grid -= grid % n_ntiles;
-    linear_kernel<<<grid, LN_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
+    launch_pdl(linear_kernel, grid, dim3(LN_THREADS), smem, static_cast<cudaStream_t>(stream),
         static_cast<const uint8_t*>(x_act), x_kblocks, x_kb0, kb_count, static_cast<const uint8_t*>(w_packed), shift, Nout, NT,
         act, N, M, n_mtiles, static_cast<uint8_t*>(y_act), y_kblocks, y_kb0, y_cm, y_bstride, resident);
     GFS_LAUNCH_OK("linear_kernel");

@@ -57,6 +57,7 @@ pointwise_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, con
 __global__ void __launch_bounds__(T_THREADS, 3)
 edge_pq_kernel(const float* __restrict__ x, int64_t bstride, int C, int N, const float* __restrict__ wt,
                const float* __restrict__ bias, __nv_bfloat16* __restrict__ pb, float* __restrict__ qo) {
+    pdl_enter();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* As = reinterpret_cast<float*>(smem_raw);   // [C][64]
     float* Bs = As + C * T_ROWS;                      // [C][128]
@@ -123,7 +124,7 @@ extern "C" int gfs_edge_pq_f32(const float* x, int64_t x_bstride, int B, int C, 
                 GFS_ERR_UNSUPPORTED, "gfs_edge_pq_f32: needs N %% 4 == 0 and 16-byte aligned pointers");
     const size_t smem = (size_t)C * (T_ROWS + T_COLS + 1) * sizeof(float);
     GFS_CUDA_OK(allow_smem(reinterpret_cast<const void*>(edge_pq_kernel), 64 * (T_ROWS + T_COLS + 1) * sizeof(float)));
-    edge_pq_kernel<<<dim3((N + T_ROWS - 1) / T_ROWS, B), T_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
+    launch_pdl(edge_pq_kernel, dim3((N + T_ROWS - 1) / T_ROWS, B), dim3(T_THREADS), smem, static_cast<cudaStream_t>(stream),
         x, x_bstride, C, N, wt, bias, static_cast<__nv_bfloat16*>(pb), q);
     GFS_LAUNCH_OK("edge_pq_kernel");
     return GFS_OK;

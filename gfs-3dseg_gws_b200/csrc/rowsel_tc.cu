@@ -49,6 +49,7 @@ enum { RT_GW = 0, RT_KMEANS = 1, RT_KMEANS_PM = 2 };   // _PM: points are rows o
 // dict_t (D, Gp) fp32 channel-major -> per 64-channel block: [hi tile | lo tile], 192 rows x 128 B, K-major SWIZZLE_128B.
 // Also the largest squared norm of an entry (k-means: scales the ambiguity bound).
 __global__ void rowsel_pack_kernel(const float* __restrict__ dict_t, int D, int G, int Gp, uint8_t* __restrict__ img) {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int chunks = D >> 3;
     if (i >= RT_N * chunks) return;
@@ -72,6 +73,7 @@ __global__ void rowsel_pack_kernel(const float* __restrict__ dict_t, int D, int 
 }
 // k-means: the largest squared norm of a centre scales the ambiguity bound; also clears the re-check counter
 __global__ void rowsel_cmax_kernel(const float* __restrict__ cnorm, int G, float* __restrict__ cmax2, int32_t* __restrict__ cnt) {
+    pdl_enter();
     float m = 0.0f;
     if (cnorm)
         for (int j = threadIdx.x; j < G; j += 32) m = fmaxf(m, cnorm[j]);
@@ -128,6 +130,7 @@ rowsel_tc_kernel(const float* __restrict__ x, int64_t bstride, int64_t cstride, 
                  const uint8_t* __restrict__ img, int G, int Gp, const float* __restrict__ cnorm, const float* __restrict__ cmax2,
                  uint8_t* __restrict__ cos_act, int kblocks, int kb0, float* __restrict__ cos_cm, int32_t* __restrict__ sel,
                  int32_t* __restrict__ recheck, int32_t* __restrict__ recheck_cnt) {
+    pdl_enter();
     extern __shared__ unsigned char smem_raw[];
     RtSmem& sm = *reinterpret_cast<RtSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -420,6 +423,7 @@ __global__ void __launch_bounds__(32 * RC_WARPS)
 rowsel_recheck_kernel(const float* __restrict__ x, int64_t bstride, int64_t cstride, int D, int N, const float* __restrict__ dict_t,
                       int G, int Gp, const float* __restrict__ cnorm, const int32_t* __restrict__ recheck,
                       const int32_t* __restrict__ recheck_cnt, int32_t* __restrict__ sel) {
+    pdl_enter();
     __shared__ float xs_all[RC_WARPS][256];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     float* xs = xs_all[wib];
@@ -530,9 +534,11 @@ static int rt_run(const char* who, const float* x, int64_t bstride, int64_t cstr
     int32_t* cnt = reinterpret_cast<int32_t*>(ws + p.off_cnt);
     int32_t* list = reinterpret_cast<int32_t*>(ws + p.off_list);
     const int pk = RT_N * (D >> 3);
-    rowsel_pack_kernel<<<(pk + 255) / 256, 256, 0, st>>>(dict_t, D, G, Gp, ws);
+    launch_pdl(rowsel_pack_kernel, dim3((unsigned)((pk + 255) / 256)), dim3(256), 0, st,
+        dict_t, D, G, Gp, ws);
     GFS_LAUNCH_OK("rowsel_pack_kernel");
-    rowsel_cmax_kernel<<<1, 32, 0, st>>>(MODE != RT_GW ? cnorm : nullptr, G, cmax2, cnt);
+    launch_pdl(rowsel_cmax_kernel, dim3((unsigned)(1)), dim3(32), 0, st,
+        MODE != RT_GW ? cnorm : nullptr, G, cmax2, cnt);
     GFS_LAUNCH_OK("rowsel_cmax_kernel");
     const int ntiles = (int)((M + RT_ROWS - 1) / RT_ROWS);
     const int sms = sm_count();
@@ -540,10 +546,11 @@ static int rt_run(const char* who, const float* x, int64_t bstride, int64_t cstr
     const size_t smem = offsetof(RtSmem, B) + (size_t)(D >> 6) * 2 * RT_BTILE + sizeof(RtCtl) + 1024;
     GFS_REQUIRE(smem <= 227 * 1024, GFS_ERR_UNSUPPORTED, "%s: D=%d: the resident dictionary does not fit shared memory (use the fp32 entry point)", who, D);
     GFS_CUDA_OK(allow_smem(reinterpret_cast<const void*>(rowsel_tc_kernel<MODE>), smem));
-    rowsel_tc_kernel<MODE><<<ntiles < sms ? ntiles : sms, RT_THREADS, smem, st>>>(
+    launch_pdl(rowsel_tc_kernel<MODE>, dim3((unsigned)(ntiles < sms ? ntiles : sms)), dim3(RT_THREADS), smem, st,
         x, bstride, cstride, D, N, M, ntiles, ws, G, Gp, cnorm, cmax2, static_cast<uint8_t*>(cos_act), kblocks, kb0, cos_cm, sel, list, cnt);
     GFS_LAUNCH_OK("rowsel_tc_kernel");
-    rowsel_recheck_kernel<MODE><<<sms * 2, 256, 0, st>>>(x, bstride, cstride, D, N, dict_t, G, Gp, cnorm, list, cnt, sel);
+    launch_pdl(rowsel_recheck_kernel<MODE>, dim3((unsigned)(sms * 2)), dim3(256), 0, st,
+        x, bstride, cstride, D, N, dict_t, G, Gp, cnorm, list, cnt, sel);
     GFS_LAUNCH_OK("rowsel_recheck_kernel");
     return GFS_OK;
 }

@@ -57,7 +57,7 @@ SIGNATURES = {
     "gfs_dropout_mask": [_i64, _i, _u32, _f, _p, _p],
 }
 UTILITIES = {"gfs_version": (_i, []), "gfs_last_error_string": (ctypes.c_char_p, []),
-             "gfs_device_sm_count": (_i, []), "gfs_kmeans_partials": (_i, []),
+             "gfs_device_sm_count": (_i, []), "gfs_set_pdl": (_i, [_i]), "gfs_kmeans_partials": (_i, []),
              "gfs_knn_tc_workspace_bytes": (_i64, [_i, _i, _i]),
              "gfs_knn_tc_chains": (_i, [_i, _i, _i]), "gfs_knn_tc_set_split": (_i, [_i]),
              "gfs_rowsel_tc_workspace_bytes": (_i64, [_i64, _i])}

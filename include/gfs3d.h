@@ -46,6 +46,12 @@ int gfs_version(void);
 const char* gfs_last_error_string(void);
 /* number of SMs of the current device (grid sizing of the persistent kernels); <0 on error */
 int gfs_device_sm_count(void);
+/* Programmatic dependent launch of the inference kernels (on by default; GFS3D_PDL=0 in the environment or
+ * gfs_set_pdl(0) turn it off): each kernel of a call chain may become resident while its predecessor on the stream
+ * drains and blocks in its first statement (griddepcontrol.wait) until the predecessor has completed, so the launch
+ * latency of ~45 kernels per forward pass (model/capl.py:170-192) overlaps the previous kernel's tail.  Stream
+ * semantics and results are unchanged; capturable into CUDA graphs.                                                */
+int gfs_set_pdl(int on);
 
 /* ---- kNN graph: model/dgcnn.py:17-23 (knn) -------------------------------------------------------------------
  * d(i,j) = -|x_i|^2 + 2 x_i.x_j - |x_j|^2 in fp32 with the pinned order of oracle/gfs_oracle.c; the k largest per
