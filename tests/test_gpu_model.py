@@ -292,3 +292,47 @@ def test_gw_projection_tensor_core_equals_fp32_kernel(B, N, G, kind):
     if kind != "zeros":
         assert rel_err(out["tc"][1], out["fp32"][1].double()) <= 1e-3
         assert rel_err(out["tc"][2], out["fp32"][2].double()) <= 8e-3
+
+
+def test_programmatic_dependent_launch_does_not_change_results(golden, golden_sd):
+    """gfs_set_pdl (include/gfs3d.h): the inference kernels launched with the programmatic-serialisation attribute (each
+    blocks in griddepcontrol.wait until its predecessor has completed) give bit-identical outputs to ordinary launches,
+    eagerly and replayed from a CUDA graph (where the dependencies become programmatic edges)."""
+    from gfs3d._lib import lib
+    from model.capl import mpti_net_Point_GeoAsWeight_v2
+    g = golden("gfs_s3dis_b2_n256")
+    t = lambda k: torch.from_numpy(g[k])
+    m = mpti_net_Point_GeoAsWeight_v2(classes=13, criterion=torch.nn.CrossEntropyLoss(ignore_index=255),
+                                      args=_args(eval_weight=float(g["eval_weight"])), base_num=7, gp=t("gp").cuda(), energy=0.9)
+    m.load_state_dict(golden_sd("gfs_s3dis_weights"), strict=True)
+    m = m.cuda().eval()
+    x = t("x").cuda().repeat(8, 1, 1)       # 16 blocks: enough CTAs for kernels to overlap their predecessors' tails
+    kw = dict(y=None, eval_model=True, gened_proto=t("gened_proto").cuda().unsqueeze(0).repeat(8, 1, 1),
+              base_class_coding=t("base_class_coding").cuda(), novel_class_coding=t("novel_class_coding").cuda())
+
+    def run():
+        with torch.no_grad():
+            return m(x=x, **kw)[0]
+
+    try:
+        assert lib().gfs_set_pdl(0) == 0
+        plain = run().clone()
+        for mode in (1, 2, 3):
+            assert lib().gfs_set_pdl(mode) == 0
+            for _ in range(3):
+                assert torch.equal(run(), plain), f"eager results differ with gfs_set_pdl({mode})"
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            run()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = run()
+        for _ in range(3):
+            out.zero_()
+            graph.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(out, plain), "graph replay with programmatic edges differs from ordinary launches"
+    finally:
+        lib().gfs_set_pdl(3)
