@@ -46,6 +46,9 @@ def test_error_convention_without_gpu():
     assert rc == 1 and b"exceeds N" in l.gfs_last_error_string()
     rc = l.gfs_linear_bf16(p, 3, 0, 3, p, None, 100, 1, 1, 128, p, 2, 0, None, 0, None)
     assert rc == 2 and b"multiple of 32" in l.gfs_last_error_string()
+    # launch-policy switches are host state only: callable without a device
+    assert l.gfs_set_pdl(0) == 0 and l.gfs_set_pdl(3) == 0
+    assert l.gfs_knn_tc_set_split(-1) == 0
 
 
 def test_product_path_has_no_cpu_fallback():
